@@ -1,0 +1,347 @@
+// extern "C" boundary of libzkp_b200.so (declared in include/zkp_b200.h).
+#include <string.h>
+
+#include "common.cuh"
+
+using namespace zkp;
+
+static_assert(sizeof(fr_t) == 32, "Fr is 4 x u64");
+static_assert(sizeof(fq_t) == 48, "Fq is 6 x u64");
+static_assert(sizeof(g1_affine) == 96, "G1 affine is 12 x u64");
+
+extern "C" {
+
+const char* zkp_strerror(int code) {
+    switch (code) {
+        case ZKP_OK: return "ok";
+        case ZKP_ERR_INVALID: return "invalid argument";
+        case ZKP_ERR_CUDA: return "CUDA failure";
+        case ZKP_ERR_DEGREE: return "polynomial degree exceeds the SRS";
+        case ZKP_ERR_NOMEM: return "out of memory";
+        case ZKP_ERR_STATE: return "prover round called out of order";
+        default: return "unknown error";
+    }
+}
+
+int zkp_ctx_create(int device, zkp_ctx** out) {
+    if (!out) return ZKP_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return ZKP_ERR_CUDA;
+    zkp_ctx* ctx = new zkp_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        prop.major < 10) {  // kernels are built for sm_100a only; no fallback
+        delete ctx;
+        return ZKP_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_start) != cudaSuccess || cudaEventCreate(&ctx->ev_stop) != cudaSuccess) {
+        delete ctx;
+        return ZKP_ERR_CUDA;
+    }
+    ctx->pinned_bytes = 1 << 16;
+    if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) {
+        delete ctx;
+        return ZKP_ERR_CUDA;
+    }
+    *out = ctx;
+    return ZKP_OK;
+}
+
+void zkp_ctx_destroy(zkp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ntt_free_domains(ctx);
+    msm_free(ctx);
+    for (auto& s : ctx->prof_spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaEventDestroy(ctx->ev_start);
+    cudaEventDestroy(ctx->ev_stop);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* zkp_last_error(const zkp_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int zkp_ctx_sync(zkp_ctx* ctx) {
+    if (!ctx) return ZKP_ERR_INVALID;
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKP_OK;
+}
+
+void* zkp_ctx_stream(zkp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int zkp_sm_count(const zkp_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t zkp_launch_count(const zkp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int zkp_timer_start(zkp_ctx* ctx) {
+    if (!ctx) return ZKP_ERR_INVALID;
+    ZKP_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    return ZKP_OK;
+}
+
+int zkp_timer_stop_ms(zkp_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return ZKP_ERR_INVALID;
+    ZKP_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+    ZKP_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop));
+    ZKP_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_stop));
+    return ZKP_OK;
+}
+
+int zkp_prof_enable(zkp_ctx* ctx, int on) {
+    if (!ctx) return ZKP_ERR_INVALID;
+    ctx->prof_on = on != 0;
+    return ZKP_OK;
+}
+
+int zkp_prof_reset(zkp_ctx* ctx) {
+    if (!ctx) return ZKP_ERR_INVALID;
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& s : ctx->prof_spans) { ctx->prof_pool.push_back(s.a); ctx->prof_pool.push_back(s.b); }
+    ctx->prof_spans.clear();
+    return ZKP_OK;
+}
+
+int zkp_prof_read(zkp_ctx* ctx, const char* name, float* total_ms, uint64_t* count) {
+    if (!ctx || !name || !total_ms || !count) return ZKP_ERR_INVALID;
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float tot = 0;
+    uint64_t n = 0;
+    for (auto& s : ctx->prof_spans) {
+        if (s.name != name) continue;
+        float ms = 0;
+        ZKP_CUDA(ctx, cudaEventElapsedTime(&ms, s.a, s.b));
+        tot += ms;
+        n++;
+    }
+    *total_ms = tot;
+    *count = n;
+    return ZKP_OK;
+}
+
+/* ---- buffers ---------------------------------------------------------------------- */
+int zkp_buf_alloc(zkp_ctx* ctx, size_t n, zkp_buf** out) {
+    if (!ctx || !out) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    zkp_buf* b = new zkp_buf();
+    b->n = n;
+    cudaError_t e = cudaMalloc(&b->d, (n ? n : 1) * sizeof(fr_t));
+    if (e != cudaSuccess) {
+        delete b;
+        cuda_fail(ctx, e, "cudaMalloc", __FILE__, __LINE__);
+        return e == cudaErrorMemoryAllocation ? ZKP_ERR_NOMEM : ZKP_ERR_CUDA;
+    }
+    *out = b;
+    return ZKP_OK;
+}
+
+int zkp_buf_free(zkp_ctx* ctx, zkp_buf* buf) {
+    if (!ctx || !buf) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZKP_CUDA(ctx, cudaFree(buf->d));
+    delete buf;
+    return ZKP_OK;
+}
+
+size_t zkp_buf_len(const zkp_buf* buf) { return buf ? buf->n : 0; }
+
+int zkp_buf_upload(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const uint64_t* src, size_t n) {
+    if (!ctx || !dst || (!src && n) || dst_off + n > dst->n) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    ZKP_CUDA(ctx, cudaMemcpyAsync(dst->d + dst_off, src, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKP_OK;
+}
+
+int zkp_buf_download(zkp_ctx* ctx, const zkp_buf* src, size_t src_off, uint64_t* dst, size_t n) {
+    if (!ctx || !src || (!dst && n) || src_off + n > src->n) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    ZKP_CUDA(ctx, cudaMemcpyAsync(dst, src->d + src_off, n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKP_OK;
+}
+
+int zkp_buf_zero(zkp_ctx* ctx, zkp_buf* buf, size_t off, size_t n) {
+    if (!ctx || !buf || off + n > buf->n) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    ZKP_CUDA(ctx, cudaMemsetAsync(buf->d + off, 0, n * sizeof(fr_t), ctx->stream));
+    return ZKP_OK;
+}
+
+int zkp_buf_copy(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const zkp_buf* src, size_t src_off, size_t n) {
+    if (!ctx || !dst || !src || dst_off + n > dst->n || src_off + n > src->n) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    ZKP_CUDA(ctx, cudaMemcpyAsync(dst->d + dst_off, src->d + src_off, n * sizeof(fr_t), cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+    return ZKP_OK;
+}
+
+/* ---- NTT -------------------------------------------------------------------------- */
+int zkp_ntt_dev_batch(zkp_ctx* ctx, const zkp_buf* in, size_t in_stride, size_t len_in, zkp_buf* out,
+                      size_t out_stride, unsigned k, int inverse, int coset, unsigned batch) {
+    if (!ctx || !in || !out || k > 28 || batch == 0) return ZKP_ERR_INVALID;
+    const size_t n = (size_t)1 << k;
+    if (len_in > n) return ZKP_ERR_INVALID;
+    if ((batch - 1) * in_stride + len_in > in->n || (batch - 1) * out_stride + n > out->n) return ZKP_ERR_INVALID;
+    if (batch > 1 && (in_stride < len_in || out_stride < n)) return ZKP_ERR_INVALID;
+    return ntt_run(ctx, in->d, in_stride, len_in, out->d, out_stride, k, inverse != 0, coset != 0, batch);
+}
+
+int zkp_ntt_dev(zkp_ctx* ctx, const zkp_buf* in, size_t len_in, zkp_buf* out, unsigned k, int inverse,
+                int coset) {
+    return zkp_ntt_dev_batch(ctx, in, 0, len_in, out, 0, k, inverse, coset, 1);
+}
+
+int zkp_ntt(zkp_ctx* ctx, uint64_t* data, size_t len_in, unsigned k, int inverse, int coset) {
+    if (!ctx || !data || k > 28) return ZKP_ERR_INVALID;
+    const size_t n = (size_t)1 << k;
+    if (len_in > n) return ZKP_ERR_INVALID;
+    zkp_buf* buf = nullptr;
+    int rc = zkp_buf_alloc(ctx, n, &buf);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(buf->d, data, len_in * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { zkp_buf_free(ctx, buf); return cuda_fail(ctx, e, "h2d", __FILE__, __LINE__); }
+    rc = ntt_run(ctx, buf->d, 0, len_in, buf->d, 0, k, inverse != 0, coset != 0, 1);
+    if (!rc) {
+        e = cudaMemcpyAsync(data, buf->d, n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "d2h", __FILE__, __LINE__);
+    }
+    zkp_buf_free(ctx, buf);
+    return rc;
+}
+
+int zkp_fft_constant(unsigned k, int kind, uint64_t out[4]) {
+    if (k > 32 || kind < 0 || kind > 4 || !out) return ZKP_ERR_INVALID;
+    fr_t v = fft_constant_host(k, kind);
+    memcpy(out, v.l, 32);
+    return ZKP_OK;
+}
+
+int zkp_fft_elements_dev(zkp_ctx* ctx, unsigned k, zkp_buf* out) {
+    if (!ctx || !out || k > 28 || out->n < ((size_t)1 << k)) return ZKP_ERR_INVALID;
+    return ntt_elements(ctx, k, out->d);
+}
+
+/* ---- SRS / MSM -------------------------------------------------------------------- */
+int zkp_srs_load(zkp_ctx* ctx, const uint64_t* xy, size_t n, zkp_srs** out) {
+    if (!ctx || !out || (!xy && n)) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    zkp_srs* s = new zkp_srs();
+    s->n = n;
+    cudaError_t e = cudaMalloc(&s->d, (n ? n : 1) * sizeof(g1_affine));
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(s->d, xy, n * sizeof(g1_affine), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        if (s->d) cudaFree(s->d);
+        delete s;
+        return cuda_fail(ctx, e, "srs upload", __FILE__, __LINE__);
+    }
+    *out = s;
+    return ZKP_OK;
+}
+
+int zkp_srs_generate(zkp_ctx* ctx, const uint64_t tau[4], size_t n, zkp_srs** out) {
+    if (!ctx || !out || !tau) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    zkp_srs* s = new zkp_srs();
+    s->n = n;
+    cudaError_t e = cudaMalloc(&s->d, (n ? n : 1) * sizeof(g1_affine));
+    if (e != cudaSuccess) { delete s; return cuda_fail(ctx, e, "cudaMalloc", __FILE__, __LINE__); }
+    fr_t t;
+    memcpy(t.l, tau, 32);
+    rc = srs_generate(ctx, t, n, s->d);
+    if (rc) { cudaFree(s->d); delete s; return rc; }
+    *out = s;
+    return ZKP_OK;
+}
+
+int zkp_srs_download(zkp_ctx* ctx, const zkp_srs* srs, size_t off, uint64_t* xy, size_t n) {
+    if (!ctx || !srs || (!xy && n) || off + n > srs->n) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    ZKP_CUDA(ctx, cudaMemcpyAsync(xy, srs->d + off, n * sizeof(g1_affine), cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKP_OK;
+}
+
+int zkp_srs_free(zkp_ctx* ctx, zkp_srs* srs) {
+    if (!ctx || !srs) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZKP_CUDA(ctx, cudaFree(srs->d));
+    delete srs;
+    return ZKP_OK;
+}
+
+size_t zkp_srs_len(const zkp_srs* srs) { return srs ? srs->n : 0; }
+
+int zkp_msm_set_window(zkp_ctx* ctx, unsigned c) {
+    if (!ctx || c > 20) return ZKP_ERR_INVALID;
+    ctx->msm_window = c;
+    return ZKP_OK;
+}
+
+int zkp_msm_g1_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* scalars, size_t off, size_t n,
+                   uint64_t out_xy[12]) {
+    if (!ctx || !srs || !scalars || !out_xy || off + n > scalars->n || n > srs->n) return ZKP_ERR_INVALID;
+    return msm_run(ctx, srs->d, scalars->d + off, n, reinterpret_cast<g1_affine*>(out_xy));
+}
+
+int zkp_commit_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* coeffs, size_t off, size_t n,
+                   uint64_t out_xy[12]) {
+    if (!ctx || !srs || !coeffs || !out_xy || off + n > coeffs->n) return ZKP_ERR_INVALID;
+    long long top = -1;
+    int rc = msm_highest_nonzero(ctx, coeffs->d + off, n, &top);
+    if (rc) return rc;
+    if (top >= (long long)srs->n) return ZKP_ERR_DEGREE;
+    return msm_run(ctx, srs->d, coeffs->d + off, (size_t)(top + 1), reinterpret_cast<g1_affine*>(out_xy));
+}
+
+static int with_uploaded(zkp_ctx* ctx, const uint64_t* scalars, size_t n, zkp_buf** out) {
+    int rc = zkp_buf_alloc(ctx, n, out);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync((*out)->d, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        zkp_buf_free(ctx, *out);
+        return cuda_fail(ctx, e, "h2d", __FILE__, __LINE__);
+    }
+    return ZKP_OK;
+}
+
+int zkp_msm_g1(zkp_ctx* ctx, const zkp_srs* srs, const uint64_t* scalars, size_t n, uint64_t out_xy[12]) {
+    if (!ctx || !srs || (!scalars && n) || !out_xy || n > srs->n) return ZKP_ERR_INVALID;
+    zkp_buf* b = nullptr;
+    int rc = with_uploaded(ctx, scalars, n, &b);
+    if (rc) return rc;
+    rc = zkp_msm_g1_dev(ctx, srs, b, 0, n, out_xy);
+    zkp_buf_free(ctx, b);
+    return rc;
+}
+
+int zkp_commit(zkp_ctx* ctx, const zkp_srs* srs, const uint64_t* coeffs, size_t n, uint64_t out_xy[12]) {
+    if (!ctx || !srs || (!coeffs && n) || !out_xy) return ZKP_ERR_INVALID;
+    zkp_buf* b = nullptr;
+    int rc = with_uploaded(ctx, coeffs, n, &b);
+    if (rc) return rc;
+    rc = zkp_commit_dev(ctx, srs, b, 0, n, out_xy);
+    zkp_buf_free(ctx, b);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// Shared runtime state behind the C ABI (include/zkp_b200.h): context, device buffers,
+// error plumbing and the launch counter bench.py reports as gpu_launches.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/zkp_b200.h"
+#include "arith.cuh"
+#include "g1.cuh"
+
+namespace zkp {
+
+struct NttDomain;  // ntt.cu
+struct MsmScratch; // msm.cu
+
+}  // namespace zkp
+
+struct zkp_buf {
+    zkp::fr_t* d = nullptr;
+    size_t n = 0;
+};
+
+struct zkp_srs {
+    zkp::g1_affine* d = nullptr;
+    size_t n = 0;
+};
+
+struct zkp_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    std::string last_error;
+    uint64_t launches = 0;
+    unsigned msm_window = 0;
+    std::map<unsigned, zkp::NttDomain*> domains;
+    zkp::fr_t* ntt_scratch = nullptr;
+    size_t ntt_scratch_n = 0;
+    zkp::MsmScratch* msm = nullptr;
+    void* pinned = nullptr;       // small pinned staging area for results
+    size_t pinned_bytes = 0;
+    // optional per-kernel timing (CUDA events on `stream`), read by bench.py for the roofline
+    bool prof_on = false;
+    struct ProfSpan { std::string name; cudaEvent_t a, b; };
+    std::vector<ProfSpan> prof_spans;
+    std::vector<cudaEvent_t> prof_pool;
+};
+
+namespace zkp {
+
+inline int cuda_fail(zkp_ctx* ctx, cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+    if (ctx) ctx->last_error = buf;
+    return ZKP_ERR_CUDA;
+}
+
+#define ZKP_CUDA(ctx, expr)                                                      \
+    do {                                                                         \
+        cudaError_t _e = (expr);                                                 \
+        if (_e != cudaSuccess) return zkp::cuda_fail(ctx, _e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// Launch check: counts the launch and surfaces configuration errors immediately.
+#define ZKP_LAUNCHED(ctx)                                                        \
+    do {                                                                         \
+        (ctx)->launches++;                                                       \
+        cudaError_t _e = cudaGetLastError();                                     \
+        if (_e != cudaSuccess) return zkp::cuda_fail(ctx, _e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+// RAII span: records an event pair around the launches issued in its scope when profiling
+// is enabled (zkp_prof_enable); otherwise free.
+struct ProfScope {
+    zkp_ctx* ctx; int idx = -1;
+    ProfScope(zkp_ctx* c, const char* name) : ctx(c) {
+        if (!c->prof_on) return;
+        cudaEvent_t a, b;
+        auto get = [&](cudaEvent_t* e) {
+            if (!c->prof_pool.empty()) { *e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+            else cudaEventCreate(e);
+        };
+        get(&a); get(&b);
+        cudaEventRecord(a, c->stream);
+        c->prof_spans.push_back({name, a, b});
+        idx = (int)c->prof_spans.size() - 1;
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(ctx->prof_spans[idx].b, ctx->stream); }
+};
+
+inline int set_device(zkp_ctx* ctx) {
+    ZKP_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ZKP_OK;
+}
+
+// ntt.cu
+int ntt_run(zkp_ctx* ctx, const fr_t* in, size_t in_stride, size_t len_in, fr_t* out,
+            size_t out_stride, unsigned k, bool inverse, bool coset, unsigned batch);
+void ntt_free_domains(zkp_ctx* ctx);
+int ntt_elements(zkp_ctx* ctx, unsigned k, fr_t* out);
+fr_t fft_constant_host(unsigned k, int kind);
+
+// msm.cu
+int msm_run(zkp_ctx* ctx, const g1_affine* bases, const fr_t* scalars_dev, size_t n,
+            g1_affine* out_host);
+int msm_highest_nonzero(zkp_ctx* ctx, const fr_t* scalars_dev, size_t n, long long* out);
+int srs_generate(zkp_ctx* ctx, const fr_t& tau, size_t n, g1_affine* out_dev);
+void msm_free(zkp_ctx* ctx);
+
+}  // namespace zkp

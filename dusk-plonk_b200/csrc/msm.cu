@@ -1,0 +1,439 @@
+// G1 multi-scalar multiplication (Pippenger bucket method) for sm_100a.
+//
+// Replaces poly_commit::msm_curve_addition / PlonkParams::commit (call sites
+// src/prover.rs:133-136,194,262-265,440,452; src/key.rs:138-159; src/prover/proof.rs:507-526):
+// sum_i s_i * P_i over BLS12-381 G1, returned in affine form (Commitment::new).
+//
+// Pipeline (all on the device, one stream):
+//   1. msm_digits_kernel   Fr Montgomery -> canonical, signed c-bit digits
+//                          d in [-2^(c-1), 2^(c-1)], histogram of |d| per window
+//   2. msm_scan_kernel     exclusive scan of the W * 2^(c-1) bucket counts
+//   3. msm_scatter_kernel  counting-sort of (point index, sign) by (window, bucket)
+//   4. msm_accumulate_kernel  one thread per bucket, XYZZ mixed additions (8M + 2S each,
+//                          384-bit Montgomery on the integer pipe) -- the hot kernel
+//   5. msm_bucket_reduce_kernel + msm_tree_reduce_kernel  sum_b (b+1) * B[w][b] per window
+//   6. msm_window_combine_kernel  Horner over the windows, one Fermat inversion -> affine
+// Addition in G1 is commutative and the result is normalised to affine, so the output is
+// bit-identical to any correct CPU evaluation regardless of accumulation order.
+#include "common.cuh"
+
+namespace zkp {
+
+struct MsmScratch {
+    size_t cap_n = 0, cap_entries = 0, cap_buckets = 0, cap_partials = 0;
+    uint32_t* digits = nullptr;   // [W][n]   bucket | sign << 31, 0xffffffff = zero digit
+    uint32_t* sorted = nullptr;   // [W * n]  point index | sign << 31, grouped by bucket
+    uint32_t* counts = nullptr;   // [W * B]
+    uint32_t* offsets = nullptr;  // [W * B]
+    uint32_t* cursor = nullptr;   // [W * B]
+    g1_xyzz* buckets = nullptr;   // [W * B]
+    g1_xyzz* part_a = nullptr;    // reduction ping-pong
+    g1_xyzz* part_b = nullptr;
+    g1_affine* result = nullptr;
+    long long* top = nullptr;
+};
+
+static constexpr uint32_t DIGIT_ZERO = 0xffffffffu;
+
+__device__ __forceinline__ fr_t msm_ld_fr(const fr_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    fr_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+
+__device__ __forceinline__ g1_affine msm_ld_affine(const g1_affine* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    g1_affine r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        uint4 v = __ldg(q + i);
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+    return r;
+}
+
+// bits [pos, pos+c) of a 256-bit little-endian value (c <= 24)
+__device__ __forceinline__ uint32_t window_bits(const fr_t& s, unsigned pos, unsigned c) {
+    const unsigned limb = pos >> 5, off = pos & 31;
+    if (limb >= 8) return 0;
+    uint64_t v = s.l[limb];
+    if (limb + 1 < 8) v |= (uint64_t)s.l[limb + 1] << 32;
+    return (uint32_t)(v >> off) & ((1u << c) - 1);
+}
+
+__global__ void msm_digits_kernel(const fr_t* scalars, size_t n, unsigned c, unsigned W,
+                                  uint32_t* digits, uint32_t* counts) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fr_t s = from_mont(msm_ld_fr(scalars + i));
+    const uint32_t B = 1u << (c - 1);
+    uint32_t carry = 0;
+    for (unsigned w = 0; w < W; w++) {
+        uint32_t d = window_bits(s, w * c, c) + carry;
+        uint32_t enc;
+        if (d > B) {  // represent as d - 2^c (negative or zero), carry into the next window
+            const uint32_t m = (1u << c) - d;  // |d - 2^c| in [0, B-1]
+            enc = m ? ((m - 1) | 0x80000000u) : DIGIT_ZERO;
+            carry = 1;
+        } else {
+            carry = 0;
+            enc = d ? (d - 1) : DIGIT_ZERO;
+        }
+        digits[(size_t)w * n + i] = enc;
+        if (enc != DIGIT_ZERO) atomicAdd(&counts[(size_t)w * B + (enc & 0x7fffffffu)], 1u);
+    }
+}
+
+// Single-block exclusive scan over m counters (m up to a few million).
+__global__ void msm_scan_kernel(const uint32_t* counts, uint32_t* offsets, uint32_t* cursor, size_t m) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t total_before;
+    const unsigned T = blockDim.x, tid = threadIdx.x;
+    const size_t per = (m + T - 1) / T;
+    const size_t lo = (size_t)tid * per, hi = lo + per < m ? lo + per : m;
+    uint32_t sum = 0;
+    for (size_t i = lo; i < hi; i++) sum += counts[i];
+    // block-wide exclusive scan of the per-thread sums
+    uint32_t incl = sum;
+    const unsigned lane = tid & 31, wid = tid >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += v;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    if (tid == 0) total_before = 0;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = lane < (T >> 5) ? warp_sums[lane] : 0;
+        uint32_t wincl = ws;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, wincl, o);
+            if (lane >= (unsigned)o) wincl += v;
+        }
+        warp_sums[lane] = wincl - ws;  // exclusive
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[wid] + (incl - sum);
+    for (size_t i = lo; i < hi; i++) {
+        offsets[i] = run;
+        cursor[i] = run;
+        run += counts[i];
+    }
+}
+
+__global__ void msm_scatter_kernel(const uint32_t* digits, size_t n, unsigned c, unsigned W,
+                                   uint32_t* cursor, uint32_t* sorted) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t B = 1u << (c - 1);
+    for (unsigned w = 0; w < W; w++) {
+        const uint32_t enc = digits[(size_t)w * n + i];
+        if (enc == DIGIT_ZERO) continue;
+        const uint32_t pos = atomicAdd(&cursor[(size_t)w * B + (enc & 0x7fffffffu)], 1u);
+        sorted[pos] = (uint32_t)i | (enc & 0x80000000u);
+    }
+}
+
+// One thread per (window, bucket): sum of +-P over the bucket's sorted entries.
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1_affine* bases, const uint32_t* sorted,
+                                                            const uint32_t* offsets, const uint32_t* counts,
+                                                            size_t nbuckets, g1_xyzz* buckets) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nbuckets) return;
+    const uint32_t off = offsets[g], cnt = counts[g];
+    g1_xyzz acc = g1_xyzz::inf();
+    for (uint32_t j = 0; j < cnt; j++) {
+        const uint32_t e = sorted[off + j];
+        g1_affine q = msm_ld_affine(bases + (e & 0x7fffffffu));
+        if (e & 0x80000000u) q.y = neg(q.y);
+        xyzz_madd(acc, q);
+    }
+    buckets[g] = acc;
+}
+
+// acc <- k * acc for a small scalar k (double-and-add)
+__device__ void xyzz_mul_small(g1_xyzz& acc, uint32_t k) {
+    g1_xyzz base = acc;
+    acc = g1_xyzz::inf();
+    if (k == 0) return;
+    for (int bit = 31 - __clz(k); bit >= 0; bit--) {
+        xyzz_dbl(acc);
+        if ((k >> bit) & 1) xyzz_add(acc, base);
+    }
+}
+
+// Each thread owns `seg` consecutive buckets of one window and emits
+//   sum_{b in segment} (b + 1) * B[w][b]
+// as a running-sum (weights 1..seg) plus seg_lo * (plain sum).
+__global__ void __launch_bounds__(64) msm_bucket_reduce_kernel(const g1_xyzz* buckets, uint32_t B, uint32_t seg,
+                                                              uint32_t nseg, unsigned W, g1_xyzz* parts) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nseg * W) return;
+    const uint32_t w = (uint32_t)(t / nseg), sidx = (uint32_t)(t % nseg);
+    const uint32_t lo = sidx * seg;
+    const uint32_t hi = lo + seg < B ? lo + seg : B;
+    const g1_xyzz* bw = buckets + (size_t)w * B;
+    g1_xyzz run = g1_xyzz::inf(), sum = g1_xyzz::inf();
+    for (uint32_t b = hi; b-- > lo;) {
+        xyzz_add(run, bw[b]);
+        xyzz_add(sum, run);
+    }
+    xyzz_mul_small(run, lo);
+    xyzz_add(sum, run);
+    parts[t] = sum;
+}
+
+// Sums groups of up to blockDim.x partial points: in[w][0..n_in) -> out[w][0..ceil(n_in/blockDim))
+__global__ void __launch_bounds__(128) msm_tree_reduce_kernel(const g1_xyzz* in, uint32_t n_in, g1_xyzz* out,
+                                                             uint32_t n_out) {
+    extern __shared__ uint4 smem_raw[];
+    g1_xyzz* sm = reinterpret_cast<g1_xyzz*>(smem_raw);
+    const unsigned tid = threadIdx.x, w = blockIdx.y;
+    const uint32_t idx = blockIdx.x * blockDim.x + tid;
+    g1_xyzz v = idx < n_in ? in[(size_t)w * n_in + idx] : g1_xyzz::inf();
+    sm[tid] = v;
+    __syncthreads();
+    for (unsigned s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (tid < s) {
+            g1_xyzz o = sm[tid + s];
+            xyzz_add(v, o);
+            sm[tid] = v;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) out[(size_t)w * n_out + blockIdx.x] = v;
+}
+
+// result = sum_w 2^(c w) * R[w], normalised to affine.
+__global__ void msm_window_combine_kernel(const g1_xyzz* win, unsigned W, unsigned c, g1_affine* result) {
+    g1_xyzz acc = win[W - 1];
+    for (int w = (int)W - 2; w >= 0; w--) {
+        for (unsigned i = 0; i < c; i++) xyzz_dbl(acc);
+        xyzz_add(acc, win[w]);
+    }
+    *result = xyzz_to_affine(acc);
+}
+
+__global__ void msm_top_nonzero_kernel(const fr_t* scalars, size_t n, long long* top) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* q = reinterpret_cast<const uint4*>(scalars + i);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    if (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) atomicMax(top, (long long)i);
+}
+
+// ------------------------------------------------------------------ SRS generation
+// tbl[w][d-1] = d * 2^(8w) * G, affine; 32 windows x 255 entries.
+static constexpr unsigned FB_W = 32, FB_D = 255;
+
+__device__ __forceinline__ g1_affine g1_generator() {
+    // canonical coordinates of the standard BLS12-381 G1 generator
+    const uint32_t gx[12] = {0xdb22c6bbu, 0xfb3af00au, 0xf97a1aefu, 0x6c55e83fu, 0x171bac58u, 0xa14e3a3fu,
+                             0x9774b905u, 0xc3688c4fu, 0x4fa9ac0fu, 0x2695638cu, 0x3197d794u, 0x17f1d3a7u};
+    const uint32_t gy[12] = {0x46c5e7e1u, 0x0caa2329u, 0xa2888ae4u, 0xd03cc744u, 0x2c04b3edu, 0x00db18cbu,
+                             0xd5d00af6u, 0xfcf5e095u, 0x741d8ae4u, 0xa09e30edu, 0xe3aaa0f1u, 0x08b3f481u};
+    g1_affine g;
+    fq_t x, y;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { x.l[i] = gx[i]; y.l[i] = gy[i]; }
+    g.x = to_mont(x);
+    g.y = to_mont(y);
+    return g;
+}
+
+__global__ void srs_table_kernel(g1_affine* tbl) {
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= FB_W) return;
+    g1_affine g = g1_generator();
+    g1_xyzz base = g1_xyzz::inf();
+    xyzz_madd(base, g);
+    for (unsigned i = 0; i < 8 * w; i++) xyzz_dbl(base);
+    g1_xyzz acc = g1_xyzz::inf();
+    for (unsigned d = 0; d < FB_D; d++) {
+        xyzz_add(acc, base);
+        tbl[w * FB_D + d] = xyzz_to_affine(acc);
+    }
+}
+
+__global__ void __launch_bounds__(128) srs_powers_kernel(const g1_affine* tbl, fr_t tau, size_t n, g1_affine* out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fr_t s = from_mont(pow_u64(tau, (uint64_t)i));
+    g1_xyzz acc = g1_xyzz::inf();
+    for (unsigned w = 0; w < FB_W; w++) {
+        const uint32_t d = (s.l[w >> 2] >> (8 * (w & 3))) & 255u;
+        if (d) xyzz_madd(acc, msm_ld_affine(tbl + w * FB_D + d - 1));
+    }
+    out[i] = xyzz_to_affine(acc);
+}
+
+int srs_generate(zkp_ctx* ctx, const fr_t& tau, size_t n, g1_affine* out_dev) {
+    g1_affine* tbl = nullptr;
+    ZKP_CUDA(ctx, cudaMalloc(&tbl, sizeof(g1_affine) * FB_W * FB_D));
+    srs_table_kernel<<<1, 32, 0, ctx->stream>>>(tbl);
+    ZKP_LAUNCHED(ctx);
+    if (n) {
+        srs_powers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(tbl, tau, n, out_dev);
+        ZKP_LAUNCHED(ctx);
+    }
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZKP_CUDA(ctx, cudaFree(tbl));
+    return ZKP_OK;
+}
+
+// ------------------------------------------------------------------ host driver
+static unsigned choose_window(size_t n) {
+    // minimise (bucket additions) + (bucket-reduce additions, weighted for their lower
+    // parallel efficiency)
+    unsigned best = 4;
+    double best_cost = 1e300;
+    for (unsigned c = 4; c <= 18; c++) {
+        const unsigned W = 255 / c + 1;
+        const double cost = (double)n * W + 4.0 * W * (double)(1u << (c - 1));
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+}
+
+template <class T>
+static int ensure(zkp_ctx* ctx, T** p, size_t* cap, size_t need) {
+    if (*cap >= need) return ZKP_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    ZKP_CUDA(ctx, cudaMalloc(p, need * sizeof(T)));
+    *cap = need;
+    return ZKP_OK;
+}
+
+static int msm_scratch(zkp_ctx* ctx, MsmScratch** out) {
+    if (!ctx->msm) {
+        ctx->msm = new MsmScratch();
+        ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->result, sizeof(g1_affine)));
+        ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->top, sizeof(long long)));
+    }
+    *out = ctx->msm;
+    return ZKP_OK;
+}
+
+void msm_free(zkp_ctx* ctx) {
+    MsmScratch* s = ctx->msm;
+    if (!s) return;
+    cudaFree(s->digits); cudaFree(s->sorted); cudaFree(s->counts); cudaFree(s->offsets); cudaFree(s->cursor);
+    cudaFree(s->buckets); cudaFree(s->part_a); cudaFree(s->part_b); cudaFree(s->result); cudaFree(s->top);
+    delete s;
+    ctx->msm = nullptr;
+}
+
+int msm_highest_nonzero(zkp_ctx* ctx, const fr_t* scalars_dev, size_t n, long long* out) {
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    MsmScratch* s;
+    if ((rc = msm_scratch(ctx, &s))) return rc;
+    long long* h = reinterpret_cast<long long*>(ctx->pinned);
+    *h = -1;
+    ZKP_CUDA(ctx, cudaMemcpyAsync(s->top, h, sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    if (n) {
+        msm_top_nonzero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(scalars_dev, n, s->top);
+        ZKP_LAUNCHED(ctx);
+    }
+    ZKP_CUDA(ctx, cudaMemcpyAsync(h, s->top, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = *h;
+    return ZKP_OK;
+}
+
+int msm_run(zkp_ctx* ctx, const g1_affine* bases, const fr_t* scalars_dev, size_t n, g1_affine* out_host) {
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    if (n == 0) {
+        memset(out_host, 0, sizeof(g1_affine));
+        return ZKP_OK;
+    }
+    if (n >= (1ull << 31)) return ZKP_ERR_INVALID;
+    MsmScratch* s;
+    if ((rc = msm_scratch(ctx, &s))) return rc;
+
+    const unsigned c = ctx->msm_window ? (ctx->msm_window < 2 ? 2 : ctx->msm_window) : choose_window(n);
+    const unsigned W = 255 / c + 1;
+    const uint32_t B = 1u << (c - 1);
+    const size_t nb = (size_t)W * B;
+    const uint32_t seg = B < 16 ? B : 16;
+    const uint32_t nseg = B / seg;
+
+    if ((rc = ensure(ctx, &s->digits, &s->cap_n, (size_t)W * n))) return rc;
+    if ((rc = ensure(ctx, &s->sorted, &s->cap_entries, (size_t)W * n))) return rc;
+    {
+        size_t cap = s->cap_buckets;
+        if (cap < nb) {
+            size_t c1 = cap, c2 = cap, c3 = cap, c4 = cap;
+            if ((rc = ensure(ctx, &s->counts, &c1, nb))) return rc;
+            if ((rc = ensure(ctx, &s->offsets, &c2, nb))) return rc;
+            if ((rc = ensure(ctx, &s->cursor, &c3, nb))) return rc;
+            if ((rc = ensure(ctx, &s->buckets, &c4, nb))) return rc;
+            s->cap_buckets = nb;
+        }
+    }
+    {
+        const size_t need = (size_t)W * nseg;
+        size_t cap = s->cap_partials;
+        if (cap < need) {
+            size_t c1 = cap, c2 = cap;
+            if ((rc = ensure(ctx, &s->part_a, &c1, need))) return rc;
+            if ((rc = ensure(ctx, &s->part_b, &c2, need))) return rc;
+            s->cap_partials = need;
+        }
+    }
+
+    cudaStream_t st = ctx->stream;
+    {
+    ProfScope prof(ctx, "msm_sort");
+    ZKP_CUDA(ctx, cudaMemsetAsync(s->counts, 0, nb * sizeof(uint32_t), st));
+    msm_digits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scalars_dev, n, c, W, s->digits, s->counts);
+    ZKP_LAUNCHED(ctx);
+    msm_scan_kernel<<<1, 1024, 0, st>>>(s->counts, s->offsets, s->cursor, nb);
+    ZKP_LAUNCHED(ctx);
+    msm_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->digits, n, c, W, s->cursor, s->sorted);
+    ZKP_LAUNCHED(ctx);
+    }
+    {
+    ProfScope prof(ctx, "msm_accumulate");
+    msm_accumulate_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(bases, s->sorted, s->offsets, s->counts, nb,
+                                                                        s->buckets);
+    ZKP_LAUNCHED(ctx);
+    }
+    g1_xyzz* cur = s->part_a;
+    g1_xyzz* nxt = s->part_b;
+    {
+    ProfScope prof(ctx, "msm_reduce");
+    {
+        const size_t t = (size_t)nseg * W;
+        msm_bucket_reduce_kernel<<<(unsigned)((t + 63) / 64), 64, 0, st>>>(s->buckets, B, seg, nseg, W, s->part_a);
+        ZKP_LAUNCHED(ctx);
+    }
+    uint32_t n_in = nseg;
+    while (n_in > 1) {
+        const uint32_t n_out = (n_in + 127) / 128;
+        dim3 grid(n_out, W);
+        msm_tree_reduce_kernel<<<grid, 128, 128 * sizeof(g1_xyzz), st>>>(cur, n_in, nxt, n_out);
+        ZKP_LAUNCHED(ctx);
+        g1_xyzz* t = cur; cur = nxt; nxt = t;
+        n_in = n_out;
+    }
+    }
+    {
+    ProfScope prof(ctx, "msm_combine");
+    msm_window_combine_kernel<<<1, 1, 0, st>>>(cur, W, c, s->result);
+    ZKP_LAUNCHED(ctx);
+    }
+    g1_affine* h = reinterpret_cast<g1_affine*>(ctx->pinned);
+    ZKP_CUDA(ctx, cudaMemcpyAsync(h, s->result, sizeof(g1_affine), cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(out_host, h, sizeof(g1_affine));
+    return ZKP_OK;
+}
+
+}  // namespace zkp

@@ -1,0 +1,359 @@
+// Radix-2 NTT / iNTT / coset NTT over BLS12-381 Fr for sm_100a.
+//
+// Replaces poly_commit::Fft::{new,dft,idft,coset_dft,coset_idft} as the reference calls
+// them (src/prover.rs:87-88,121-124,192,229; src/prover/quotient_poly.rs:50-58,115,145,237;
+// src/key.rs:83,121-131,222-245; src/permutation.rs:194-197,229-235): by-value transforms,
+// short inputs zero-padded, natural-order output, coset shift g = 7, n^-1 on the inverse.
+//
+// Design (not a translation of the CPU recursion):
+//  * log2(N) radix-2 decimation-in-frequency stages are grouped into P passes over HBM.
+//    Pass i owns a "digit" of s_i index bits; a thread block stages a tile of
+//    2^s_i (digit) x 2^c (neighbouring columns, for 128-byte coalescing) elements in
+//    shared memory, runs s_i butterfly stages there, and writes the tile back.
+//  * Every butterfly costs exactly one Montgomery multiplication: the twiddle of stage t
+//    is read from a per-domain table w^j (j < N/2) precomputed in HBM, so there are no
+//    separate inter-pass twiddle multiplies (the classical four-step penalty).
+//  * Passes 1..P-1 are index-preserving (tile in, tile out); the last pass scatters each
+//    tile to the digit-reversed address, which makes the overall transform
+//    natural-order -> natural-order with no bit-reversal pass.  The scatter stays
+//    128-byte coalesced because the tile's column bits are the low bits of the *first*
+//    digit, i.e. the low bits of the output index.
+//  * iNTT uses the same table: w^-j = -w^(N/2-j), folded into the butterfly as (v-u).
+//  * Zero padding is applied on load; coset scaling (g^i on input of the forward
+//    transform, g^-i n^-1 on output of the inverse) is fused into the first / last pass
+//    through two-level power tables (g^i = lo[i & 1023] * hi[i >> 10]).
+#include "common.cuh"
+
+namespace zkp {
+
+static constexpr unsigned S_MAX = 8;    // digit bits per pass
+static constexpr unsigned C_LOG = 2;    // 4 columns x 32 B = 128 B segments
+static constexpr unsigned LOG_LO = 10;  // low table of the two-level coset powers
+
+struct NttDomain {
+    unsigned k = 0;
+    fr_t* tw = nullptr;     // w^j, j < max(1, N/2)
+    fr_t* g_lo = nullptr;   // g^i,            i < 2^min(k,10)
+    fr_t* g_hi = nullptr;   // g^(i << 10),    i < 2^(k-10)       (k > 10)
+    fr_t* gi_lo = nullptr;  // n^-1 g^-i,      i < 2^min(k,10)
+    fr_t* gi_hi = nullptr;  // g^-(i << 10)
+    fr_t n_inv;
+};
+
+// ------------------------------------------------------------------ host-side constants
+static fr_t host_root_of_unity() {
+    // 7^((r-1)/2^32), canonical limbs (zkstd FftField::ROOT_OF_UNITY)
+    fr_t raw;
+    const uint32_t t[8] = {0x439f0d2bu, 0x3829971fu, 0x8c2280b9u, 0xb6368350u,
+                           0x22c813b4u, 0xd09b6819u, 0xdfe81f20u, 0x16a2a19eu};
+    for (int i = 0; i < 8; i++) raw.l[i] = t[i];
+    return to_mont(raw);
+}
+
+fr_t fft_constant_host(unsigned k, int kind) {
+    switch (kind) {
+        case 0:
+        case 1: {
+            fr_t w = host_root_of_unity();
+            for (unsigned i = k; i < 32; i++) w = sqr(w);
+            return kind == 0 ? w : inverse(w);
+        }
+        case 2: return inverse(from_u64<FrParams>(1ull << k));
+        case 3: return from_u64<FrParams>(7);
+        default: return inverse(from_u64<FrParams>(7));
+    }
+}
+
+// out[i] = first * base^i
+__global__ void geometric_table_kernel(fr_t* out, size_t n, fr_t base, fr_t first) {
+    constexpr unsigned B = 16;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = t * B;
+    if (lo >= n) return;
+    fr_t v = first * pow_u64(base, lo);
+    for (unsigned i = 0; i < B && lo + i < n; i++) {
+        out[lo + i] = v;
+        v = v * base;
+    }
+}
+
+static int build_table(zkp_ctx* ctx, fr_t** out, size_t n, const fr_t& base, const fr_t& first) {
+    ZKP_CUDA(ctx, cudaMalloc(out, n * sizeof(fr_t)));
+    size_t threads = (n + 15) / 16;
+    unsigned block = 128;
+    geometric_table_kernel<<<(unsigned)((threads + block - 1) / block), block, 0, ctx->stream>>>(
+        *out, n, base, first);
+    ZKP_LAUNCHED(ctx);
+    return ZKP_OK;
+}
+
+static int get_domain(zkp_ctx* ctx, unsigned k, NttDomain** out) {
+    auto it = ctx->domains.find(k);
+    if (it != ctx->domains.end()) { *out = it->second; return ZKP_OK; }
+    NttDomain* d = new NttDomain();
+    d->k = k;
+    const size_t n = (size_t)1 << k;
+    fr_t w = fft_constant_host(k, 0);
+    fr_t g = fft_constant_host(k, 3), gi = fft_constant_host(k, 4);
+    d->n_inv = fft_constant_host(k, 2);
+    int rc;
+    if ((rc = build_table(ctx, &d->tw, n > 1 ? n / 2 : 1, w, fr_t::one()))) return rc;
+    const size_t nlo = (size_t)1 << (k < LOG_LO ? k : LOG_LO);
+    if ((rc = build_table(ctx, &d->g_lo, nlo, g, fr_t::one()))) return rc;
+    if ((rc = build_table(ctx, &d->gi_lo, nlo, gi, d->n_inv))) return rc;
+    if (k > LOG_LO) {
+        const size_t nhi = (size_t)1 << (k - LOG_LO);
+        if ((rc = build_table(ctx, &d->g_hi, nhi, pow_u64(g, 1ull << LOG_LO), fr_t::one()))) return rc;
+        if ((rc = build_table(ctx, &d->gi_hi, nhi, pow_u64(gi, 1ull << LOG_LO), fr_t::one()))) return rc;
+    }
+    ctx->domains[k] = d;
+    *out = d;
+    return ZKP_OK;
+}
+
+void ntt_free_domains(zkp_ctx* ctx) {
+    for (auto& kv : ctx->domains) {
+        NttDomain* d = kv.second;
+        cudaFree(d->tw); cudaFree(d->g_lo); cudaFree(d->g_hi); cudaFree(d->gi_lo); cudaFree(d->gi_hi);
+        delete d;
+    }
+    ctx->domains.clear();
+    if (ctx->ntt_scratch) cudaFree(ctx->ntt_scratch);
+    ctx->ntt_scratch = nullptr;
+    ctx->ntt_scratch_n = 0;
+}
+
+// ------------------------------------------------------------------ the pass kernel
+struct PassParams {
+    const fr_t* in;
+    fr_t* out;
+    size_t in_stride, out_stride, len_in;
+    const fr_t* tw;
+    const fr_t* sc_lo;
+    const fr_t* sc_hi;
+    fr_t n_inv;
+    unsigned k, lo, s, c_log, cpos, tw_shift;
+    unsigned ndig, dig[6];
+    int last, inverse;
+    int scale_in;   // forward coset: a_i *= g^i on load
+    int scale_out;  // 0 none, 1 constant n^-1, 2 table n^-1 g^-i
+};
+
+__device__ __forceinline__ fr_t ld_fr(const fr_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    fr_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ fr_t ldg_fr(const fr_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    fr_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fr(fr_t* p, const fr_t& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+// shared-memory tile: low and high 16-byte halves in separate planes (conflict-free
+// 128-bit accesses for unit-stride element indices)
+__device__ __forceinline__ fr_t lds_fr(const uint4* lo, const uint4* hi, unsigned e) {
+    uint4 a = lo[e], b = hi[e];
+    fr_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void sts_fr(uint4* lo, uint4* hi, unsigned e, const fr_t& v) {
+    lo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    hi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+__device__ __forceinline__ size_t insert_bits(size_t x, unsigned pos, unsigned len, size_t val) {
+    return ((x >> pos) << (pos + len)) | (val << pos) | (x & (((size_t)1 << pos) - 1));
+}
+
+__device__ __forceinline__ size_t tile_index(const PassParams& p, size_t rest, unsigned d, unsigned c) {
+    if (p.last) {  // digit at bit 0, columns at cpos >= s
+        size_t x = insert_bits(rest, 0, p.s, d);
+        return insert_bits(x, p.cpos, p.c_log, c);
+    }
+    size_t x = insert_bits(rest, 0, p.c_log, c);
+    return insert_bits(x, p.lo, p.s, d);
+}
+
+__device__ __forceinline__ size_t digit_reverse(const PassParams& p, size_t idx) {
+    size_t o = 0;
+    unsigned pos = p.k, sh = 0;
+    for (unsigned i = 0; i < p.ndig; i++) {
+        pos -= p.dig[i];
+        o |= ((idx >> pos) & (((size_t)1 << p.dig[i]) - 1)) << sh;
+        sh += p.dig[i];
+    }
+    return o;
+}
+
+__device__ __forceinline__ fr_t scale_factor(const PassParams& p, size_t i) {
+    fr_t f = ldg_fr(p.sc_lo + (i & ((1u << LOG_LO) - 1)));
+    if (p.k > LOG_LO) f = f * ldg_fr(p.sc_hi + (i >> LOG_LO));
+    return f;
+}
+
+__global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
+    extern __shared__ uint4 smem[];
+    const unsigned T = 1u << (p.s + p.c_log);
+    uint4* s_lo = smem;
+    uint4* s_hi = smem + T;
+    const unsigned tid = threadIdx.x;
+    const size_t rest = blockIdx.x;
+    const fr_t* in = p.in + (size_t)blockIdx.y * p.in_stride;
+    fr_t* out = p.out + (size_t)blockIdx.y * p.out_stride;
+    const unsigned C = 1u << p.c_log;
+
+    for (unsigned e = tid; e < T; e += blockDim.x) {
+        const unsigned c = e & (C - 1), d = e >> p.c_log;
+        const size_t idx = tile_index(p, rest, d, c);
+        fr_t v = fr_t::zero();
+        if (idx < p.len_in) {
+            v = ld_fr(in + idx);
+            if (p.scale_in) v = v * scale_factor(p, idx);
+        }
+        sts_fr(s_lo, s_hi, e, v);
+    }
+    __syncthreads();
+
+    {
+        const bool active = tid < (T >> 1);
+        const unsigned c = tid & (C - 1), q = tid >> p.c_log;
+        // index bits below the digit (zero on the last pass)
+        const size_t low = p.last ? 0 : ((rest & (((size_t)1 << (p.lo - p.c_log)) - 1)) << p.c_log) | c;
+        const size_t half = ((size_t)1 << p.k) >> 1;
+        for (unsigned t = 0; t < p.s; t++) {
+            if (active) {
+                const unsigned span_log = p.s - 1 - t;
+                const unsigned j = q & ((1u << span_log) - 1);
+                const unsigned d0 = ((q >> span_log) << (span_log + 1)) | j;
+                const unsigned e0 = (d0 << p.c_log) | c;
+                const unsigned e1 = e0 + (1u << (span_log + p.c_log));
+                const fr_t u = lds_fr(s_lo, s_hi, e0);
+                const fr_t v = lds_fr(s_lo, s_hi, e1);
+                fr_t diff;
+                if (p.lo == 0 && span_log == 0) {
+                    diff = u - v;  // the last stage of the transform has twiddle 1 everywhere
+                } else {
+                    size_t widx = ((((size_t)j << p.lo) | low) << t) << p.tw_shift;
+                    const bool flip = p.inverse && widx != 0;  // w^-j = -w^(N/2-j)
+                    diff = flip ? v - u : u - v;
+                    widx = flip ? half - widx : widx;
+                    diff = diff * ldg_fr(p.tw + widx);
+                }
+                sts_fr(s_lo, s_hi, e0, u + v);
+                sts_fr(s_lo, s_hi, e1, diff);
+            }
+            __syncthreads();
+        }
+    }
+
+    for (unsigned e = tid; e < T; e += blockDim.x) {
+        const unsigned c = e & (C - 1), d = e >> p.c_log;
+        const unsigned kd = p.s ? (__brev(d) >> (32 - p.s)) : 0;  // DIF leaves the digit bit-reversed
+        size_t idx = tile_index(p, rest, kd, c);
+        fr_t v = lds_fr(s_lo, s_hi, e);
+        if (p.last) {
+            idx = digit_reverse(p, idx);
+            if (p.scale_out == 1) v = v * p.n_inv;
+            else if (p.scale_out == 2) v = v * scale_factor(p, idx);
+        }
+        st_fr(out + idx, v);
+    }
+}
+
+// ------------------------------------------------------------------ planning + launch
+int ntt_run(zkp_ctx* ctx, const fr_t* in, size_t in_stride, size_t len_in, fr_t* out,
+            size_t out_stride, unsigned k, bool inverse, bool coset, unsigned batch) {
+    if (k > 28 || batch == 0) return ZKP_ERR_INVALID;
+    const size_t n = (size_t)1 << k;
+    if (len_in > n) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    NttDomain* dom;
+    if ((rc = get_domain(ctx, k, &dom))) return rc;
+
+    const unsigned P = k == 0 ? 1 : (k + S_MAX - 1) / S_MAX;
+    unsigned dig[6];
+    for (unsigned i = 0; i < P; i++) dig[i] = k / P + (i < k % P ? 1 : 0);
+
+    const fr_t* src = in;
+    size_t src_stride = in_stride;
+    fr_t* work = nullptr;
+    if (P > 1) {
+        const size_t need = n * batch;
+        if (ctx->ntt_scratch_n < need) {
+            if (ctx->ntt_scratch) cudaFree(ctx->ntt_scratch);
+            ctx->ntt_scratch = nullptr; ctx->ntt_scratch_n = 0;
+            ZKP_CUDA(ctx, cudaMalloc(&ctx->ntt_scratch, need * sizeof(fr_t)));
+            ctx->ntt_scratch_n = need;
+        }
+        work = ctx->ntt_scratch;
+    }
+
+    ProfScope prof(ctx, "ntt");
+    unsigned lo = k;
+    for (unsigned i = 0; i < P; i++) {
+        lo -= dig[i];
+        PassParams p;
+        p.k = k; p.s = dig[i]; p.lo = lo;
+        p.last = (i == P - 1);
+        p.inverse = inverse;
+        p.tw = dom->tw;
+        p.tw_shift = k - p.s - lo;
+        p.ndig = P;
+        for (unsigned j = 0; j < 6; j++) p.dig[j] = j < P ? dig[j] : 0;
+        if (p.last) {
+            p.c_log = P > 1 ? (dig[0] < C_LOG ? dig[0] : C_LOG) : 0;
+            p.cpos = k - dig[0];
+        } else {
+            p.c_log = lo < C_LOG ? lo : C_LOG;
+            p.cpos = 0;
+        }
+        p.in = src; p.in_stride = src_stride;
+        p.len_in = (i == 0) ? len_in : n;
+        if (p.last) { p.out = out; p.out_stride = out_stride; }
+        else { p.out = work; p.out_stride = n; }
+        p.scale_in = (i == 0 && coset && !inverse);
+        p.scale_out = 0;
+        p.sc_lo = nullptr; p.sc_hi = nullptr;
+        p.n_inv = dom->n_inv;
+        if (p.scale_in) { p.sc_lo = dom->g_lo; p.sc_hi = dom->g_hi; }
+        if (p.last && inverse) {
+            p.scale_out = coset ? 2 : 1;
+            if (coset) { p.sc_lo = dom->gi_lo; p.sc_hi = dom->gi_hi; }
+        }
+        const unsigned tlog = p.s + p.c_log;
+        const unsigned threads = tlog ? (1u << (tlog - 1)) : 1;
+        const size_t smem = ((size_t)2 << tlog) * sizeof(uint4);
+        dim3 grid((unsigned)(n >> tlog), batch);
+        ntt_pass_kernel<<<grid, threads < 32 ? 32 : threads, smem, ctx->stream>>>(p);
+        ZKP_LAUNCHED(ctx);
+        src = p.out; src_stride = p.out_stride;
+    }
+    return ZKP_OK;
+}
+
+int ntt_elements(zkp_ctx* ctx, unsigned k, fr_t* out) {
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    const size_t n = (size_t)1 << k;
+    size_t threads = (n + 15) / 16;
+    geometric_table_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(
+        out, n, fft_constant_host(k, 0), fr_t::one());
+    ZKP_LAUNCHED(ctx);
+    return ZKP_OK;
+}
+
+}  // namespace zkp

@@ -1,0 +1,317 @@
+"""ctypes binding of libzkp_b200.so -- the same C ABI (include/zkp_b200.h) a Rust
+``extern "C"`` block would bind.  There is no CPU fallback: loading fails
+loudly when the CUDA library has not been built, and every call fails when no sm_100
+device is present."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libzkp_b200.so")
+
+ZKP_OK = 0
+ZKP_ERR_INVALID = -1
+ZKP_ERR_CUDA = -2
+ZKP_ERR_DEGREE = -3
+ZKP_ERR_NOMEM = -4
+ZKP_ERR_STATE = -5
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_vp = ctypes.c_void_p
+_sz = ctypes.c_size_t
+_int = ctypes.c_int
+_uint = ctypes.c_uint
+
+# name -> (restype, argtypes); every symbol include/zkp_b200.h declares
+SIGNATURES = {
+    "zkp_ctx_create": (_int, [_int, ctypes.POINTER(_vp)]),
+    "zkp_ctx_destroy": (None, [_vp]),
+    "zkp_last_error": (ctypes.c_char_p, [_vp]),
+    "zkp_strerror": (ctypes.c_char_p, [_int]),
+    "zkp_ctx_sync": (_int, [_vp]),
+    "zkp_ctx_stream": (_vp, [_vp]),
+    "zkp_sm_count": (_int, [_vp]),
+    "zkp_launch_count": (ctypes.c_uint64, [_vp]),
+    "zkp_timer_start": (_int, [_vp]),
+    "zkp_timer_stop_ms": (_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "zkp_prof_enable": (_int, [_vp, _int]),
+    "zkp_prof_reset": (_int, [_vp]),
+    "zkp_prof_read": (_int, [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64)]),
+    "zkp_buf_alloc": (_int, [_vp, _sz, ctypes.POINTER(_vp)]),
+    "zkp_buf_free": (_int, [_vp, _vp]),
+    "zkp_buf_len": (_sz, [_vp]),
+    "zkp_buf_upload": (_int, [_vp, _vp, _sz, _vp, _sz]),
+    "zkp_buf_download": (_int, [_vp, _vp, _sz, _vp, _sz]),
+    "zkp_buf_zero": (_int, [_vp, _vp, _sz, _sz]),
+    "zkp_buf_copy": (_int, [_vp, _vp, _sz, _vp, _sz, _sz]),
+    "zkp_ntt": (_int, [_vp, _vp, _sz, _uint, _int, _int]),
+    "zkp_ntt_dev": (_int, [_vp, _vp, _sz, _vp, _uint, _int, _int]),
+    "zkp_ntt_dev_batch": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _uint, _int, _int, _uint]),
+    "zkp_fft_constant": (_int, [_uint, _int, _vp]),
+    "zkp_fft_elements_dev": (_int, [_vp, _uint, _vp]),
+    "zkp_srs_load": (_int, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "zkp_srs_free": (_int, [_vp, _vp]),
+    "zkp_srs_len": (_sz, [_vp]),
+    "zkp_srs_generate": (_int, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "zkp_srs_download": (_int, [_vp, _vp, _sz, _vp, _sz]),
+    "zkp_msm_g1": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "zkp_msm_g1_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp]),
+    "zkp_commit": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "zkp_commit_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp]),
+    "zkp_msm_set_window": (_int, [_vp, _uint]),
+}
+
+_lib = None
+
+
+class ZkpError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        msg = "zkp_b200 error %d" % code
+        if _lib is not None:
+            msg += " (%s)" % _lib.zkp_strerror(code).decode()
+        if detail:
+            msg += ": " + detail
+        super().__init__(msg)
+
+
+def load_library():
+    """Load libzkp_b200.so and bind every exported symbol.  Raises if it is missing --
+    the product has no other compute path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libzkp_b200.so not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`"
+            % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI drifted
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def as_fr_array(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    assert a.ndim == 2 and a.shape[1] == 4, "Fr arrays are (n, 4) uint64 Montgomery limbs"
+    return a
+
+
+class Context:
+    """One CUDA device + stream (``zkp_ctx``)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = _vp()
+        rc = self.lib.zkp_ctx_create(device, ctypes.byref(h))
+        if rc:
+            raise ZkpError(rc, "zkp_ctx_create(device=%d): no usable sm_100 GPU" % device)
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc:
+            raise ZkpError(rc, self.lib.zkp_last_error(self.h).decode() if rc == ZKP_ERR_CUDA else "")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.zkp_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self.check(self.lib.zkp_ctx_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.zkp_ctx_stream(self.h)
+
+    @property
+    def sm_count(self):
+        return self.lib.zkp_sm_count(self.h)
+
+    @property
+    def launches(self):
+        return int(self.lib.zkp_launch_count(self.h))
+
+    def timer_start(self):
+        self.check(self.lib.zkp_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = ctypes.c_float()
+        self.check(self.lib.zkp_timer_stop_ms(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def prof_enable(self, on=True):
+        self.check(self.lib.zkp_prof_enable(self.h, int(on)))
+
+    def prof_reset(self):
+        self.check(self.lib.zkp_prof_reset(self.h))
+
+    def prof_read(self, name):
+        ms = ctypes.c_float()
+        cnt = ctypes.c_uint64()
+        self.check(self.lib.zkp_prof_read(self.h, name.encode(), ctypes.byref(ms), ctypes.byref(cnt)))
+        return ms.value, int(cnt.value)
+
+    # ---- buffers
+    def alloc(self, n):
+        return DeviceBuffer(self, n)
+
+    def upload(self, arr):
+        arr = as_fr_array(arr)
+        b = DeviceBuffer(self, arr.shape[0])
+        b.upload(arr)
+        return b
+
+    # ---- NTT on host vectors
+    def ntt(self, data, k, inverse=False, coset=False):
+        data = as_fr_array(data)
+        n = 1 << k
+        m = data.shape[0]
+        assert m <= n
+        buf = np.zeros((n, 4), dtype=np.uint64)
+        buf[:m] = data
+        self.check(self.lib.zkp_ntt(self.h, _ptr(buf), m, k, int(inverse), int(coset)))
+        return buf
+
+    def ntt_dev(self, src, len_in, dst, k, inverse=False, coset=False):
+        self.check(self.lib.zkp_ntt_dev(self.h, src.h, len_in, dst.h, k, int(inverse), int(coset)))
+
+    def ntt_dev_batch(self, src, in_stride, len_in, dst, out_stride, k, inverse, coset, batch):
+        self.check(self.lib.zkp_ntt_dev_batch(self.h, src.h, in_stride, len_in, dst.h, out_stride, k,
+                                              int(inverse), int(coset), batch))
+
+    def fft_elements(self, k):
+        b = DeviceBuffer(self, 1 << k)
+        self.check(self.lib.zkp_fft_elements_dev(self.h, k, b.h))
+        return b
+
+    # ---- SRS / MSM
+    def srs_load(self, xy):
+        xy = np.ascontiguousarray(xy, dtype=np.uint64).reshape(-1, 12)
+        return Srs(self, xy=xy)
+
+    def srs_generate(self, tau_mont, n):
+        return Srs(self, tau=np.ascontiguousarray(tau_mont, dtype=np.uint64).reshape(4), n=n)
+
+    def msm(self, srs, scalars):
+        scalars = as_fr_array(scalars)
+        out = np.zeros(12, dtype=np.uint64)
+        self.check(self.lib.zkp_msm_g1(self.h, srs.h, _ptr(scalars), scalars.shape[0], _ptr(out)))
+        return out
+
+    def msm_dev(self, srs, buf, off=0, n=None):
+        n = buf.n - off if n is None else n
+        out = np.zeros(12, dtype=np.uint64)
+        self.check(self.lib.zkp_msm_g1_dev(self.h, srs.h, buf.h, off, n, _ptr(out)))
+        return out
+
+    def commit(self, srs, coeffs):
+        coeffs = as_fr_array(coeffs)
+        out = np.zeros(12, dtype=np.uint64)
+        rc = self.lib.zkp_commit(self.h, srs.h, _ptr(coeffs), coeffs.shape[0], _ptr(out))
+        self.check(rc)
+        return out
+
+    def commit_dev(self, srs, buf, off=0, n=None):
+        n = buf.n - off if n is None else n
+        out = np.zeros(12, dtype=np.uint64)
+        self.check(self.lib.zkp_commit_dev(self.h, srs.h, buf.h, off, n, _ptr(out)))
+        return out
+
+    def set_msm_window(self, c):
+        self.check(self.lib.zkp_msm_set_window(self.h, c))
+
+
+def fft_constant(k, kind):
+    lib = load_library()
+    out = np.zeros(4, dtype=np.uint64)
+    rc = lib.zkp_fft_constant(k, kind, _ptr(out))
+    if rc:
+        raise ZkpError(rc)
+    return out
+
+
+class DeviceBuffer:
+    """Device-resident Fr vector (``zkp_buf``)."""
+
+    def __init__(self, ctx, n):
+        self.ctx = ctx
+        self.n = n
+        h = _vp()
+        ctx.check(ctx.lib.zkp_buf_alloc(ctx.h, n, ctypes.byref(h)))
+        self.h = h
+
+    def upload(self, arr, off=0):
+        arr = as_fr_array(arr)
+        self.ctx.check(self.ctx.lib.zkp_buf_upload(self.ctx.h, self.h, off, _ptr(arr), arr.shape[0]))
+
+    def download(self, off=0, n=None):
+        n = self.n - off if n is None else n
+        out = np.empty((n, 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.zkp_buf_download(self.ctx.h, self.h, off, _ptr(out), n))
+        return out
+
+    def zero(self, off=0, n=None):
+        n = self.n - off if n is None else n
+        self.ctx.check(self.ctx.lib.zkp_buf_zero(self.ctx.h, self.h, off, n))
+
+    def copy_from(self, src, n, dst_off=0, src_off=0):
+        self.ctx.check(self.ctx.lib.zkp_buf_copy(self.ctx.h, self.h, dst_off, src.h, src_off, n))
+
+    def free(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.zkp_buf_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Srs:
+    """Device-resident SRS powers (``zkp_srs``)."""
+
+    def __init__(self, ctx, xy=None, tau=None, n=None):
+        self.ctx = ctx
+        h = _vp()
+        if xy is not None:
+            ctx.check(ctx.lib.zkp_srs_load(ctx.h, _ptr(xy), xy.shape[0], ctypes.byref(h)))
+            self.n = xy.shape[0]
+        else:
+            ctx.check(ctx.lib.zkp_srs_generate(ctx.h, _ptr(tau), n, ctypes.byref(h)))
+            self.n = n
+        self.h = h
+
+    def download(self, off=0, n=None):
+        n = self.n - off if n is None else n
+        out = np.empty((n, 12), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.zkp_srs_download(self.ctx.h, self.h, off, _ptr(out), n))
+        return out
+
+    def free(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.zkp_srs_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

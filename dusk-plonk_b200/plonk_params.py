@@ -1,0 +1,57 @@
+"""Host-side mirror of ``zksnarks::plonk::PlonkParams`` for the commit path
+(``keypair.commit(&poly)?``, src/prover.rs:133; ``.unwrap_or_default()``, src/key.rs:138;
+``keypair.trim(additional_n)``, src/key.rs:82), backed by the CUDA MSM."""
+import numpy as np
+
+from .ffi import Context, DeviceBuffer, ZkpError, ZKP_ERR_DEGREE
+from .poly_commit import Coefficients, Commitment
+
+
+class Error(Exception):
+    """Stands in for ``zksnarks::error::Error`` on the commit path."""
+
+
+class PlonkParams:
+    def __init__(self, ctx: Context, srs):
+        self.ctx = ctx
+        self.srs = srs
+
+    @classmethod
+    def setup_synthetic(cls, ctx, k, tau_mont):
+        """SRS with the structure of ``PlonkParams::setup(k, rng)`` (tests/range.rs:26):
+        [tau^i]_1 for i < 2^k + 7 (the prover needs n + 7 powers for t_4).
+        tau is an explicit input because the reference's RNG derivation is unreachable."""
+        return cls(ctx, ctx.srs_generate(tau_mont, (1 << k) + 7))
+
+    @classmethod
+    def from_points(cls, ctx, xy):
+        return cls(ctx, ctx.srs_load(xy))
+
+    def max_degree(self):
+        return self.srs.n - 1
+
+    def trim(self, n):
+        """Keep n + 7 powers (``trim`` must leave room for the blinded quotient chunk)."""
+        keep = min(self.srs.n, n + 7)
+        if keep == self.srs.n:
+            return self
+        return PlonkParams(self.ctx, self.ctx.srs_load(self.srs.download(0, keep)))
+
+    def commit(self, poly):
+        """-> Commitment, raising ``Error`` when degree > SRS (Err in the reference)."""
+        try:
+            if isinstance(poly, DeviceBuffer):
+                return Commitment(self.ctx.commit_dev(self.srs, poly))
+            v = poly.v if isinstance(poly, Coefficients) else poly
+            return Commitment(self.ctx.commit(self.srs, v))
+        except ZkpError as e:
+            if e.code == ZKP_ERR_DEGREE:
+                raise Error("polynomial degree exceeds the SRS") from e
+            raise
+
+    def commit_or_default(self, poly):
+        """``keypair.commit(&p).unwrap_or_default()`` (src/key.rs:138-154)."""
+        try:
+            return self.commit(poly)
+        except Error:
+            return Commitment(np.zeros(12, dtype=np.uint64))

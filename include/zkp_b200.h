@@ -1,0 +1,132 @@
+/*
+ * zkp_b200 -- C ABI of the B200-native zkplonk hot path.
+ *
+ * This is the drop-in boundary: the entry points a Rust `extern "C"` block in
+ * the reference's `poly-commit` / `zksnarks` crates would bind to replace
+ *   - poly_commit::Fft::{new,dft,idft,coset_dft,coset_idft}   (call sites src/prover.rs:87-88,
+ *     121-124,192,229; src/prover/quotient_poly.rs:50-58,115,145,237; src/key.rs:83,121-131,
+ *     222-245; src/permutation.rs:194-197,229-235)
+ *   - PlonkParams::commit / poly_commit::msm_curve_addition    (src/prover.rs:133-136,194,
+ *     262-265,440,452; src/key.rs:138-159; src/prover/proof.rs:507-526)
+ *   - the element-wise prover rounds between them              (src/prover.rs:107-452,
+ *     src/prover/quotient_poly.rs, src/permutation.rs:205-300,
+ *     src/prover/linearization_poly.rs)
+ * INTEGRATION.md shows the Rust-side binding.
+ *
+ * Layouts (explicit, because the Rust struct layout of the absent crates is not visible):
+ *   Fr  : 4 x uint64 little-endian limbs, Montgomery form, R = 2^256  (src/lib.rs:583-588)
+ *   Fq  : 6 x uint64 little-endian limbs, Montgomery form, R = 2^384
+ *   G1 affine : x then y = 12 x uint64; the point at infinity is x = y = 0
+ *
+ * All functions return 0 on success or a negative ZKP_ERR_* code; nothing unwinds across
+ * the boundary (the reference builds with panic = "abort", Cargo.toml:52).  A context owns
+ * one CUDA device and one stream; calls on the same context are serialised by the caller
+ * (one context per proving thread mirrors `Prover: Clone`, src/prover.rs:28).
+ * There is NO CPU fallback: every entry point fails with ZKP_ERR_CUDA when no sm_100 device
+ * is usable.
+ */
+#ifndef ZKP_B200_H
+#define ZKP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKP_OK 0
+#define ZKP_ERR_INVALID (-1)   /* bad argument (null, size, k out of range)                      */
+#define ZKP_ERR_CUDA (-2)      /* CUDA runtime failure; see zkp_last_error()                     */
+#define ZKP_ERR_DEGREE (-3)    /* polynomial degree exceeds the SRS: PlonkParams::commit's Err   */
+#define ZKP_ERR_NOMEM (-4)
+#define ZKP_ERR_STATE (-5)     /* prover round called out of order                               */
+
+typedef struct zkp_ctx zkp_ctx;
+typedef struct zkp_srs zkp_srs;   /* device-resident [tau^i]_1 powers (PlonkParams after trim)  */
+typedef struct zkp_buf zkp_buf;   /* device-resident vector of Fr                               */
+
+/* ---- context --------------------------------------------------------------------- */
+int zkp_ctx_create(int device, zkp_ctx** out);
+void zkp_ctx_destroy(zkp_ctx* ctx);
+const char* zkp_last_error(const zkp_ctx* ctx); /* text of the last CUDA failure          */
+const char* zkp_strerror(int code);
+int zkp_ctx_sync(zkp_ctx* ctx);
+void* zkp_ctx_stream(zkp_ctx* ctx);             /* cudaStream_t the kernels are launched on */
+int zkp_sm_count(const zkp_ctx* ctx);
+/* number of kernels this library launched on ctx since creation (bench.py gpu_launches) */
+uint64_t zkp_launch_count(const zkp_ctx* ctx);
+
+/* CUDA-event timing on the context's stream (events are recorded where the kernels run) */
+int zkp_timer_start(zkp_ctx* ctx);
+int zkp_timer_stop_ms(zkp_ctx* ctx, float* ms);  /* records stop, synchronises, returns ms  */
+
+/* Per-kernel timing for the roofline report: when enabled, the library brackets its named
+ * kernel groups ("msm_accumulate", "msm_sort", "msm_reduce", "ntt_pass", ...) with CUDA
+ * events on the context's stream.  zkp_prof_read synchronises and sums a group. */
+int zkp_prof_enable(zkp_ctx* ctx, int on);
+int zkp_prof_reset(zkp_ctx* ctx);
+int zkp_prof_read(zkp_ctx* ctx, const char* name, float* total_ms, uint64_t* count);
+
+/* ---- Fr vectors on the device ----------------------------------------------------- */
+int zkp_buf_alloc(zkp_ctx* ctx, size_t n, zkp_buf** out);
+int zkp_buf_free(zkp_ctx* ctx, zkp_buf* buf);
+size_t zkp_buf_len(const zkp_buf* buf);
+int zkp_buf_upload(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const uint64_t* src, size_t n);
+int zkp_buf_download(zkp_ctx* ctx, const zkp_buf* src, size_t src_off, uint64_t* dst, size_t n);
+int zkp_buf_zero(zkp_ctx* ctx, zkp_buf* buf, size_t off, size_t n);
+int zkp_buf_copy(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const zkp_buf* src, size_t src_off,
+                 size_t n);
+
+/* ---- NTT: poly_commit::Fft ---------------------------------------------------------- */
+/* Host vector, in place.  data holds 2^k Fr; the first len_in are inputs, the rest is
+ * treated as zero (Fft pads short inputs).  inverse=0,coset=0: dft; 1,0: idft (x n^-1);
+ * 0,1: coset_dft (a_i * g^i first, g = 7); 1,1: coset_idft (x g^-i last).
+ * Output in natural order: out[j] = sum_i a_i w^(ij), w = Fft::new(k).generator(). */
+int zkp_ntt(zkp_ctx* ctx, uint64_t* data, size_t len_in, unsigned k, int inverse, int coset);
+/* Device-resident variant.  in may equal out.  in holds >= len_in, out >= 2^k elements. */
+int zkp_ntt_dev(zkp_ctx* ctx, const zkp_buf* in, size_t len_in, zkp_buf* out, unsigned k,
+                int inverse, int coset);
+/* `batch` transforms of the same shape: polynomial b reads in[b*in_stride ..] and writes
+ * out[b*out_stride ..] (wire / selector batches of src/prover.rs:121-124, src/key.rs:121-131). */
+int zkp_ntt_dev_batch(zkp_ctx* ctx, const zkp_buf* in, size_t in_stride, size_t len_in,
+                      zkp_buf* out, size_t out_stride, unsigned k, int inverse, int coset,
+                      unsigned batch);
+/* Fft accessors: generator w (kind 0), w^-1 (1), n^-1 (2), coset g (3), g^-1 (4) */
+int zkp_fft_constant(unsigned k, int kind, uint64_t out[4]);
+/* Fft::elements: out[i] = w^i, i < 2^k (device buffer) */
+int zkp_fft_elements_dev(zkp_ctx* ctx, unsigned k, zkp_buf* out);
+
+/* ---- KZG10 commit: PlonkParams ------------------------------------------------------- */
+/* Upload n affine powers (n x 12 uint64).  Mirrors PlonkParams::trim: the handle is what
+ * `keypair` holds afterwards. */
+int zkp_srs_load(zkp_ctx* ctx, const uint64_t* xy, size_t n, zkp_srs** out);
+int zkp_srs_free(zkp_ctx* ctx, zkp_srs* srs);
+size_t zkp_srs_len(const zkp_srs* srs);
+/* Synthetic SRS [tau^i * G]_{i<n} generated on the device (PlonkParams::setup's structure,
+ * tests/range.rs:26; tau is Montgomery Fr).  Used by benchmarks and full-size tests. */
+int zkp_srs_generate(zkp_ctx* ctx, const uint64_t tau[4], size_t n, zkp_srs** out);
+int zkp_srs_download(zkp_ctx* ctx, const zkp_srs* srs, size_t off, uint64_t* xy, size_t n);
+
+/* msm_curve_addition(&bases[..n], &scalars[..n]) -> affine (Commitment::new).
+ * scalars: n x 4 uint64 Montgomery Fr on the host. */
+int zkp_msm_g1(zkp_ctx* ctx, const zkp_srs* srs, const uint64_t* scalars, size_t n,
+               uint64_t out_xy[12]);
+/* Same with device-resident scalars scalars[off .. off+n). */
+int zkp_msm_g1_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* scalars, size_t off,
+                   size_t n, uint64_t out_xy[12]);
+/* PlonkParams::commit(&Coefficients): as zkp_msm_g1, but trailing zero coefficients are
+ * ignored and ZKP_ERR_DEGREE is returned when the highest non-zero index is >= the SRS
+ * length (the only way create_proof fails for an unsatisfied circuit).  An
+ * all-zero polynomial commits to the identity (x = y = 0). */
+int zkp_commit(zkp_ctx* ctx, const zkp_srs* srs, const uint64_t* coeffs, size_t n,
+               uint64_t out_xy[12]);
+int zkp_commit_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* coeffs, size_t off, size_t n,
+                   uint64_t out_xy[12]);
+/* MSM tuning knob (window bits c; 0 = automatic). */
+int zkp_msm_set_window(zkp_ctx* ctx, unsigned c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKP_B200_H */
