@@ -57,6 +57,7 @@ void zkp_ctx_destroy(zkp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ntt_free_domains(ctx);
     msm_free(ctx);
+    prover_free(ctx);
     for (auto& s : ctx->prof_spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto& e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -42,6 +42,8 @@ struct zkp_ctx {
     zkp::fr_t* ntt_scratch = nullptr;
     size_t ntt_scratch_n = 0;
     zkp::MsmScratch* msm = nullptr;
+    zkp::fr_t* prover_scratch = nullptr;  // prover.cu: scan / evaluation temporaries
+    size_t prover_scratch_n = 0;
     void* pinned = nullptr;       // small pinned staging area for results
     size_t pinned_bytes = 0;
     // optional per-kernel timing (CUDA events on `stream`), read by bench.py for the roofline
@@ -111,5 +113,8 @@ int msm_run(zkp_ctx* ctx, const g1_affine* bases, const fr_t* scalars_dev, size_
 int msm_highest_nonzero(zkp_ctx* ctx, const fr_t* scalars_dev, size_t n, long long* out);
 int srs_generate(zkp_ctx* ctx, const fr_t& tau, size_t n, g1_affine* out_dev);
 void msm_free(zkp_ctx* ctx);
+
+// prover.cu
+void prover_free(zkp_ctx* ctx);
 
 }  // namespace zkp

@@ -1,0 +1,660 @@
+// Element-wise prover rounds on device-resident polynomials (sm_100a).
+//
+// Replaces the host loops the reference runs between its NTTs and commits:
+//   * Permutation::compute_permutation_vec           src/permutation.rs:205-300
+//   * quotient_poly::compute (gate + permutation identities, / Z_H)
+//                                                    src/prover/quotient_poly.rs:20-118,122-262
+//   * Coefficients::evaluate (16 openings + t, r)    src/prover/linearization_poly.rs:52-73,108
+//   * widget.linearize sums and `&poly * &scalar + ..` src/prover/linearization_poly.rs:75-105,
+//                                                    src/prover.rs:408-418
+//   * PlonkParams::compute_aggregate_witness          src/prover.rs:422-451
+//   * Coefficients::blind                             src/prover.rs:126-129,193
+//   * compute_permutation_lagrange                    src/permutation.rs:140-169
+// Every result is an exact function of its inputs over Fr, so any evaluation order gives
+// the reference's bits; the kernels are organised for the GPU, not after the Rust loops:
+//   - n per-gate inversions + a serial product scan  ->  two chunked product scans + ONE inversion
+//   - 8n inversions of Z_H (8 distinct values)        ->  an 8-entry table
+//   - 17 serial Horner passes                         ->  batched chunk-Horner + power-table tree
+//   - synthetic division                              ->  chunked suffix-Horner scan
+#include <string.h>
+
+#include "common.cuh"
+
+namespace zkp {
+
+// ------------------------------------------------------------------ helpers
+__device__ __forceinline__ fr_t pld(const fr_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    fr_t r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void pst(fr_t* p, const fr_t& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+// x * K for a small compile-time K by double-and-add (additions only)
+template <unsigned K>
+__device__ __forceinline__ fr_t mul_small(const fr_t& x) {
+    static_assert(K >= 1, "K >= 1");
+    if constexpr (K == 1) {
+        return x;
+    } else {
+        fr_t h = dbl(mul_small<(K >> 1)>(x));
+        if constexpr (K & 1) h = h + x;
+        return h;
+    }
+}
+
+static inline fr_t fr_from_host(const uint64_t* p) { fr_t r; memcpy(r.l, p, 32); return r; }
+
+#define CHECK_REF(r) ((r).buf && (r).off + (r).len <= (r).buf->n)
+
+// ------------------------------------------------------------------ small kernels
+__global__ void fill_kernel(fr_t* out, size_t n, fr_t v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pst(out + i, v);
+}
+
+// Coefficients::blind: p <- p + (b0 + b1 X + ..)(X^n - 1)
+__global__ void blind_kernel(fr_t* p, size_t n, fr_t b0, fr_t b1, fr_t b2, unsigned cnt) {
+    unsigned i = threadIdx.x;
+    if (i >= cnt) return;
+    fr_t b = i == 0 ? b0 : (i == 1 ? b1 : b2);
+    pst(p + i, pld(p + i) - b);
+    pst(p + n + i, b);
+}
+
+// sigma evaluations: out[i] = K[wire] * w^gate, enc = wire << 30 | gate
+__global__ void perm_lagrange_kernel(const uint32_t* enc, size_t n, const fr_t* roots, fr_t k1, fr_t k2, fr_t k3,
+                                     fr_t* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t e = enc[i];
+    const uint32_t w = e >> 30;
+    fr_t r = pld(roots + (e & 0x3fffffffu));
+    if (w == 1) r = r * k1;
+    else if (w == 2) r = r * k2;
+    else if (w == 3) r = r * k3;
+    pst(out + i, r);
+}
+
+// ------------------------------------------------------------------ permutation accumulator
+struct PermArgs {
+    const fr_t* w[4];
+    const fr_t* sigma[4];
+    const fr_t* roots;
+    fr_t beta, gamma, bk[4];
+    size_t n;
+    fr_t* num;
+    fr_t* den;
+};
+
+__global__ void __launch_bounds__(128) perm_numden_kernel(PermArgs a) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const fr_t root = pld(a.roots + i);
+    fr_t nu, de;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const fr_t w = pld(a.w[j] + i) + a.gamma;
+        const fr_t f = w + a.bk[j] * root;
+        const fr_t g = w + a.beta * pld(a.sigma[j] + i);
+        nu = j ? nu * f : f;
+        de = j ? de * g : g;
+    }
+    pst(a.num + i, nu);
+    pst(a.den + i, de);
+}
+
+// Chunked product scan, three passes.  reverse = 0: inclusive prefix products;
+// reverse = 1: inclusive suffix products.
+static constexpr unsigned SCAN_L = 16;
+
+__global__ void prod_chunk_kernel(const fr_t* in, size_t n, fr_t* chunk) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = t * SCAN_L;
+    if (lo >= n) return;
+    size_t hi = lo + SCAN_L < n ? lo + SCAN_L : n;
+    fr_t p = pld(in + lo);
+    for (size_t i = lo + 1; i < hi; i++) p = p * pld(in + i);
+    pst(chunk + t, p);
+}
+
+// single block: chunk[t] <- product of the chunks before (after, if reverse) t
+__global__ void __launch_bounds__(1024) prod_carry_kernel(fr_t* chunk, size_t nc, int reverse) {
+    __shared__ fr_t sm[1024];
+    const unsigned T = blockDim.x, tid = threadIdx.x;
+    const size_t per = (nc + T - 1) / T;
+    // logical index j runs in scan direction
+    auto at = [&](size_t j) { return reverse ? nc - 1 - j : j; };
+    const size_t lo = (size_t)tid * per, hi = lo + per < nc ? lo + per : nc;
+    fr_t p = fr_t::one();
+    for (size_t j = lo; j < hi; j++) p = p * pld(chunk + at(j));
+    sm[tid] = p;
+    __syncthreads();
+    for (unsigned s = 1; s < T; s <<= 1) {
+        fr_t v = sm[tid];
+        if (tid >= s) v = sm[tid - s] * v;
+        __syncthreads();
+        sm[tid] = v;
+        __syncthreads();
+    }
+    fr_t run = tid ? sm[tid - 1] : fr_t::one();
+    for (size_t j = lo; j < hi; j++) {
+        fr_t c = pld(chunk + at(j));
+        pst(chunk + at(j), run);
+        run = run * c;
+    }
+}
+
+__global__ void prod_apply_kernel(const fr_t* in, size_t n, const fr_t* carry, int reverse, fr_t* out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = t * SCAN_L;
+    if (lo >= n) return;
+    size_t hi = lo + SCAN_L < n ? lo + SCAN_L : n;
+    fr_t run = pld(carry + t);
+    if (!reverse) {
+        for (size_t i = lo; i < hi; i++) { run = run * pld(in + i); pst(out + i, run); }
+    } else {
+        for (size_t i = hi; i-- > lo;) { run = run * pld(in + i); pst(out + i, run); }
+    }
+}
+
+__global__ void fr_inverse_kernel(const fr_t* in, fr_t* out) { pst(out, inverse(pld(in))); }
+
+// z[0] = 1, z[i] = P[i-1] * S[i] * inv   (P inclusive prefix of num, S inclusive suffix of den,
+// inv = 1 / prod(den)):  prod_{j<i} num_j / den_j
+__global__ void perm_z_combine_kernel(const fr_t* P, const fr_t* S, const fr_t* inv, size_t n, fr_t* z) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i == 0) { pst(z, fr_t::one()); return; }
+    pst(z + i, pld(P + i - 1) * pld(S + i) * pld(inv));
+}
+
+// ------------------------------------------------------------------ quotient
+struct QuotArgs {
+    const fr_t* w[4];
+    const fr_t* z;
+    const fr_t* pi;
+    const fr_t* l1;
+    const fr_t* sel[11];  // q_m q_l q_r q_o q_c q_4 q_arith q_range q_logic q_fixed q_var
+    const fr_t* sigma[4];
+    const fr_t* linear;
+    fr_t alpha, beta, gamma, rs, ls, fs, vs;
+    fr_t bk1, bk2, bk3;  // beta * K_j
+    fr_t edwards_d;
+    fr_t zh_inv[8];
+    uint32_t mask;
+    size_t n8;
+    fr_t* out;
+};
+
+__device__ __forceinline__ fr_t delta4(const fr_t& f, const fr_t& one, const fr_t& two, const fr_t& three) {
+    return f * (f - one) * ((f - two) * (f - three));
+}
+
+__global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ QuotArgs q) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.n8) return;
+    const size_t in = (i + 8) & (q.n8 - 1);  // "next gate" on the 8n coset (quotient_poly.rs:60-66)
+    const fr_t one = fr_t::one(), two = dbl(one), three = two + one;
+    const fr_t a = pld(q.w[0] + i), b = pld(q.w[1] + i), c = pld(q.w[2] + i), d = pld(q.w[3] + i);
+    const fr_t qc = pld(q.sel[4] + i);
+    // arithmetic widget + PI
+    fr_t t = a * b * pld(q.sel[0] + i) + a * pld(q.sel[1] + i) + b * pld(q.sel[2] + i) + c * pld(q.sel[3] + i) +
+             d * pld(q.sel[5] + i) + qc;
+    t = t * pld(q.sel[6] + i) + pld(q.pi + i);
+    if (q.mask) {
+        const fr_t an = pld(q.w[0] + in), bn = pld(q.w[1] + in), dn = pld(q.w[3] + in);
+        if (q.mask & 1u) {  // range
+            const fr_t k = sqr(q.rs), k2 = sqr(k), k3 = k2 * k;
+            fr_t s = delta4(c - mul_small<4>(d), one, two, three) + delta4(b - mul_small<4>(c), one, two, three) * k +
+                     delta4(a - mul_small<4>(b), one, two, three) * k2 +
+                     delta4(dn - mul_small<4>(a), one, two, three) * k3;
+            t = t + s * q.rs * pld(q.sel[7] + i);
+        }
+        if (q.mask & 2u) {  // logic
+            const fr_t k = sqr(q.ls), k2 = sqr(k), k3 = k2 * k, k4 = k3 * k;
+            const fr_t A = an - mul_small<4>(a), B = bn - mul_small<4>(b), D = dn - mul_small<4>(d);
+            const fr_t ab = A + B;
+            // F = w (w (4w - 18(A+B) + 81) + 18(A^2 + B^2) - 81(A+B) + 83)
+            fr_t f = mul_small<4>(c) - mul_small<18>(ab) + mul_small<81>(one);
+            f = c * f + mul_small<18>(sqr(A) + sqr(B)) - mul_small<81>(ab) + mul_small<83>(one);
+            f = c * f;
+            const fr_t e = mul_small<3>(ab + D) - dbl(f);
+            const fr_t bb = qc * (mul_small<9>(D) - mul_small<3>(ab));
+            fr_t s = (c - A * B) * k3 + delta4(A, one, two, three) + delta4(B, one, two, three) * k +
+                     delta4(D, one, two, three) * k2 + (bb + e) * k4;
+            t = t + s * q.ls * pld(q.sel[8] + i);
+        }
+        if (q.mask & 4u) {  // fixed-base scalar mul
+            const fr_t k = sqr(q.fs), k2 = sqr(k), k3 = k2 * k;
+            const fr_t xb = pld(q.sel[1] + i), yb = pld(q.sel[2] + i);
+            const fr_t bit = dn - dbl(d);
+            const fr_t bitc = bit * (bit - one) * (bit + one);
+            const fr_t ya = sqr(bit) * (yb - one) + one;
+            const fr_t xa = bit * xb;
+            const fr_t xyc = (bit * qc - c) * k;
+            const fr_t tt = c * a * b * q.edwards_d;
+            const fr_t xacc = ((an + an * tt) - (a * ya + b * xa)) * k2;
+            const fr_t yacc = ((bn - bn * tt) - (b * ya + a * xa)) * k3;
+            t = t + (bitc + xacc + yacc + xyc) * q.fs * pld(q.sel[9] + i);
+        }
+        if (q.mask & 8u) {  // variable-base addition
+            const fr_t k = sqr(q.vs);
+            const fr_t y1x2 = b * c, y1y2 = b * d, x1x2 = a * c;
+            const fr_t tt = q.edwards_d * dn * y1x2;
+            const fr_t xyc = a * d - dn;
+            const fr_t x3c = ((dn + y1x2) - (an + an * tt)) * k;
+            const fr_t y3c = ((y1y2 + x1x2) - (bn - bn * tt)) * sqr(k);
+            t = t + (xyc + x3c + y3c) * q.vs * pld(q.sel[10] + i);
+        }
+    }
+    // permutation argument (quotient_poly.rs:245-261)
+    {
+        const fr_t z = pld(q.z + i), zn = pld(q.z + in), x = pld(q.linear + i);
+        const fr_t ag = a + q.gamma, bg = b + q.gamma, cg = c + q.gamma, dg = d + q.gamma;
+        fr_t ident = (ag + q.beta * x) * (bg + q.bk1 * x) * ((cg + q.bk2 * x) * (dg + q.bk3 * x)) * z;
+        fr_t copy = (ag + q.beta * pld(q.sigma[0] + i)) * (bg + q.beta * pld(q.sigma[1] + i)) *
+                    ((cg + q.beta * pld(q.sigma[2] + i)) * (dg + q.beta * pld(q.sigma[3] + i))) * zn;
+        t = t + (ident - copy) * q.alpha + (z - one) * pld(q.l1 + i);
+    }
+    pst(q.out + i, t * q.zh_inv[i & 7]);
+}
+
+// ------------------------------------------------------------------ batched evaluation
+static constexpr unsigned EV_MAX = 16;   // polynomials per launch
+static constexpr unsigned EV_L = 8;      // coefficients per thread
+static constexpr unsigned EV_T = 256;    // threads per block
+
+struct EvalArgs {
+    const fr_t* p[EV_MAX];
+    uint64_t len[EV_MAX];
+    fr_t pw[28];  // point^(2^j)
+    unsigned nblocks;
+    fr_t* partial;  // [count][nblocks]
+};
+
+// block b of polynomial y: value of coefficients [b*2048, (b+1)*2048) relative to the block start
+__global__ void __launch_bounds__(EV_T) eval_block_kernel(const __grid_constant__ EvalArgs a) {
+    __shared__ fr_t sm[EV_T];
+    const unsigned y = blockIdx.y, tid = threadIdx.x;
+    const fr_t* p = a.p[y];
+    const size_t len = a.len[y];
+    const size_t lo = ((size_t)blockIdx.x * EV_T + tid) * EV_L;
+    fr_t s = fr_t::zero();
+    if (lo < len) {
+        const size_t hi = lo + EV_L < len ? lo + EV_L : len;
+        s = pld(p + hi - 1);
+        for (size_t i = hi - 1; i-- > lo;) s = s * a.pw[0] + pld(p + i);
+    }
+    sm[tid] = s;
+    __syncthreads();
+    unsigned lvl = 3;  // log2(EV_L)
+    for (unsigned st = 1; st < EV_T; st <<= 1, lvl++) {
+        if ((tid & (2 * st - 1)) == 0) sm[tid] = sm[tid] + a.pw[lvl] * sm[tid + st];
+        __syncthreads();
+    }
+    if (tid == 0) pst(a.partial + (size_t)y * a.nblocks + blockIdx.x, sm[0]);
+}
+
+// one block per polynomial: sum_b partial[b] * X^b with X = point^2048
+__global__ void __launch_bounds__(EV_T) eval_final_kernel(const __grid_constant__ EvalArgs a, fr_t* out) {
+    __shared__ fr_t sm[EV_T];
+    const unsigned y = blockIdx.x, tid = threadIdx.x;
+    const fr_t* part = a.partial + (size_t)y * a.nblocks;
+    // thread t owns blocks [t*per, (t+1)*per): per is a power of two so X^per is in the table
+    unsigned per_log = 0;
+    while (((size_t)EV_T << per_log) < a.nblocks) per_log++;
+    const size_t per = (size_t)1 << per_log;
+    const size_t lo = (size_t)tid * per;
+    fr_t s = fr_t::zero();
+    if (lo < a.nblocks) {
+        const size_t hi = lo + per < a.nblocks ? lo + per : a.nblocks;
+        s = pld(part + hi - 1);
+        for (size_t i = hi - 1; i-- > lo;) s = s * a.pw[11] + pld(part + i);
+    }
+    sm[tid] = s;
+    __syncthreads();
+    unsigned lvl = 11 + per_log;
+    for (unsigned st = 1; st < EV_T; st <<= 1, lvl++) {
+        if ((tid & (2 * st - 1)) == 0) sm[tid] = sm[tid] + a.pw[lvl < 28 ? lvl : 27] * sm[tid + st];
+        __syncthreads();
+    }
+    if (tid == 0) pst(out + y, sm[0]);
+}
+
+// ------------------------------------------------------------------ linear combination
+static constexpr unsigned LC_MAX = 16;
+struct LincombArgs {
+    const fr_t* p[LC_MAX];
+    uint64_t len[LC_MAX];
+    fr_t s[LC_MAX];
+    unsigned count;
+    size_t n;
+    fr_t* out;
+};
+
+__global__ void __launch_bounds__(256) lincomb_kernel(const __grid_constant__ LincombArgs a) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    fr_t acc = fr_t::zero();
+    for (unsigned k = 0; k < a.count; k++)
+        if (i < a.len[k]) acc = acc + a.s[k] * pld(a.p[k] + i);
+    pst(a.out + i, acc);
+}
+
+// ------------------------------------------------------------------ division by (X - point)
+// h_j = sum_{i >= j} c_i point^(i-j);  quotient q_j = h_{j+1}  (ruffini, remainder dropped)
+static constexpr unsigned DV_L = 16;
+
+__global__ void div_chunk_kernel(const fr_t* c, size_t n, fr_t point, fr_t* chunk) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = t * DV_L;
+    if (lo >= n) return;
+    size_t hi = lo + DV_L < n ? lo + DV_L : n;
+    fr_t s = pld(c + hi - 1);
+    for (size_t i = hi - 1; i-- > lo;) s = s * point + pld(c + i);
+    pst(chunk + t, s);
+}
+
+// single block: chunk[t] <- sum_{t' > t} chunk[t'] X^(t'-t-1), X = point^DV_L  (carry into chunk t)
+__global__ void __launch_bounds__(512) div_carry_kernel(fr_t* chunk, size_t nc, fr_t X) {
+    __shared__ fr_t sm[512];
+    __shared__ fr_t xp[512];
+    const unsigned T = blockDim.x, tid = threadIdx.x;
+    const size_t per = (nc + T - 1) / T;
+    // reversed logical order: j = 0 is the top chunk
+    const size_t lo = (size_t)tid * per, hi = lo + per < nc ? lo + per : nc;
+    // local value of this thread's span relative to the span's lowest chunk, and X^(span length)
+    fr_t s = fr_t::zero(), xl = fr_t::one();
+    for (size_t j = lo; j < hi; j++) { s = s * X + pld(chunk + (nc - 1 - j)); xl = xl * X; }
+    sm[tid] = s;
+    xp[tid] = xl;
+    __syncthreads();
+    // inclusive scan over threads of the affine maps carry -> carry * xl + s
+    for (unsigned st = 1; st < T; st <<= 1) {
+        fr_t v = sm[tid], w = xp[tid];
+        if (tid >= st) { v = sm[tid - st] * w + v; w = xp[tid - st] * w; }
+        __syncthreads();
+        sm[tid] = v;
+        xp[tid] = w;
+        __syncthreads();
+    }
+    fr_t run = tid ? sm[tid - 1] : fr_t::zero();
+    for (size_t j = lo; j < hi; j++) {
+        const size_t idx = nc - 1 - j;
+        fr_t cv = pld(chunk + idx);
+        pst(chunk + idx, run);
+        run = run * X + cv;
+    }
+}
+
+__global__ void div_apply_kernel(const fr_t* c, size_t n, fr_t point, const fr_t* carry, fr_t* out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = t * DV_L;
+    if (lo >= n) return;
+    size_t hi = lo + DV_L < n ? lo + DV_L : n;
+    fr_t h = pld(carry + t);  // h_{hi}
+    for (size_t i = hi; i-- > lo;) {
+        if (i + 1 < n) pst(out + i, h);  // q_i = h_{i+1}
+        h = h * point + pld(c + i);
+    }
+}
+
+// ------------------------------------------------------------------ scratch
+static int scratch(zkp_ctx* ctx, size_t n, fr_t** out) {
+    if (ctx->prover_scratch_n < n) {
+        if (ctx->prover_scratch) cudaFree(ctx->prover_scratch);
+        ctx->prover_scratch = nullptr;
+        ctx->prover_scratch_n = 0;
+        ZKP_CUDA(ctx, cudaMalloc(&ctx->prover_scratch, n * sizeof(fr_t)));
+        ctx->prover_scratch_n = n;
+    }
+    *out = ctx->prover_scratch;
+    return ZKP_OK;
+}
+
+void prover_free(zkp_ctx* ctx) {
+    if (ctx->prover_scratch) cudaFree(ctx->prover_scratch);
+    ctx->prover_scratch = nullptr;
+    ctx->prover_scratch_n = 0;
+}
+
+static inline unsigned blocks_for(size_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace zkp
+
+using namespace zkp;
+
+extern "C" {
+
+int zkp_ntt_ref_dev(zkp_ctx* ctx, zkp_poly_ref in, zkp_buf* out, size_t out_off, unsigned k, int inverse,
+                    int coset) {
+    if (!ctx || !out || !CHECK_REF(in) || k > 28) return ZKP_ERR_INVALID;
+    const size_t n = (size_t)1 << k;
+    if (in.len > n || out_off + n > out->n) return ZKP_ERR_INVALID;
+    return ntt_run(ctx, in.buf->d + in.off, 0, in.len, out->d + out_off, 0, k, inverse != 0, coset != 0, 1);
+}
+
+int zkp_buf_fill(zkp_ctx* ctx, zkp_buf* buf, size_t off, size_t n, const uint64_t value[4]) {
+    if (!ctx || !buf || !value || off + n > buf->n) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    if (!n) return ZKP_OK;
+    fill_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(buf->d + off, n, fr_from_host(value));
+    ZKP_LAUNCHED(ctx);
+    return ZKP_OK;
+}
+
+int zkp_poly_blind_dev(zkp_ctx* ctx, zkp_buf* buf, size_t off, size_t n, const uint64_t* blinders, unsigned count) {
+    if (!ctx || !buf || !blinders || count == 0 || count > 3 || off + n + count > buf->n || count > n)
+        return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    fr_t b[3] = {fr_t::zero(), fr_t::zero(), fr_t::zero()};
+    for (unsigned i = 0; i < count; i++) b[i] = fr_from_host(blinders + 4 * i);
+    blind_kernel<<<1, 32, 0, ctx->stream>>>(buf->d + off, n, b[0], b[1], b[2], count);
+    ZKP_LAUNCHED(ctx);
+    return ZKP_OK;
+}
+
+int zkp_perm_lagrange_dev(zkp_ctx* ctx, unsigned k, const uint32_t* enc, size_t n, const zkp_buf* roots,
+                          zkp_buf* out, size_t out_off) {
+    if (!ctx || !enc || !roots || !out || k > 28 || n > ((size_t)1 << k) || roots->n < ((size_t)1 << k) ||
+        out_off + n > out->n || k > 30)
+        return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    uint32_t* d_enc = nullptr;
+    ZKP_CUDA(ctx, cudaMalloc(&d_enc, n * sizeof(uint32_t)));
+    cudaError_t e = cudaMemcpyAsync(d_enc, enc, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(d_enc); return cuda_fail(ctx, e, "h2d", __FILE__, __LINE__); }
+    perm_lagrange_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(d_enc, n, roots->d, from_u64<FrParams>(7),
+                                                                     from_u64<FrParams>(13), from_u64<FrParams>(17),
+                                                                     out->d + out_off);
+    ctx->launches++;
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_enc);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "perm_lagrange", __FILE__, __LINE__);
+    return ZKP_OK;
+}
+
+int zkp_perm_z_dev(zkp_ctx* ctx, size_t n, const zkp_poly_ref wires[4], const zkp_poly_ref sigmas[4],
+                   const zkp_buf* roots, const uint64_t beta[4], const uint64_t gamma[4], zkp_buf* out,
+                   size_t out_off) {
+    if (!ctx || !wires || !sigmas || !roots || !beta || !gamma || !out || n == 0 || roots->n < n ||
+        out_off + n > out->n)
+        return ZKP_ERR_INVALID;
+    for (int j = 0; j < 4; j++)
+        if (!CHECK_REF(wires[j]) || !CHECK_REF(sigmas[j]) || wires[j].len < n || sigmas[j].len < n)
+            return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    const size_t nc = (n + SCAN_L - 1) / SCAN_L;
+    fr_t* s;
+    if ((rc = scratch(ctx, 4 * n + 2 * nc + 1, &s))) return rc;
+    fr_t *num = s, *den = s + n, *P = s + 2 * n, *S = s + 3 * n, *c1 = s + 4 * n, *c2 = c1 + nc, *inv = c2 + nc;
+    PermArgs a;
+    for (int j = 0; j < 4; j++) {
+        a.w[j] = wires[j].buf->d + wires[j].off;
+        a.sigma[j] = sigmas[j].buf->d + sigmas[j].off;
+    }
+    a.roots = roots->d;
+    a.beta = fr_from_host(beta);
+    a.gamma = fr_from_host(gamma);
+    a.bk[0] = a.beta;
+    a.bk[1] = a.beta * from_u64<FrParams>(7);
+    a.bk[2] = a.beta * from_u64<FrParams>(13);
+    a.bk[3] = a.beta * from_u64<FrParams>(17);
+    a.n = n; a.num = num; a.den = den;
+    cudaStream_t st = ctx->stream;
+    ProfScope prof(ctx, "perm_z");
+    perm_numden_kernel<<<blocks_for(n, 128), 128, 0, st>>>(a);
+    ZKP_LAUNCHED(ctx);
+    const unsigned cb = blocks_for(nc, 128);
+    prod_chunk_kernel<<<cb, 128, 0, st>>>(num, n, c1);
+    ZKP_LAUNCHED(ctx);
+    prod_chunk_kernel<<<cb, 128, 0, st>>>(den, n, c2);
+    ZKP_LAUNCHED(ctx);
+    prod_carry_kernel<<<1, 1024, 0, st>>>(c1, nc, 0);
+    ZKP_LAUNCHED(ctx);
+    prod_carry_kernel<<<1, 1024, 0, st>>>(c2, nc, 1);
+    ZKP_LAUNCHED(ctx);
+    prod_apply_kernel<<<cb, 128, 0, st>>>(num, n, c1, 0, P);
+    ZKP_LAUNCHED(ctx);
+    prod_apply_kernel<<<cb, 128, 0, st>>>(den, n, c2, 1, S);
+    ZKP_LAUNCHED(ctx);
+    fr_inverse_kernel<<<1, 1, 0, st>>>(S, inv);
+    ZKP_LAUNCHED(ctx);
+    perm_z_combine_kernel<<<blocks_for(n, 128), 128, 0, st>>>(P, S, inv, n, out->d + out_off);
+    ZKP_LAUNCHED(ctx);
+    return ZKP_OK;
+}
+
+int zkp_quotient_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* q, zkp_buf* out, size_t out_off) {
+    if (!ctx || !q || !out || k8 < 3 || k8 > 28) return ZKP_ERR_INVALID;
+    const size_t n8 = (size_t)1 << k8;
+    if (out_off + n8 > out->n) return ZKP_ERR_INVALID;
+    QuotArgs a;
+    auto ptr = [&](const zkp_poly_ref& r, const fr_t** p) {
+        if (!CHECK_REF(r) || r.len < n8) return false;
+        *p = r.buf->d + r.off;
+        return true;
+    };
+    bool ok = true;
+    for (int j = 0; j < 4; j++) ok = ok && ptr(q->wires[j], &a.w[j]) && ptr(q->sigma[j], &a.sigma[j]);
+    ok = ok && ptr(q->z, &a.z) && ptr(q->pi, &a.pi) && ptr(q->l1, &a.l1) && ptr(q->linear, &a.linear);
+    for (int j = 0; j < 11; j++) ok = ok && ptr(q->sel[j], &a.sel[j]);
+    if (!ok) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    a.alpha = fr_from_host(q->challenges[0]);
+    a.beta = fr_from_host(q->challenges[1]);
+    a.gamma = fr_from_host(q->challenges[2]);
+    a.rs = fr_from_host(q->challenges[3]);
+    a.ls = fr_from_host(q->challenges[4]);
+    a.fs = fr_from_host(q->challenges[5]);
+    a.vs = fr_from_host(q->challenges[6]);
+    a.bk1 = a.beta * from_u64<FrParams>(7);
+    a.bk2 = a.beta * from_u64<FrParams>(13);
+    a.bk3 = a.beta * from_u64<FrParams>(17);
+    // JubJub d = -(10240 / 10241)
+    a.edwards_d = neg(from_u64<FrParams>(10240) * inverse(from_u64<FrParams>(10241)));
+    for (int j = 0; j < 8; j++) a.zh_inv[j] = fr_from_host(q->zh_inv[j]);
+    a.mask = q->widget_mask;
+    a.n8 = n8;
+    a.out = out->d + out_off;
+    ProfScope prof(ctx, "quotient");
+    quotient_kernel<<<blocks_for(n8, 128), 128, 0, ctx->stream>>>(a);
+    ZKP_LAUNCHED(ctx);
+    return ZKP_OK;
+}
+
+int zkp_poly_eval_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, unsigned count, const uint64_t point[4],
+                      uint64_t* out) {
+    if (!ctx || !polys || !point || !out || count == 0 || count > EV_MAX) return ZKP_ERR_INVALID;
+    size_t maxlen = 0;
+    for (unsigned i = 0; i < count; i++) {
+        if (!CHECK_REF(polys[i])) return ZKP_ERR_INVALID;
+        if (polys[i].len > maxlen) maxlen = polys[i].len;
+    }
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    EvalArgs a;
+    memset(&a, 0, sizeof a);
+    for (unsigned i = 0; i < count; i++) { a.p[i] = polys[i].buf->d + polys[i].off; a.len[i] = polys[i].len; }
+    a.pw[0] = fr_from_host(point);
+    for (int j = 1; j < 28; j++) a.pw[j] = sqr(a.pw[j - 1]);
+    const size_t per_block = (size_t)EV_T * EV_L;
+    a.nblocks = (unsigned)((maxlen + per_block - 1) / per_block);
+    if (a.nblocks == 0) a.nblocks = 1;
+    if ((size_t)a.nblocks > ((size_t)1 << 16)) return ZKP_ERR_INVALID;  // 2^27 coefficients
+    fr_t* s;
+    if ((rc = scratch(ctx, (size_t)count * a.nblocks + count, &s))) return rc;
+    a.partial = s;
+    fr_t* res = s + (size_t)count * a.nblocks;
+    ProfScope prof(ctx, "poly_eval");
+    eval_block_kernel<<<dim3(a.nblocks, count), EV_T, 0, ctx->stream>>>(a);
+    ZKP_LAUNCHED(ctx);
+    eval_final_kernel<<<count, EV_T, 0, ctx->stream>>>(a, res);
+    ZKP_LAUNCHED(ctx);
+    fr_t* h = reinterpret_cast<fr_t*>(ctx->pinned);
+    ZKP_CUDA(ctx, cudaMemcpyAsync(h, res, count * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(out, h, count * sizeof(fr_t));
+    return ZKP_OK;
+}
+
+int zkp_poly_lincomb_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, const uint64_t* scalars, unsigned count,
+                         zkp_buf* out, size_t out_off, size_t out_len) {
+    if (!ctx || !polys || !scalars || !out || count == 0 || count > LC_MAX || out_off + out_len > out->n)
+        return ZKP_ERR_INVALID;
+    LincombArgs a;
+    memset(&a, 0, sizeof a);
+    for (unsigned i = 0; i < count; i++) {
+        if (!CHECK_REF(polys[i])) return ZKP_ERR_INVALID;
+        a.p[i] = polys[i].buf->d + polys[i].off;
+        a.len[i] = polys[i].len;
+        a.s[i] = fr_from_host(scalars + 4 * i);
+    }
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    if (!out_len) return ZKP_OK;
+    a.count = count; a.n = out_len; a.out = out->d + out_off;
+    ProfScope prof(ctx, "poly_lincomb");
+    lincomb_kernel<<<blocks_for(out_len, 256), 256, 0, ctx->stream>>>(a);
+    ZKP_LAUNCHED(ctx);
+    return ZKP_OK;
+}
+
+int zkp_poly_div_linear_dev(zkp_ctx* ctx, zkp_poly_ref in, const uint64_t point[4], zkp_buf* out, size_t out_off) {
+    if (!ctx || !point || !out || !CHECK_REF(in) || in.len < 1 || out_off + in.len - 1 > out->n)
+        return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    const size_t n = in.len;
+    if (n == 1) return ZKP_OK;
+    const size_t nc = (n + DV_L - 1) / DV_L;
+    fr_t* s;
+    if ((rc = scratch(ctx, nc, &s))) return rc;
+    const fr_t pt = fr_from_host(point);
+    const fr_t X = pow_u64(pt, DV_L);
+    const fr_t* c = in.buf->d + in.off;
+    cudaStream_t st = ctx->stream;
+    ProfScope prof(ctx, "poly_div");
+    div_chunk_kernel<<<blocks_for(nc, 128), 128, 0, st>>>(c, n, pt, s);
+    ZKP_LAUNCHED(ctx);
+    div_carry_kernel<<<1, 512, 0, st>>>(s, nc, X);
+    ZKP_LAUNCHED(ctx);
+    div_apply_kernel<<<blocks_for(nc, 128), 128, 0, st>>>(c, n, pt, s, out->d + out_off);
+    ZKP_LAUNCHED(ctx);
+    return ZKP_OK;
+}
+
+}  // extern "C"

@@ -62,6 +62,33 @@ SIGNATURES = {
     "zkp_msm_set_window": (_int, [_vp, _uint]),
 }
 
+
+
+class PolyRef(ctypes.Structure):
+    """``zkp_poly_ref``: buf[off .. off+len)."""
+    _fields_ = [("buf", _vp), ("off", _sz), ("len", _sz)]
+
+
+class QuotientArgs(ctypes.Structure):
+    """``zkp_quotient_args``."""
+    _fields_ = [("wires", PolyRef * 4), ("z", PolyRef), ("pi", PolyRef), ("l1", PolyRef),
+                ("sel", PolyRef * 11), ("sigma", PolyRef * 4), ("linear", PolyRef),
+                ("challenges", (ctypes.c_uint64 * 4) * 7), ("zh_inv", (ctypes.c_uint64 * 4) * 8),
+                ("widget_mask", ctypes.c_uint32)]
+
+
+SIGNATURES.update({
+    "zkp_ntt_ref_dev": (_int, [_vp, PolyRef, _vp, _sz, _uint, _int, _int]),
+    "zkp_buf_fill": (_int, [_vp, _vp, _sz, _sz, _vp]),
+    "zkp_poly_blind_dev": (_int, [_vp, _vp, _sz, _sz, _vp, _uint]),
+    "zkp_perm_lagrange_dev": (_int, [_vp, _uint, _vp, _sz, _vp, _vp, _sz]),
+    "zkp_perm_z_dev": (_int, [_vp, _sz, ctypes.POINTER(PolyRef), ctypes.POINTER(PolyRef), _vp, _vp, _vp, _vp, _sz]),
+    "zkp_quotient_dev": (_int, [_vp, _uint, ctypes.POINTER(QuotientArgs), _vp, _sz]),
+    "zkp_poly_eval_dev": (_int, [_vp, ctypes.POINTER(PolyRef), _uint, _vp, _vp]),
+    "zkp_poly_lincomb_dev": (_int, [_vp, ctypes.POINTER(PolyRef), _vp, _uint, _vp, _sz, _sz]),
+    "zkp_poly_div_linear_dev": (_int, [_vp, PolyRef, _vp, _vp, _sz]),
+})
+
 _lib = None
 
 
@@ -189,7 +216,11 @@ class Context:
         return buf
 
     def ntt_dev(self, src, len_in, dst, k, inverse=False, coset=False):
-        self.check(self.lib.zkp_ntt_dev(self.h, src.h, len_in, dst.h, k, int(inverse), int(coset)))
+        """src / dst: DeviceBuffer or BufferView."""
+        sb, so = (src.buf, src.off) if isinstance(src, BufferView) else (src, 0)
+        db, do = (dst.buf, dst.off) if isinstance(dst, BufferView) else (dst, 0)
+        self.check(self.lib.zkp_ntt_ref_dev(self.h, PolyRef(sb.h, so, len_in), db.h, do, k, int(inverse),
+                                            int(coset)))
 
     def ntt_dev_batch(self, src, in_stride, len_in, dst, out_stride, k, inverse, coset, batch):
         self.check(self.lib.zkp_ntt_dev_batch(self.h, src.h, in_stride, len_in, dst.h, out_stride, k,
@@ -236,6 +267,50 @@ class Context:
     def set_msm_window(self, c):
         self.check(self.lib.zkp_msm_set_window(self.h, c))
 
+    # ---- prover rounds (device-resident)
+    @staticmethod
+    def ref(buf, off=0, n=None):
+        return PolyRef(buf.h, off, (buf.n - off) if n is None else n)
+
+    def fill(self, buf, off, n, value):
+        v = np.ascontiguousarray(value, dtype=np.uint64).reshape(4)
+        self.check(self.lib.zkp_buf_fill(self.h, buf.h, off, n, _ptr(v)))
+
+    def poly_blind(self, buf, off, n, blinders):
+        b = as_fr_array(blinders)
+        self.check(self.lib.zkp_poly_blind_dev(self.h, buf.h, off, n, _ptr(b), b.shape[0]))
+
+    def perm_lagrange(self, k, enc, roots, out, out_off=0):
+        enc = np.ascontiguousarray(enc, dtype=np.uint32)
+        self.check(self.lib.zkp_perm_lagrange_dev(self.h, k, _ptr(enc), enc.shape[0], roots.h, out.h, out_off))
+
+    def perm_z(self, n, wires, sigmas, roots, beta, gamma, out, out_off=0):
+        w = (PolyRef * 4)(*wires)
+        s = (PolyRef * 4)(*sigmas)
+        b = np.ascontiguousarray(beta, dtype=np.uint64).reshape(4)
+        g = np.ascontiguousarray(gamma, dtype=np.uint64).reshape(4)
+        self.check(self.lib.zkp_perm_z_dev(self.h, n, w, s, roots.h, _ptr(b), _ptr(g), out.h, out_off))
+
+    def quotient(self, k8, args, out, out_off=0):
+        self.check(self.lib.zkp_quotient_dev(self.h, k8, ctypes.byref(args), out.h, out_off))
+
+    def poly_eval(self, refs, point):
+        arr = (PolyRef * len(refs))(*refs)
+        pt = np.ascontiguousarray(point, dtype=np.uint64).reshape(4)
+        out = np.zeros((len(refs), 4), dtype=np.uint64)
+        self.check(self.lib.zkp_poly_eval_dev(self.h, arr, len(refs), _ptr(pt), _ptr(out)))
+        return out
+
+    def poly_lincomb(self, refs, scalars, out, out_off, out_len):
+        arr = (PolyRef * len(refs))(*refs)
+        sc = as_fr_array(scalars)
+        assert sc.shape[0] == len(refs)
+        self.check(self.lib.zkp_poly_lincomb_dev(self.h, arr, _ptr(sc), len(refs), out.h, out_off, out_len))
+
+    def poly_div_linear(self, ref, point, out, out_off=0):
+        pt = np.ascontiguousarray(point, dtype=np.uint64).reshape(4)
+        self.check(self.lib.zkp_poly_div_linear_dev(self.h, ref, _ptr(pt), out.h, out_off))
+
 
 def fft_constant(k, kind):
     lib = load_library()
@@ -244,6 +319,14 @@ def fft_constant(k, kind):
     if rc:
         raise ZkpError(rc)
     return out
+
+
+class BufferView:
+    """buf[off .. off+n): a polynomial living inside a larger device buffer."""
+
+    def __init__(self, buf, off=0, n=None):
+        self.buf, self.off = buf, off
+        self.n = (buf.n - off) if n is None else n
 
 
 class DeviceBuffer:

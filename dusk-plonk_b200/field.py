@@ -1,0 +1,62 @@
+"""Host-side Fr / Fq / G1 encodings at the C-ABI boundary (Python ints <-> Montgomery limbs).
+
+``BlsScalar([u64; 4])`` is little-endian Montgomery with R = 2^256 (pinned by MINUS_ONE,
+src/lib.rs:583-588); Fq is 6 x u64 with R = 2^384; G1 affine is x || y with x = y = 0 for
+the identity (include/zkp_b200.h).  Challenges, blinders and evaluations cross the boundary
+through these helpers; bulk vectors stay on the device."""
+import numpy as np
+
+R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+P_MOD = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+_FR_R = (1 << 256) % R_MOD
+_FR_RINV = pow(_FR_R, -1, R_MOD)
+_FQ_RINV = pow((1 << 384) % P_MOD, -1, P_MOD)
+K1, K2, K3 = 7, 13, 17  # src/permutation.rs:28-30
+
+
+def fr_to_mont(vals):
+    """iterable of canonical ints -> (n, 4) uint64 Montgomery limbs."""
+    vals = list(vals)
+    buf = b"".join(((int(v) % R_MOD) * _FR_R % R_MOD).to_bytes(32, "little") for v in vals)
+    return np.frombuffer(buf, dtype="<u8").reshape(len(vals), 4).copy()
+
+
+def fr_to_mont1(v):
+    return fr_to_mont([v])[0]
+
+
+def fr_from_mont(arr):
+    arr = np.ascontiguousarray(np.asarray(arr, dtype="<u8").reshape(-1, 4))
+    raw = arr.tobytes()
+    return [int.from_bytes(raw[i * 32:(i + 1) * 32], "little") * _FR_RINV % R_MOD for i in range(arr.shape[0])]
+
+
+def fr_column_to_mont(col, n):
+    """Selector / wire column (list of ints or integer ndarray) -> (n, 4) Montgomery limbs,
+    zero padded; repeated values are converted once."""
+    out = np.zeros((n, 4), dtype=np.uint64)
+    if isinstance(col, np.ndarray) and col.dtype != object:
+        uniq, inv = np.unique(col, return_inverse=True)
+        table = fr_to_mont([int(u) for u in uniq])
+        out[:len(col)] = table[inv]
+        return out
+    cache = {}
+    idx = np.empty(len(col), dtype=np.int64)
+    keys = []
+    for i, v in enumerate(col):
+        j = cache.get(v)
+        if j is None:
+            j = cache[v] = len(keys)
+            keys.append(v)
+        idx[i] = j
+    if keys:
+        out[:len(col)] = fr_to_mont(keys)[idx]
+    return out
+
+
+def g1_from_mont(xy):
+    """12 x uint64 Montgomery (x, y) -> (x, y) canonical ints, or None for the identity."""
+    raw = np.ascontiguousarray(np.asarray(xy, dtype="<u8").reshape(12)).tobytes()
+    x = int.from_bytes(raw[:48], "little") * _FQ_RINV % P_MOD
+    y = int.from_bytes(raw[48:], "little") * _FQ_RINV % P_MOD
+    return None if (x == 0 and y == 0) else (x, y)

@@ -3,7 +3,7 @@
 ``keypair.trim(additional_n)``, src/key.rs:82), backed by the CUDA MSM."""
 import numpy as np
 
-from .ffi import Context, DeviceBuffer, ZkpError, ZKP_ERR_DEGREE
+from .ffi import BufferView, Context, DeviceBuffer, ZkpError, ZKP_ERR_DEGREE
 from .poly_commit import Coefficients, Commitment
 
 
@@ -42,6 +42,8 @@ class PlonkParams:
         try:
             if isinstance(poly, DeviceBuffer):
                 return Commitment(self.ctx.commit_dev(self.srs, poly))
+            if isinstance(poly, BufferView):
+                return Commitment(self.ctx.commit_dev(self.srs, poly.buf, poly.off, poly.n))
             v = poly.v if isinstance(poly, Coefficients) else poly
             return Commitment(self.ctx.commit(self.srs, v))
         except ZkpError as e:

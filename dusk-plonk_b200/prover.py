@@ -1,0 +1,213 @@
+"""``Prover::create_proof`` with device-resident rounds (host mirror of ``src/prover.rs:67-474``).
+
+Round structure, transcript labels and commit order follow the reference line by line;
+everything between the transcript appends runs on the GPU through the C ABI and the
+polynomials never leave HBM.  Host <-> device traffic per proof: the witness upload
+(4n Fr), 11 affine commitments and 17 evaluations down, 8 challenges + 11 blinders up.
+"""
+import numpy as np
+
+from .field import R_MOD, K1, K2, K3, fr_from_mont, fr_to_mont, fr_to_mont1, g1_from_mont
+from .ffi import QuotientArgs, BufferView as _View
+from .composer import SELECTORS, SynthesizedCircuit, Plonk
+from .widgets import linearization_scalars
+
+_r = R_MOD
+EVAL_NAMES = ("a_eval", "b_eval", "c_eval", "d_eval", "a_next_eval", "b_next_eval", "d_next_eval",
+              "s_sigma_1_eval", "s_sigma_2_eval", "s_sigma_3_eval", "q_arith_eval", "q_c_eval",
+              "q_l_eval", "q_r_eval", "perm_eval", "r_poly_eval")
+COMM_NAMES = ("a_comm", "b_comm", "c_comm", "d_comm", "z_comm", "t_low_comm", "t_mid_comm",
+              "t_high_comm", "t_4_comm", "w_z_chall_comm", "w_z_chall_w_comm")
+
+
+class Proof:
+    """``Proof<P>`` (src/prover/proof.rs:38-66): 11 commitments + 16 evaluations, as affine
+    points ((x, y) canonical ints or None) and canonical ints."""
+
+    def __init__(self):
+        self.evaluations = {}
+
+    def __eq__(self, o):
+        return all(getattr(self, c) == getattr(o, c) for c in COMM_NAMES) and \
+            dict(self.evaluations) == dict(o.evaluations)
+
+
+class Prover:
+    def __init__(self, ctx, keypair, prover_key, verifier_key, transcript, pi_indexes):
+        self.ctx = ctx
+        self.keypair = keypair
+        self.prover_key = prover_key
+        self.verifier_key = verifier_key
+        self.transcript = transcript
+        self.size = prover_key.n
+        self.pi_indexes = list(pi_indexes)
+        self._ws = None
+
+    # ---------------------------------------------------------------- workspace
+    def _workspace(self):
+        if self._ws is None:
+            n, c = self.size, self.ctx
+            ws = {"W": c.alloc(4 * n), "Z": c.alloc(n), "PI": c.alloc(n), "L1": c.alloc(n),
+                  "wp": [c.alloc(n + 2) for _ in range(4)], "zp": c.alloc(n + 3),
+                  "e8": [c.alloc(8 * n) for _ in range(4)], "z8": c.alloc(8 * n), "pi8": c.alloc(8 * n),
+                  "l18": c.alloc(8 * n), "T": c.alloc(8 * n), "R": c.alloc(n + 3),
+                  "AGG": c.alloc(5 * n), "WZ": c.alloc(5 * n), "SAGG": c.alloc(n + 3), "WZW": c.alloc(n + 3)}
+            self._ws = ws
+        return self._ws
+
+    def _commit(self, buf, off=0, n=None):
+        return g1_from_mont(self.keypair.commit(_View(buf, off, n)).xy)
+
+    # ---------------------------------------------------------------- create_proof
+    def create_proof(self, blinders, circuit, trace=None):
+        """``blinders``: the 11 scalars ``blind`` draws from the RNG, in draw order
+        (2 each for a, b, o, d, then 3 for z; src/prover.rs:126-129,193).  ``circuit`` is a
+        synthesized composer / ``SynthesizedCircuit`` / ``WitnessAssignment``.  Raises
+        ``plonk_params.Error`` where the reference returns ``Err``.  Returns
+        (Proof, public_inputs)."""
+        ctx, pk, n, k = self.ctx, self.prover_key, self.size, self.prover_key.k
+        ref = ctx.ref
+        ws = self._workspace()
+        T = trace if trace is not None else None
+        if isinstance(circuit, Plonk):
+            circuit = SynthesizedCircuit.from_composer(circuit)
+        wa = circuit if isinstance(circuit, WitnessAssignment) else WitnessAssignment.from_circuit(circuit, n)
+        tr = self.transcript.clone()
+        for pi in wa.pi_values:
+            tr.append_scalar(b"pi", pi)
+        bl = fr_to_mont(blinders)
+        proof = Proof()
+
+        # round 1: wires -> iNTT -> blind -> commit (src/prover.rs:107-158)
+        W = ws["W"]
+        W.upload(wa.wires_mont.reshape(4 * n, 4))
+        for j in range(4):
+            ctx.ntt_dev(_View(W, j * n, n), n, ws["wp"][j], k, True, False)
+            ctx.poly_blind(ws["wp"][j], 0, n, bl[2 * j:2 * j + 2])
+        comms = [self._commit(ws["wp"][j]) for j in range(4)]
+        proof.a_comm, proof.b_comm, proof.c_comm, proof.d_comm = comms
+        for lab, c in zip((b"a_w", b"b_w", b"c_w", b"d_w"), comms):
+            tr.append_commitment(lab, c)
+
+        # round 2: permutation accumulator (src/prover.rs:160-199)
+        beta = tr.challenge_scalar(b"beta")
+        tr.append_scalar(b"beta", beta)
+        gamma = tr.challenge_scalar(b"gamma")
+        ctx.perm_z(n, [ref(W, j * n, n) for j in range(4)], [ref(s, 0, n) for s in pk.sigma_evals], pk.roots,
+                   fr_to_mont1(beta), fr_to_mont1(gamma), ws["Z"])
+        ctx.ntt_dev(ws["Z"], n, ws["zp"], k, True, False)
+        ctx.poly_blind(ws["zp"], 0, n, bl[8:11])
+        proof.z_comm = self._commit(ws["zp"])
+        tr.append_commitment(b"z", proof.z_comm)
+
+        # round 3: quotient on the 8n coset (src/prover.rs:201-287, quotient_poly.rs)
+        alpha = tr.challenge_scalar(b"alpha")
+        rs = tr.challenge_scalar(b"range separation challenge")
+        ls = tr.challenge_scalar(b"logic separation challenge")
+        fs = tr.challenge_scalar(b"fixed base separation challenge")
+        vs = tr.challenge_scalar(b"variable base separation challenge")
+        ch7 = (alpha, beta, gamma, rs, ls, fs, vs)
+        PI = ws["PI"]
+        PI.upload(wa.dense_pi_mont)
+        ctx.ntt_dev(PI, n, PI, k, True, False)
+        k8, n8 = k + 3, 8 * n
+        for j in range(4):
+            ctx.ntt_dev(ws["wp"][j], n + 2, ws["e8"][j], k8, False, True)
+        ctx.ntt_dev(ws["zp"], n + 3, ws["z8"], k8, False, True)
+        ctx.ntt_dev(PI, n, ws["pi8"], k8, False, True)
+        # L1 * alpha^2: idft of (alpha^2, 0, ..) has every coefficient alpha^2 / n (quotient_poly.rs:264-272)
+        ctx.fill(ws["L1"], 0, n, fr_to_mont1(alpha * alpha % _r * pow(n, -1, _r) % _r))
+        ctx.ntt_dev(ws["L1"], n, ws["l18"], k8, False, True)
+        qa = QuotientArgs()
+        for j in range(4):
+            qa.wires[j] = ref(ws["e8"][j], 0, n8)
+            qa.sigma[j] = ref(pk.eval8["s_sigma_%d" % (j + 1)], 0, n8)
+        qa.z, qa.pi, qa.l1 = ref(ws["z8"], 0, n8), ref(ws["pi8"], 0, n8), ref(ws["l18"], 0, n8)
+        for j, s in enumerate(SELECTORS):
+            qa.sel[j] = ref(pk.eval8[s], 0, n8)
+        qa.linear = ref(pk.eval8["linear"], 0, n8)
+        chm = fr_to_mont(ch7)
+        for j in range(7):
+            for l in range(4):
+                qa.challenges[j][l] = int(chm[j, l])
+        for j in range(8):
+            for l in range(4):
+                qa.zh_inv[j][l] = int(pk.zh_inv[j, l])
+        qa.widget_mask = pk.widget_mask
+        Tb = ws["T"]
+        ctx.quotient(k8, qa, Tb)
+        ctx.ntt_dev(Tb, n8, Tb, k8, True, True)   # coset_idft -> t coefficients
+        tc = [self._commit(Tb, 0, n), self._commit(Tb, n, n), self._commit(Tb, 2 * n, n),
+              self._commit(Tb, 3 * n, 5 * n)]
+        proof.t_low_comm, proof.t_mid_comm, proof.t_high_comm, proof.t_4_comm = tc
+        for lab, c in zip((b"t_low", b"t_mid", b"t_high", b"t_4"), tc):
+            tr.append_commitment(lab, c)
+
+        # round 4/5: evaluations, linearisation, openings (src/prover.rs:289-452)
+        zc = tr.challenge_scalar(b"z_challenge")
+        gen = self.verifier_key["generator"]
+        zw = zc * gen % _r
+        P = pk.poly
+        at_z = [ref(Tb, 0, n8)] + [ref(ws["wp"][j], 0, n + 2) for j in range(4)] + \
+            [ref(P[s], 0, n) for s in ("s_sigma_1", "s_sigma_2", "s_sigma_3", "q_arith", "q_c", "q_l", "q_r")]
+        e1 = fr_from_mont(ctx.poly_eval(at_z, fr_to_mont1(zc)))
+        e2 = fr_from_mont(ctx.poly_eval([ref(ws["wp"][0], 0, n + 2), ref(ws["wp"][1], 0, n + 2),
+                                         ref(ws["wp"][3], 0, n + 2), ref(ws["zp"], 0, n + 3)], fr_to_mont1(zw)))
+        ev = dict(zip(("a_eval", "b_eval", "c_eval", "d_eval", "s_sigma_1_eval", "s_sigma_2_eval", "s_sigma_3_eval",
+                       "q_arith_eval", "q_c_eval", "q_l_eval", "q_r_eval"), e1[1:]))
+        t_eval = e1[0]
+        ev["a_next_eval"], ev["b_next_eval"], ev["d_next_eval"], ev["perm_eval"] = e2
+        scal = linearization_scalars(n, ch7 + (zc,), ev)
+        lin_refs = [ref(ws["zp"], 0, n + 3) if nm == "z" else ref(P[nm], 0, n) for nm, _ in scal]
+        ctx.poly_lincomb(lin_refs, fr_to_mont([s for _, s in scal]), ws["R"], 0, n + 3)
+        ev["r_poly_eval"] = fr_from_mont(ctx.poly_eval([ref(ws["R"], 0, n + 3)], fr_to_mont1(zc)))[0]
+        for nm in ("a_eval", "b_eval", "c_eval", "d_eval", "a_next_eval", "b_next_eval", "d_next_eval",
+                   "s_sigma_1_eval", "s_sigma_2_eval", "s_sigma_3_eval", "q_arith_eval", "q_c_eval", "q_l_eval",
+                   "q_r_eval", "perm_eval"):
+            tr.append_scalar(nm.encode(), ev[nm])
+        tr.append_scalar(b"t_eval", t_eval)
+        tr.append_scalar(b"r_eval", ev["r_poly_eval"])
+        # W_z: (t_low + z^n t_mid + z^2n t_high + z^3n t_4) + v r + v^2 a + .. , divided by (X - z)
+        z_n = pow(zc, n, _r)
+        v1 = tr.challenge_scalar(b"v_challenge")
+        vp = [pow(v1, i, _r) for i in range(9)]
+        refs = [ref(Tb, 0, n), ref(Tb, n, n), ref(Tb, 2 * n, n), ref(Tb, 3 * n, 5 * n), ref(ws["R"], 0, n + 3)] + \
+            [ref(ws["wp"][j], 0, n + 2) for j in range(4)] + [ref(P[s], 0, n) for s in ("s_sigma_1", "s_sigma_2", "s_sigma_3")]
+        sc = [1, z_n, z_n * z_n % _r, pow(z_n, 3, _r)] + vp[1:]
+        ctx.poly_lincomb(refs, fr_to_mont(sc), ws["AGG"], 0, 5 * n)
+        ctx.poly_div_linear(ref(ws["AGG"], 0, 5 * n), fr_to_mont1(zc), ws["WZ"])
+        proof.w_z_chall_comm = self._commit(ws["WZ"], 0, 5 * n - 1)
+        v2 = tr.challenge_scalar(b"v_challenge")
+        refs = [ref(ws["zp"], 0, n + 3), ref(ws["wp"][0], 0, n + 2), ref(ws["wp"][1], 0, n + 2),
+                ref(ws["wp"][3], 0, n + 2)]
+        ctx.poly_lincomb(refs, fr_to_mont([pow(v2, i, _r) for i in range(4)]), ws["SAGG"], 0, n + 3)
+        ctx.poly_div_linear(ref(ws["SAGG"], 0, n + 3), fr_to_mont1(zw), ws["WZW"])
+        proof.w_z_chall_w_comm = self._commit(ws["WZW"], 0, n + 2)
+        proof.evaluations = {nm: ev[nm] for nm in EVAL_NAMES}
+        if T is not None:
+            T.update({"challenges": ch7, "z_challenge": zc, "t_eval": t_eval, "workspace": ws})
+        return proof, list(wa.pi_values)
+
+
+class WitnessAssignment:
+    """What a proof needs from the synthesized circuit, already in limb form: the four wire
+    columns over the n-domain (src/prover.rs:109-119) and the dense public inputs
+    (src/lib.rs:206-219).  Building it is the host-side gather; ``create_proof`` accepts it
+    directly so repeated proofs do not redo the conversion."""
+
+    def __init__(self, wires_mont, dense_pi_mont, pi_values):
+        self.wires_mont = wires_mont          # (4, n, 4) uint64
+        self.dense_pi_mont = dense_pi_mont    # (n, 4) uint64
+        self.pi_values = list(pi_values)
+
+    @classmethod
+    def from_circuit(cls, circ, n):
+        wit = fr_to_mont(circ.witness)                      # (num_witness, 4)
+        wires = np.zeros((4, n, 4), dtype=np.uint64)
+        idx = np.asarray(circ.wires, dtype=np.int64)
+        for j in range(4):
+            wires[j, :idx.shape[1]] = wit[idx[j]]
+        dense = np.zeros((n, 4), dtype=np.uint64)
+        if len(circ.pi_indexes):
+            dense[np.asarray(circ.pi_indexes, dtype=np.int64)] = fr_to_mont(circ.pi_values)
+        return cls(wires, dense, circ.pi_values)

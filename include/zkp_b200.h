@@ -126,6 +126,61 @@ int zkp_commit_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* coeffs, size
 /* MSM tuning knob (window bits c; 0 = automatic). */
 int zkp_msm_set_window(zkp_ctx* ctx, unsigned c);
 
+/* ---- prover rounds on device-resident polynomials ------------------------------------ */
+/* A polynomial / evaluation vector living inside a device buffer: buf[off .. off+len). */
+typedef struct zkp_poly_ref {
+    const zkp_buf* buf;
+    size_t off;
+    size_t len;
+} zkp_poly_ref;
+
+/* zkp_ntt_dev on a sub-range: reads in.len inputs (zero-padded to 2^k), writes 2^k outputs at
+ * out[out_off ..).  In place when both name the same storage. */
+int zkp_ntt_ref_dev(zkp_ctx* ctx, zkp_poly_ref in, zkp_buf* out, size_t out_off, unsigned k, int inverse,
+                    int coset);
+int zkp_buf_fill(zkp_ctx* ctx, zkp_buf* buf, size_t off, size_t n, const uint64_t value[4]);
+/* Coefficients::blind(h, rng) with the h+1 = count (<= 3) scalars drawn by the caller
+ * (src/prover.rs:126-129,193): p <- p + (b0 + b1 X + ..)(X^n - 1); buf needs n + count slots. */
+int zkp_poly_blind_dev(zkp_ctx* ctx, zkp_buf* buf, size_t off, size_t n, const uint64_t* blinders,
+                       unsigned count);
+/* compute_permutation_lagrange (src/permutation.rs:140-169): out[i] = K[wire] * w^gate with
+ * enc[i] = wire << 30 | gate (host array), K = (1, 7, 13, 17), roots = Fft::elements. */
+int zkp_perm_lagrange_dev(zkp_ctx* ctx, unsigned k, const uint32_t* enc, size_t n, const zkp_buf* roots,
+                          zkp_buf* out, size_t out_off);
+/* Permutation::compute_permutation_vec (src/permutation.rs:205-300): z[0] = 1,
+ * z[i+1] = z[i] * prod_j (w_j[i] + beta K_j w^i + gamma) / prod_j (w_j[i] + beta sigma_j[i] + gamma).
+ * wires / sigmas: evaluations over the n-point domain. */
+int zkp_perm_z_dev(zkp_ctx* ctx, size_t n, const zkp_poly_ref wires[4], const zkp_poly_ref sigmas[4],
+                   const zkp_buf* roots, const uint64_t beta[4], const uint64_t gamma[4], zkp_buf* out,
+                   size_t out_off);
+
+/* quotient_poly::compute between its NTTs (src/prover/quotient_poly.rs:74-114): all inputs are
+ * evaluations on the 8n coset; out[i] = (gates_i + PI_i + permutation_i) / Z_H(g w8^i). */
+typedef struct zkp_quotient_args {
+    zkp_poly_ref wires[4];        /* a, b, c, d */
+    zkp_poly_ref z, pi, l1;       /* z, public inputs, L1 * alpha^2 */
+    zkp_poly_ref sel[11];         /* q_m q_l q_r q_o q_c q_4 q_arith q_range q_logic q_fixed q_var */
+    zkp_poly_ref sigma[4];
+    zkp_poly_ref linear;          /* the polynomial X (permutation.linear_evaluations) */
+    uint64_t challenges[7][4];    /* alpha beta gamma range logic fixed-base var-base separation */
+    uint64_t zh_inv[8][4];        /* 1 / Z_H on the coset: period 8 */
+    uint32_t widget_mask;         /* bit0 range, 1 logic, 2 fixed-base, 3 var-base: clear = selector
+                                     polynomial identically zero, widget skipped (contributes 0) */
+} zkp_quotient_args;
+int zkp_quotient_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* args, zkp_buf* out, size_t out_off);
+
+/* Coefficients::evaluate for up to 16 polynomials at one point (linearization_poly.rs:52-73). */
+int zkp_poly_eval_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, unsigned count, const uint64_t point[4],
+                      uint64_t* out /* count x 4 */);
+/* out[i] = sum_k scalars[k] * polys[k][i], i < out_len (polys zero beyond their len; count <= 16):
+ * widget.linearize sums, t_low + z^n t_mid + .., sum_i v^i p_i. */
+int zkp_poly_lincomb_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, const uint64_t* scalars, unsigned count,
+                         zkp_buf* out, size_t out_off, size_t out_len);
+/* ruffini: quotient of in(X) by (X - point), remainder dropped; writes in.len - 1 coefficients
+ * (PlonkParams::compute_aggregate_witness, src/prover.rs:422-451). */
+int zkp_poly_div_linear_dev(zkp_ctx* ctx, zkp_poly_ref in, const uint64_t point[4], zkp_buf* out,
+                            size_t out_off);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,62 @@
+"""Circuits shared by the CPU and GPU tests: the reference's own test circuits
+(tests/range.rs, tests/logic.rs, tests/ecc.rs, README.md TestCircuit) restated on the
+Python composer."""
+from dusk_plonk_b200.composer import (Plonk, Constraint, JUBJUB_GENERATOR, jubjub_mul, R_MOD)
+
+
+def range_circuit(a, bits=76):
+    """tests/range.rs:47-58 DummyCircuit."""
+    cs = Plonk.initialize()
+    w = cs.append_witness(a)
+    cs.component_range(w, bits)
+    return cs
+
+
+def readme_circuit(a=20, b=5, e=2, c=None, d=None, f=None):
+    """README.md:24-71 TestCircuit: a + b = c (PI), range checks, a * b = d (PI), e * G = f (PI)."""
+    cs = Plonk.initialize()
+    c = (a + b) % R_MOD if c is None else c
+    d = a * b % R_MOD if d is None else d
+    f = jubjub_mul(JUBJUB_GENERATOR, e) if f is None else f
+    wa = cs.append_witness(a)
+    wb = cs.append_witness(b)
+    cs.append_gate(Constraint().left(1).right(1).public(-c).a(wa).b(wb))
+    cs.component_range(wa, 1 << 6)
+    cs.component_range(wb, 1 << 5)
+    cs.append_gate(Constraint().mult(1).public(-d).a(wa).b(wb))
+    we = cs.append_witness(e)
+    res = cs.component_mul_generator(we, JUBJUB_GENERATOR)
+    cs.assert_equal_public_point(res, f)
+    return cs
+
+
+def logic_curve_circuit(a=0x1234567890ABCDEF, b=0xFEDCBA0987654321, s1=77, s2=1234567, bad=False):
+    """tests/logic.rs + tests/ecc.rs (component_add_point) in one circuit."""
+    cs = Plonk.initialize()
+    wa = cs.append_witness(a)
+    wb = cs.append_witness(b)
+    r1 = cs.append_logic_and(wa, wb, 64)
+    r2 = cs.append_logic_xor(wa, wb, 64)
+    cs.assert_equal_constant(r1, (a & b) + (1 if bad else 0), None)
+    cs.assert_equal_constant(r2, a ^ b, None)
+    p1 = cs.append_point(jubjub_mul(JUBJUB_GENERATOR, s1))
+    p2 = cs.append_point(jubjub_mul(JUBJUB_GENERATOR, s2))
+    p3 = cs.component_add_point(p1, p2)
+    cs.assert_equal_public_point(p3, jubjub_mul(JUBJUB_GENERATOR, s1 + s2))
+    return cs
+
+
+def arithmetic_chain(m_target, seed=3):
+    """Synthetic add / mul gate chain: m_target gates in total."""
+    cs = Plonk.initialize()
+    x = cs.append_witness(seed)
+    y = cs.append_witness(seed + 4)
+    i = 0
+    while cs.m() < m_target - 1:
+        if i & 1:
+            x = cs.gate_mul(Constraint().mult(1).a(x).b(y))
+        else:
+            y = cs.gate_add(Constraint().left(1).right(1).constant(i).a(x).b(y))
+        i += 1
+    pub = cs.append_public(cs[x]) if cs.m() < m_target else None
+    return cs

@@ -1,0 +1,193 @@
+"""GPU parity: device-resident prover rounds (csrc/prover.cu through the C ABI) and the full
+``create_proof`` against the CPU restatement (oracle/plonk.py), bit-exact.
+
+Mirrors the reference's integration tests (tests/range.rs, tests/logic.rs, tests/ecc.rs,
+README TestCircuit): compile -> create_proof -> verify; unsatisfied circuits make
+create_proof return Err.  Blinders, SRS trapdoor and transcript are shared explicit inputs."""
+import numpy as np
+import pytest
+
+import dusk_plonk_b200 as z
+from dusk_plonk_b200.composer import SynthesizedCircuit
+from dusk_plonk_b200.field import fr_from_mont, fr_to_mont, fr_to_mont1
+from dusk_plonk_b200.plonk_params import Error, PlonkParams
+from oracle import plonk as oplonk
+from oracle.fields import K1, K2, K3, R_MOD, domain_generator
+from oracle.ntt import Fft as OFft, poly_eval
+from oracle.rng import SplitMix64
+
+import circuits
+
+pytestmark = pytest.mark.gpu
+
+
+def rand_vec(seed, n):
+    rng = SplitMix64(seed)
+    return [rng.fr() for _ in range(n)]
+
+
+# ------------------------------------------------------------------ primitives
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 255, 2049, 5000])
+def test_poly_eval_batch(ctx, n):
+    polys = [rand_vec(10 * n + i, max(1, n - i)) for i in range(5)]
+    bufs = [ctx.upload(fr_to_mont(p)) for p in polys]
+    pt = rand_vec(77, 1)[0]
+    got = fr_from_mont(ctx.poly_eval([ctx.ref(b) for b in bufs], fr_to_mont1(pt)))
+    assert got == [poly_eval(p, pt) for p in polys]
+
+
+def test_poly_eval_large_and_offsets(ctx):
+    n = (1 << 17) + 3
+    p = rand_vec(5, n)
+    buf = ctx.upload(fr_to_mont(p))
+    pt = rand_vec(6, 1)[0]
+    got = fr_from_mont(ctx.poly_eval([ctx.ref(buf), ctx.ref(buf, 100, 5000), ctx.ref(buf, n - 1, 1)], fr_to_mont1(pt)))
+    assert got == [poly_eval(p, pt), poly_eval(p[100:5100], pt), p[-1]]
+
+
+@pytest.mark.parametrize("n", [2, 3, 16, 17, 33, 1000, 16385])
+def test_div_linear_is_ruffini(ctx, n):
+    p = rand_vec(n, n)
+    pt = rand_vec(n + 1, 1)[0]
+    src = ctx.upload(fr_to_mont(p))
+    dst = ctx.alloc(n)
+    ctx.poly_div_linear(ctx.ref(src), fr_to_mont1(pt), dst)
+    assert fr_from_mont(dst.download(0, n - 1)) == oplonk.ruffini(p, pt)
+
+
+def test_lincomb_ragged(ctx):
+    lens = [7, 100, 64, 1]
+    polys = [rand_vec(20 + i, l) for i, l in enumerate(lens)]
+    sc = rand_vec(30, 4)
+    bufs = [ctx.upload(fr_to_mont(p)) for p in polys]
+    out = ctx.alloc(120)
+    ctx.poly_lincomb([ctx.ref(b) for b in bufs], fr_to_mont(sc), out, 10, 110)
+    exp = [sum(s * (p[i] if i < len(p) else 0) for s, p in zip(sc, polys)) % R_MOD for i in range(110)]
+    assert fr_from_mont(out.download(10, 110)) == exp
+
+
+def test_blind_and_fill(ctx):
+    n = 64
+    p = rand_vec(1, n)
+    for cnt in (2, 3):
+        bl = rand_vec(2 + cnt, cnt)
+        buf = ctx.alloc(n + cnt)
+        buf.upload(fr_to_mont(p))
+        ctx.poly_blind(buf, 0, n, fr_to_mont(bl))
+        assert fr_from_mont(buf.download()) == oplonk.blind(p, bl, n)
+    v = rand_vec(9, 1)[0]
+    buf = ctx.alloc(100)
+    buf.zero()
+    ctx.fill(buf, 3, 90, fr_to_mont1(v))
+    assert fr_from_mont(buf.download()) == [0] * 3 + [v] * 90 + [0] * 7
+
+
+@pytest.mark.parametrize("k", [0, 1, 4, 5, 9, 12])
+def test_perm_z_matches_reference_loop(ctx, k):
+    """src/permutation.rs:205-300 with per-gate inversions vs the scan formulation."""
+    n = 1 << k
+    fft = OFft(k)
+    wires = [rand_vec(40 + j, n) for j in range(4)]
+    sig = [rand_vec(50 + j, n) for j in range(4)]
+    beta, gamma = rand_vec(60, 2)
+    roots = ctx.fft_elements(k)
+    wb = [ctx.upload(fr_to_mont(w)) for w in wires]
+    sb = [ctx.upload(fr_to_mont(s)) for s in sig]
+    out = ctx.alloc(n)
+    ctx.perm_z(n, [ctx.ref(b) for b in wb], [ctx.ref(b) for b in sb], roots, fr_to_mont1(beta), fr_to_mont1(gamma), out)
+    assert fr_from_mont(out.download()) == oplonk.compute_permutation_vec(fft, wires, beta, gamma, sig)
+
+
+def test_perm_lagrange(ctx):
+    k = 6
+    n = 1 << k
+    rng = np.random.default_rng(1)
+    w = rng.integers(0, 4, n)
+    g = rng.integers(0, n, n)
+    enc = (w.astype(np.uint32) << np.uint32(30)) | g.astype(np.uint32)
+    roots = ctx.fft_elements(k)
+    out = ctx.alloc(n)
+    ctx.perm_lagrange(k, enc, roots, out)
+    om = domain_generator(k)
+    ks = (1, K1, K2, K3)
+    assert fr_from_mont(out.download()) == [ks[int(a)] * pow(om, int(b), R_MOD) % R_MOD for a, b in zip(w, g)]
+
+
+# ------------------------------------------------------------------ full proofs
+CIRCUITS = {
+    "range": lambda: circuits.range_circuit((1 << 64) - 1),
+    "logic_curve": circuits.logic_curve_circuit,
+    "readme": circuits.readme_circuit,
+    "chain": lambda: circuits.arithmetic_chain(1000),
+}
+
+
+def both_sides(ctx, cs, label=b"demo", seed=8349):
+    circ = SynthesizedCircuit.from_composer(cs)
+    rng = SplitMix64(seed)
+    tau = rng.fr()
+    k = circ.n.bit_length() - 1
+    pp = PlonkParams.setup_synthetic(ctx, max(k, 4) + 1, fr_to_mont1(tau))
+    prover = z.PlonkKey.compile_with_circuit(pp, label, circ)
+    commit = oplonk.default_commit(tau=tau)
+    opk, ovk = oplonk.compile_circuit(circ, commit, pp.srs.n)
+    otr = z.Transcript.base(label, oplonk.vk_transcript_list(ovk), circ.m)
+    bl = [rng.fr() for _ in range(11)]
+    return circ, tau, prover, commit, opk, ovk, otr, bl
+
+
+@pytest.mark.parametrize("name", list(CIRCUITS))
+def test_compile_and_prove_bit_exact(ctx, name):
+    circ, tau, prover, commit, opk, ovk, otr, bl = both_sides(ctx, CIRCUITS[name]())
+    # key preprocessing: 15 commitments and every resident polynomial (src/key.rs)
+    for nm in list(oplonk.SELECTORS) + ["s_sigma_%d" % i for i in (1, 2, 3, 4)]:
+        assert prover.verifier_key[nm] == ovk[nm], nm
+        assert fr_from_mont(prover.prover_key.poly[nm].download()) == opk.poly[nm], nm
+    for nm in ("q_m", "q_arith", "s_sigma_3", "linear"):
+        assert fr_from_mont(prover.prover_key.eval8[nm].download()) == opk.eval8[nm], nm
+    otrace, gtrace = {}, {}
+    oproof, opi = oplonk.create_proof(opk, circ, commit, otr, bl, trace=otrace)
+    gproof, gpi = prover.create_proof(bl, circ, trace=gtrace)
+    assert gpi == opi
+    assert gtrace["challenges"] == otrace["challenges"] and gtrace["z_challenge"] == otrace["z_challenge"]
+    ws = gtrace["workspace"]
+    n = circ.n
+    for j in range(4):
+        assert fr_from_mont(ws["wp"][j].download()) == otrace["w_polys"][j]
+    assert fr_from_mont(ws["Z"].download()) == otrace["z_evals"]
+    assert fr_from_mont(ws["zp"].download()) == otrace["z_poly"]
+    assert fr_from_mont(ws["T"].download()) == otrace["t_poly"]
+    r = otrace["r_poly"]
+    assert fr_from_mont(ws["R"].download()) == r + [0] * (n + 3 - len(r))
+    wz = otrace["w_z_poly"]
+    assert fr_from_mont(ws["WZ"].download(0, len(wz))) == wz
+    assert fr_from_mont(ws["WZW"].download(0, n + 2)) == otrace["w_zw_poly"]
+    assert gtrace["t_eval"] == otrace["t_eval"]
+    for c in oplonk.Proof.COMM_NAMES:
+        assert getattr(gproof, c) == getattr(oproof, c), c
+    assert gproof.evaluations == oproof.evaluations
+    # and the restated verifier accepts the GPU proof
+    assert oplonk.verify(ovk, n, gproof, circ.pi_indexes, gpi, otr, oplonk.trapdoor_kzg_check(tau))
+
+
+def test_unsatisfied_circuit_errs(ctx):
+    """tests/range.rs:79-85: the only Err path is commit's degree check."""
+    circ, tau, prover, commit, opk, ovk, otr, bl = both_sides(ctx, circuits.range_circuit(7))
+    bad = SynthesizedCircuit.from_composer(circuits.range_circuit((-(1 << 77)) % R_MOD))
+    with pytest.raises(Error):
+        prover.create_proof(bl, bad)
+    with pytest.raises(oplonk.ProverError):
+        oplonk.create_proof(opk, bad, commit, otr, bl)
+    # the prover object is still usable afterwards
+    gproof, gpi = prover.create_proof(bl, circ)
+    assert oplonk.verify(ovk, circ.n, gproof, circ.pi_indexes, gpi, otr, oplonk.trapdoor_kzg_check(tau))
+
+
+def test_prover_is_deterministic_and_blinders_matter(ctx):
+    circ, tau, prover, commit, opk, ovk, otr, bl = both_sides(ctx, circuits.range_circuit(123456))
+    p1, _ = prover.create_proof(bl, circ)
+    p2, _ = prover.create_proof(bl, circ)
+    assert p1 == p2
+    p3, pi = prover.create_proof([b + 1 for b in bl], circ)
+    assert p3.a_comm != p1.a_comm
+    assert oplonk.verify(ovk, circ.n, p3, circ.pi_indexes, pi, otr, oplonk.trapdoor_kzg_check(tau))
