@@ -117,6 +117,29 @@ def run_reference(args, rank, world):
     from oracle.rng import random_fr_raw_limbs
     cport.build()
     cores = cport.num_threads()
+    if args.workload == "prove":
+        cp, circ, bl = cpu_prover(args.logn)
+        fn = lambda: cp.create_proof(bl, circ)
+        n = 1
+        unit, metric = "proofs/s", "create_proof_throughput"
+        sample = ("one full create_proof of the 2^%d-gate synthetic circuit per step, C restatement, OpenMP "
+                  "(tuned: batch inversion, threaded loops)" % args.logn)
+        for _ in range(min(args.warmup, 1)):
+            fn()
+        steps = min(args.steps, 3)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        dt = (time.perf_counter() - t0) / steps
+        val = 1.0 / dt
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": world,
+                "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (modular integer)", "data": "synthetic",
+                "config": workload_config(args), "prove_ms": dt * 1e3,
+                "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
     if args.workload == "msm":
         logs = min(args.logn, 16)
         n = 1 << logs
@@ -156,7 +179,33 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def cpu_prover(logn):
+    """CPU restatement of compile + the witness for the same synthetic circuit (oracle side)."""
+    from oracle import cport, cprover, curve
+    from oracle.fields import R_MOD, fr_to_raw_limbs, g1_to_mont_limbs
+    from oracle.rng import SplitMix64
+    from dusk_plonk_b200.composer import synthetic_circuit
+    from dusk_plonk_b200.transcript import Transcript
+    circ = synthetic_circuit(logn)
+    rng = SplitMix64(8349)
+    tau = rng.fr()
+    dl, t = [], 1
+    for _ in range((1 << logn) + 7):
+        dl.append(t)
+        t = t * tau % R_MOD
+    srs = cport.fixed_base_mul(g1_to_mont_limbs([curve.G1_GEN])[0], fr_to_raw_limbs(dl))
+    cp = cprover.CProver(circ, srs, b"plonk", Transcript)
+    bl = [rng.fr() for _ in range(11)]
+    return cp, circ, bl
+
+
 def workload_config(args):
+    if args.workload == "prove":
+        return {"workload": "create_proof, synthetic 2^%d-gate add/mul circuit (n = 2^%d, quotient domain 8n = 2^%d), "
+                            "11 commits + 11 NTT(n) + 8 NTT(8n) + element-wise rounds" % (args.logn, args.logn, args.logn + 3),
+                "log2_gates": args.logn,
+                "l2": "proving key + workspace (%d MiB) stream through each proof: larger than L2" %
+                      ((16 + 9) * (1 << (args.logn + 3)) * 32 >> 20)}
     if args.workload == "msm":
         return {"workload": "G1 MSM (KZG commit) over 2^%d SRS powers, uniform scalars" % args.logn,
                 "log2_n": args.logn, "l2": "inputs (bases+scalars) larger than L2"}
@@ -171,12 +220,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="msm", choices=["msm", "ntt"])
+    ap.add_argument("--workload", default="prove", choices=["prove", "msm", "ntt"])
     ap.add_argument("--logn", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.logn is None:
-        args.logn = 22 if args.workload == "msm" else 24
+        args.logn = {"prove": 16, "msm": 22, "ntt": 24}[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
     rank = env_int("RANK", 0)
@@ -202,7 +251,27 @@ def main():
     hbm_peak, hbm_src = measured_peaks()
     imad_pk, imad_src = imad_peak()
 
-    if args.workload == "msm":
+    if args.workload == "prove":
+        from dusk_plonk_b200.composer import synthetic_circuit
+        from dusk_plonk_b200.field import fr_to_mont1
+        from dusk_plonk_b200.plonk_params import PlonkParams
+        from oracle.rng import SplitMix64   # seeded input generator only
+        circ = synthetic_circuit(args.logn)
+        rng = SplitMix64(8349)
+        tau = rng.fr()
+        pp = PlonkParams.setup_synthetic(ctx, args.logn, fr_to_mont1(tau))
+        prover = z.PlonkKey.compile(pp, circ)
+        bl = [rng.fr() for _ in range(11)]
+        wa_host = z.WitnessAssignment.from_circuit(circ, circ.n)
+        wa_dev = z.WitnessAssignment.from_circuit(circ, circ.n).to_device(ctx)
+        proofs = []
+        step = lambda: proofs.append(prover.create_proof(bl, wa_dev)[0])
+        e2e_step = lambda: proofs.append(prover.create_proof(bl, wa_host)[0])
+        h2d, d2h = 5 * circ.n * 32 + 19 * 32, 11 * 96 + 17 * 32
+        dominant = "msm_accumulate"
+        metric = "create_proof_throughput"
+        n = 1
+    elif args.workload == "msm":
         tau = random_fr_raw_limbs(4242 + rank, 1)[0]
         srs = ctx.srs_generate(tau, n)
         host_scalars = random_fr_raw_limbs(8349 + rank, n)
@@ -238,14 +307,18 @@ def main():
     ctx.prof_enable(True)
     ctx.prof_reset()
     l0 = ctx.launches
+    pts0 = ctx.msm_points
     ctx.timer_start()
     for _ in range(args.steps):
         step()
     ms = ctx.timer_stop_ms()
     launches = ctx.launches - l0
+    msm_pts = ctx.msm_points - pts0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     dom_ms, dom_cnt = ctx.prof_read(dominant)
+    prof_groups = {g: ctx.prof_read(g) for g in ("msm_sort", "msm_accumulate", "msm_reduce", "msm_combine", "ntt",
+                                                 "quotient", "perm_z", "poly_eval", "poly_lincomb", "poly_div")}
     ctx.prof_enable(False)
     ctx.prof_reset()
 
@@ -270,7 +343,27 @@ def main():
         value = world * n / (ms_step * 1e-3) / 1e6
         e2e_val = world * n / (e2e_ms / args.steps * 1e-3) / 1e6
         dom_avg_ms = dom_ms / max(dom_cnt, 1)
-        if args.workload == "msm":
+        unit = "Melem/s"
+        extra = {}
+        if args.workload == "prove":
+            unit = "proofs/s"
+            value, e2e_val = value * 1e6, e2e_val * 1e6
+            assert all(p == proofs[0] for p in proofs), "non-deterministic proofs"
+            # dominant kernel: msm_accumulate over the proof's 11 commits
+            achieved = MSM_IMAD_PER_POINT * (msm_pts / max(dom_cnt, 1)) / (dom_avg_ms * 1e-3) / 1e12
+            shares = {}
+            for g in ("msm_sort", "msm_accumulate", "msm_reduce", "msm_combine", "ntt", "quotient", "perm_z",
+                      "poly_eval", "poly_lincomb", "poly_div"):
+                gm, gc = prof_groups.get(g, (0.0, 0))
+                shares[g] = {"ms_per_proof": gm / args.steps, "launch_groups_per_proof": gc / args.steps}
+            roofline = {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": imad_pk,
+                        "unit": "T IMAD/s", "frac": achieved / imad_pk, "traffic": None, "peak_source": imad_src,
+                        "kernel_ms": dom_avg_ms, "launches_per_step": dom_cnt / args.steps,
+                        "kernel_share_of_step": dom_ms / args.steps / ms_step,
+                        "algorithmic": "48000 mul-adds per committed point (SURVEY 8d); %d points per proof" %
+                                       (msm_pts // args.steps)}
+            extra = {"prove_ms": ms_step, "e2e_prove_ms": e2e_ms / args.steps, "kernel_groups": shares}
+        elif args.workload == "msm":
             achieved = MSM_IMAD_PER_POINT * n / (dom_avg_ms * 1e-3) / 1e12
             roofline = {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": imad_pk,
                         "unit": "T IMAD/s", "frac": achieved / imad_pk, "traffic": None, "peak_source": imad_src,
@@ -284,12 +377,13 @@ def main():
                         "peak_source": hbm_src, "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_avg_ms / ms_step,
                         "imad_achieved_T": imad, "imad_frac": imad / imad_pk, "imad_peak_source": imad_src,
                         "algorithmic": "64 B per element; 68*N*log2(N) mul-adds (SURVEY 8d)"}
-        line = {"metric": metric, "value": value, "unit": "Melem/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32 limbs (modular integer)", "data": "synthetic",
                 "config": workload_config(args), "roofline": roofline,
-                "e2e": {"value": e2e_val, "unit": "Melem/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clocks}
+        line.update(extra)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
@@ -304,6 +398,14 @@ def cpu_baseline(args):
     from oracle.rng import random_fr_raw_limbs
     cport.build()
     cores = cport.num_threads()
+    if args.workload == "prove":
+        cp, circ, bl = cpu_prover(args.logn)
+        t0 = time.perf_counter()
+        cp.create_proof(bl, circ)
+        dt = time.perf_counter() - t0
+        return {"value": 1.0 / dt, "unit": "proofs/s", "cores": cores, "kind": "port", "prove_ms": dt * 1e3,
+                "sample": "one full create_proof of the same 2^%d-gate circuit (whole workload, not a sample); "
+                          "C restatement, OpenMP, tuned (batch inversion, threaded loops)" % args.logn}
     if args.workload == "msm":
         from oracle import curve
         from oracle.fields import R_MOD, fr_to_raw_limbs, g1_to_mont_limbs

@@ -428,6 +428,87 @@ class SynthesizedCircuit:
     def from_composer(cls, cs: Plonk):
         m = cs.m()
         n = 1 << (m - 1).bit_length()
-        sw, sg = cs.compute_sigma_permutations(n)
+        sw, sg = sigma_from_wires(cs.wire_indices(), n)
         return cls(m, cs.selector_columns(), cs.wire_indices(), list(cs.witness), sw, sg,
                    cs.public_input_indexes(), cs.instance_values())
+
+
+def sigma_from_wires(wires, n):
+    """Vectorised ``compute_sigma_permutations`` (src/permutation.rs:108-145) from the (4, m)
+    wire -> witness table: positions are visited gate by gate in a, b, o, d order, exactly
+    the insertion order of ``add_witnesses_to_map``; each maps to the next position holding
+    the same witness (cyclically)."""
+    wires = np.asarray(wires, dtype=np.int64)
+    m = wires.shape[1]
+    wid = wires.T.reshape(-1)                      # position p = gate * 4 + wire
+    order = np.argsort(wid, kind="stable")         # grouped by witness, insertion order inside
+    sw = wid[order]
+    first = np.ones(len(order), dtype=bool)
+    first[1:] = sw[1:] != sw[:-1]
+    starts = np.nonzero(first)[0]
+    group_start = np.repeat(starts, np.diff(np.append(starts, len(order))))
+    nxt = np.empty(len(order), dtype=np.int64)
+    nxt[:-1] = order[1:]
+    nxt[-1] = order[0]
+    last = np.ones(len(order), dtype=bool)
+    last[:-1] = sw[1:] != sw[:-1]
+    nxt[last] = order[group_start[last]]
+    sigma_pos = np.empty(len(order), dtype=np.int64)
+    sigma_pos[order] = nxt
+    sig_w = np.tile(np.arange(4, dtype=np.int64)[:, None], (1, n))
+    sig_g = np.tile(np.arange(n, dtype=np.int64)[None, :], (4, 1))
+    sp = sigma_pos.reshape(m, 4).T                 # (4, m)
+    sig_w[:, :m] = sp % 4
+    sig_g[:, :m] = sp // 4
+    return sig_w, sig_g
+
+
+def synthetic_circuit(k, seed=8349, slack=8):
+    """Synthetic 2^k-gate workload (SURVEY 8d): ``Plonk::initialize`` followed by an alternating
+    ``gate_add`` / ``gate_mul`` chain and one public input, m = 2^k - slack gates so that
+    ``additional_n`` stays 2^k (src/key.rs:81).  Built with numpy (the per-gate Python composer
+    is too slow for 2^20 gates); returns a ``SynthesizedCircuit``."""
+    cs = Plonk.initialize()
+    x = cs.append_witness(seed)
+    y = cs.append_witness(seed + 4)
+    m0 = cs.m()
+    m = (1 << k) - slack
+    nchain = m - m0 - 1
+    assert nchain > 0
+    base = len(cs.witness)
+    wit = list(cs.witness)
+    xv, yv = wit[x], wit[y]
+    wa = np.empty(nchain, dtype=np.int64)
+    wb = np.empty(nchain, dtype=np.int64)
+    xi, yi = x, y
+    for i in range(nchain):
+        wa[i], wb[i] = xi, yi
+        if i & 1:
+            xv = xv * yv % R_MOD
+            wit.append(xv)
+            xi = base + i
+        else:
+            yv = (xv + yv + i) % R_MOD
+            wit.append(yv)
+            yi = base + i
+    wo = base + np.arange(nchain, dtype=np.int64)
+    odd = (np.arange(nchain) & 1).astype(np.int64)
+    sel0 = cs.selector_columns()
+    W0 = cs.wire_indices()
+    # final gate: append_public(x)
+    pub = len(wit)
+    wit.append(xv)
+    sel = {}
+    zeros = np.zeros(nchain, dtype=np.int64)
+    chain = {"q_m": odd, "q_l": 1 - odd, "q_r": 1 - odd, "q_o": zeros - 1, "q_c": (1 - odd) * np.arange(nchain),
+             "q_d": zeros, "q_arith": zeros + 1, "q_range": zeros, "q_logic": zeros, "q_fixed_group_add": zeros,
+             "q_variable_group_add": zeros}
+    last = {s: 0 for s in SELECTORS}
+    last.update({"q_l": 1, "q_arith": 1})
+    for s in SELECTORS:
+        head = np.array([v if v < (1 << 62) else v - R_MOD for v in sel0[s]], dtype=np.int64)
+        sel[s] = np.concatenate([head, chain[s], np.array([last[s]], dtype=np.int64)])
+    wires = np.concatenate([W0, np.stack([wa, wb, wo, zeros]), np.array([[pub], [0], [0], [0]], dtype=np.int64)], axis=1)
+    n = 1 << k
+    sw, sg = sigma_from_wires(wires, n)
+    return SynthesizedCircuit(m, sel, wires, wit, sw, sg, [m - 1], [(-xv) % R_MOD])

@@ -78,6 +78,7 @@ int zkp_ctx_sync(zkp_ctx* ctx) {
 void* zkp_ctx_stream(zkp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int zkp_sm_count(const zkp_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t zkp_launch_count(const zkp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t zkp_msm_point_count(const zkp_ctx* ctx) { return ctx ? ctx->msm_points : 0; }
 
 int zkp_timer_start(zkp_ctx* ctx) {
     if (!ctx) return ZKP_ERR_INVALID;

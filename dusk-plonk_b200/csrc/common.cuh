@@ -37,6 +37,7 @@ struct zkp_ctx {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     std::string last_error;
     uint64_t launches = 0;
+    uint64_t msm_points = 0;  // points summed by msm_run since creation (roofline accounting)
     unsigned msm_window = 0;
     std::map<unsigned, zkp::NttDomain*> domains;
     zkp::fr_t* ntt_scratch = nullptr;

@@ -354,6 +354,7 @@ int msm_run(zkp_ctx* ctx, const g1_affine* bases, const fr_t* scalars_dev, size_
         return ZKP_OK;
     }
     if (n >= (1ull << 31)) return ZKP_ERR_INVALID;
+    ctx->msm_points += n;
     MsmScratch* s;
     if ((rc = msm_scratch(ctx, &s))) return rc;
 

@@ -33,6 +33,7 @@ SIGNATURES = {
     "zkp_ctx_stream": (_vp, [_vp]),
     "zkp_sm_count": (_int, [_vp]),
     "zkp_launch_count": (ctypes.c_uint64, [_vp]),
+    "zkp_msm_point_count": (ctypes.c_uint64, [_vp]),
     "zkp_timer_start": (_int, [_vp]),
     "zkp_timer_stop_ms": (_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "zkp_prof_enable": (_int, [_vp, _int]),
@@ -173,6 +174,10 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.zkp_launch_count(self.h))
+
+    @property
+    def msm_points(self):
+        return int(self.lib.zkp_msm_point_count(self.h))
 
     def timer_start(self):
         self.check(self.lib.zkp_timer_start(self.h))

@@ -79,8 +79,11 @@ class Prover:
         proof = Proof()
 
         # round 1: wires -> iNTT -> blind -> commit (src/prover.rs:107-158)
-        W = ws["W"]
-        W.upload(wa.wires_mont.reshape(4 * n, 4))
+        if wa.wires_dev is not None:      # witness already resident in HBM
+            W = wa.wires_dev
+        else:
+            W = ws["W"]
+            W.upload(wa.wires_mont.reshape(4 * n, 4))
         for j in range(4):
             ctx.ntt_dev(_View(W, j * n, n), n, ws["wp"][j], k, True, False)
             ctx.poly_blind(ws["wp"][j], 0, n, bl[2 * j:2 * j + 2])
@@ -108,8 +111,11 @@ class Prover:
         vs = tr.challenge_scalar(b"variable base separation challenge")
         ch7 = (alpha, beta, gamma, rs, ls, fs, vs)
         PI = ws["PI"]
-        PI.upload(wa.dense_pi_mont)
-        ctx.ntt_dev(PI, n, PI, k, True, False)
+        if wa.pi_dev is not None:
+            ctx.ntt_dev(wa.pi_dev, n, PI, k, True, False)
+        else:
+            PI.upload(wa.dense_pi_mont)
+            ctx.ntt_dev(PI, n, PI, k, True, False)
         k8, n8 = k + 3, 8 * n
         for j in range(4):
             ctx.ntt_dev(ws["wp"][j], n + 2, ws["e8"][j], k8, False, True)
@@ -199,6 +205,15 @@ class WitnessAssignment:
         self.wires_mont = wires_mont          # (4, n, 4) uint64
         self.dense_pi_mont = dense_pi_mont    # (n, 4) uint64
         self.pi_values = list(pi_values)
+        self.wires_dev = None
+        self.pi_dev = None
+
+    def to_device(self, ctx):
+        """Upload once; later proofs read the witness from HBM."""
+        n = self.wires_mont.shape[1]
+        self.wires_dev = ctx.upload(self.wires_mont.reshape(4 * n, 4))
+        self.pi_dev = ctx.upload(self.dense_pi_mont)
+        return self
 
     @classmethod
     def from_circuit(cls, circ, n):

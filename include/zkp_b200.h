@@ -56,6 +56,8 @@ void* zkp_ctx_stream(zkp_ctx* ctx);             /* cudaStream_t the kernels are 
 int zkp_sm_count(const zkp_ctx* ctx);
 /* number of kernels this library launched on ctx since creation (bench.py gpu_launches) */
 uint64_t zkp_launch_count(const zkp_ctx* ctx);
+/* points summed by the MSM since creation (algorithmic-work accounting of the roofline report) */
+uint64_t zkp_msm_point_count(const zkp_ctx* ctx);
 
 /* CUDA-event timing on the context's stream (events are recorded where the kernels run) */
 int zkp_timer_start(zkp_ctx* ctx);

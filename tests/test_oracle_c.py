@@ -1,6 +1,7 @@
 """The threaded C restatement (oracle/zkp_oracle.c, the CPU baseline) against the Python
 big-integer oracle."""
 import numpy as np
+import pytest
 
 from oracle import curve, ntt
 from oracle.fields import (P_MOD, R_MOD, fq_from_mont_limbs, fq_to_mont_limbs, fr_from_mont_limbs,
@@ -54,3 +55,44 @@ def test_msm_and_fixed_base(cport):
     b3 = np.tile(g, (50, 1))
     assert g1_from_mont_limbs(cport.msm_g1(b3, fr_to_mont_limbs(s3)))[0] is None
     assert g1_from_mont_limbs(cport.msm_g1(b3[:0], fr_to_mont_limbs([])))[0] is None
+
+
+# ---------------------------------------------------------------- C prover vs Python prover
+def _srs(cport, tau, n):
+    from oracle import curve
+    from oracle.fields import fr_to_raw_limbs, g1_to_mont_limbs
+    dl, t = [], 1
+    for _ in range(n):
+        dl.append(t)
+        t = t * tau % R_MOD
+    return cport.fixed_base_mul(g1_to_mont_limbs([curve.G1_GEN])[0], fr_to_raw_limbs(dl))
+
+
+@pytest.mark.parametrize("name,faithful", [("range", False), ("range", True), ("logic_curve", False), ("readme", False)])
+def test_c_prover_equals_python_prover(cport, name, faithful):
+    import circuits
+    from dusk_plonk_b200.composer import SynthesizedCircuit
+    from dusk_plonk_b200.transcript import Transcript
+    from oracle import plonk, cprover
+    from oracle.rng import SplitMix64
+    cs = {"range": lambda: circuits.range_circuit((1 << 64) - 1), "readme": circuits.readme_circuit,
+          "logic_curve": circuits.logic_curve_circuit}[name]()
+    circ = SynthesizedCircuit.from_composer(cs)
+    rng = SplitMix64(8349)
+    tau = rng.fr()
+    commit = plonk.default_commit(tau=tau)
+    pk, vk = plonk.compile_circuit(circ, commit, 1 << 20)
+    tr = Transcript.base(b"demo", plonk.vk_transcript_list(vk), circ.m)
+    bl = [rng.fr() for _ in range(11)]
+    t_py, t_c = {}, {}
+    p_py, pi = plonk.create_proof(pk, circ, commit, tr, bl, trace=t_py)
+    cp = cprover.CProver(circ, _srs(cport, tau, pk.max_len), b"demo", Transcript, faithful=faithful)
+    for nm in plonk.SELECTORS:
+        assert cp.vk[nm] == vk[nm], nm
+    p_c, pi_c = cp.create_proof(bl, circ, trace=t_c)
+    assert pi_c == pi
+    assert fr_from_mont_limbs(t_c["t_poly"]) == t_py["t_poly"]
+    assert fr_from_mont_limbs(t_c["z_evals"]) == t_py["z_evals"]
+    assert fr_from_mont_limbs(t_c["w_z_poly"]) == t_py["w_z_poly"][:len(t_c["w_z_poly"])]
+    assert p_c == p_py
+    assert plonk.verify(vk, pk.n, p_c, circ.pi_indexes, pi_c, tr, plonk.trapdoor_kzg_check(tau))
