@@ -189,6 +189,18 @@ int zkp_buf_copy(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const zkp_buf* src,
     return ZKP_OK;
 }
 
+int zkp_host_alloc(size_t bytes, void** out) {
+    if (!out) return ZKP_ERR_INVALID;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) { *out = nullptr; return e == cudaErrorMemoryAllocation ? ZKP_ERR_NOMEM : ZKP_ERR_CUDA; }
+    return ZKP_OK;
+}
+
+int zkp_host_free(void* p) {
+    if (!p) return ZKP_OK;
+    return cudaFreeHost(p) == cudaSuccess ? ZKP_OK : ZKP_ERR_CUDA;
+}
+
 /* ---- NTT -------------------------------------------------------------------------- */
 int zkp_ntt_dev_batch(zkp_ctx* ctx, const zkp_buf* in, size_t in_stride, size_t len_in, zkp_buf* out,
                       size_t out_stride, unsigned k, int inverse, int coset, unsigned batch) {
@@ -237,21 +249,37 @@ int zkp_fft_elements_dev(zkp_ctx* ctx, unsigned k, zkp_buf* out) {
 }
 
 /* ---- SRS / MSM -------------------------------------------------------------------- */
+// Allocates the W-row table for n powers; row 0 is filled by the caller.
+static int srs_alloc(zkp_ctx* ctx, size_t n, zkp_srs** out) {
+    zkp_srs* s = new zkp_srs();
+    s->n = n;
+    s->c = ctx->msm_window ? (ctx->msm_window < 2 ? 2 : ctx->msm_window) : msm_choose_window(n);
+    s->W = 255 / s->c + 1;
+    if ((size_t)s->W * n >= (1ull << 31)) { delete s; return ZKP_ERR_INVALID; }
+    cudaError_t e = cudaMalloc(&s->d, (n ? (size_t)s->W * n : 1) * sizeof(g1_affine));
+    if (e != cudaSuccess) {
+        delete s;
+        cuda_fail(ctx, e, "cudaMalloc(srs table)", __FILE__, __LINE__);
+        return e == cudaErrorMemoryAllocation ? ZKP_ERR_NOMEM : ZKP_ERR_CUDA;
+    }
+    *out = s;
+    return ZKP_OK;
+}
+
 int zkp_srs_load(zkp_ctx* ctx, const uint64_t* xy, size_t n, zkp_srs** out) {
     if (!ctx || !out || (!xy && n)) return ZKP_ERR_INVALID;
     int rc;
     if ((rc = set_device(ctx))) return rc;
-    zkp_srs* s = new zkp_srs();
-    s->n = n;
-    cudaError_t e = cudaMalloc(&s->d, (n ? n : 1) * sizeof(g1_affine));
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(s->d, xy, n * sizeof(g1_affine), cudaMemcpyHostToDevice, ctx->stream);
+    zkp_srs* s = nullptr;
+    if ((rc = srs_alloc(ctx, n, &s))) return rc;
+    cudaError_t e = cudaMemcpyAsync(s->d, xy, n * sizeof(g1_affine), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
-        if (s->d) cudaFree(s->d);
+        cudaFree(s->d);
         delete s;
         return cuda_fail(ctx, e, "srs upload", __FILE__, __LINE__);
     }
+    if ((rc = srs_build_table(ctx, s))) { cudaFree(s->d); delete s; return rc; }
     *out = s;
     return ZKP_OK;
 }
@@ -260,13 +288,12 @@ int zkp_srs_generate(zkp_ctx* ctx, const uint64_t tau[4], size_t n, zkp_srs** ou
     if (!ctx || !out || !tau) return ZKP_ERR_INVALID;
     int rc;
     if ((rc = set_device(ctx))) return rc;
-    zkp_srs* s = new zkp_srs();
-    s->n = n;
-    cudaError_t e = cudaMalloc(&s->d, (n ? n : 1) * sizeof(g1_affine));
-    if (e != cudaSuccess) { delete s; return cuda_fail(ctx, e, "cudaMalloc", __FILE__, __LINE__); }
+    zkp_srs* s = nullptr;
+    if ((rc = srs_alloc(ctx, n, &s))) return rc;
     fr_t t;
     memcpy(t.l, tau, 32);
     rc = srs_generate(ctx, t, n, s->d);
+    if (!rc) rc = srs_build_table(ctx, s);
     if (rc) { cudaFree(s->d); delete s; return rc; }
     *out = s;
     return ZKP_OK;
@@ -302,7 +329,7 @@ int zkp_msm_set_window(zkp_ctx* ctx, unsigned c) {
 int zkp_msm_g1_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* scalars, size_t off, size_t n,
                    uint64_t out_xy[12]) {
     if (!ctx || !srs || !scalars || !out_xy || off + n > scalars->n || n > srs->n) return ZKP_ERR_INVALID;
-    return msm_run(ctx, srs->d, scalars->d + off, n, reinterpret_cast<g1_affine*>(out_xy));
+    return msm_run(ctx, srs, scalars->d + off, n, reinterpret_cast<g1_affine*>(out_xy));
 }
 
 int zkp_commit_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* coeffs, size_t off, size_t n,
@@ -312,7 +339,7 @@ int zkp_commit_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* coeffs, size
     int rc = msm_highest_nonzero(ctx, coeffs->d + off, n, &top);
     if (rc) return rc;
     if (top >= (long long)srs->n) return ZKP_ERR_DEGREE;
-    return msm_run(ctx, srs->d, coeffs->d + off, (size_t)(top + 1), reinterpret_cast<g1_affine*>(out_xy));
+    return msm_run(ctx, srs, coeffs->d + off, (size_t)(top + 1), reinterpret_cast<g1_affine*>(out_xy));
 }
 
 static int with_uploaded(zkp_ctx* ctx, const uint64_t* scalars, size_t n, zkp_buf** out) {

@@ -26,8 +26,9 @@ struct zkp_buf {
 };
 
 struct zkp_srs {
-    zkp::g1_affine* d = nullptr;
+    zkp::g1_affine* d = nullptr;  // table: row w holds 2^(c w) * P_i, i < n; row 0 = the SRS powers
     size_t n = 0;
+    unsigned c = 0, W = 0;        // window bits / number of table rows (fixed at load time)
 };
 
 struct zkp_ctx {
@@ -109,8 +110,9 @@ int ntt_elements(zkp_ctx* ctx, unsigned k, fr_t* out);
 fr_t fft_constant_host(unsigned k, int kind);
 
 // msm.cu
-int msm_run(zkp_ctx* ctx, const g1_affine* bases, const fr_t* scalars_dev, size_t n,
-            g1_affine* out_host);
+int msm_run(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* scalars_dev, size_t n, g1_affine* out_host);
+unsigned msm_choose_window(size_t n);
+int srs_build_table(zkp_ctx* ctx, zkp_srs* srs);
 int msm_highest_nonzero(zkp_ctx* ctx, const fr_t* scalars_dev, size_t n, long long* out);
 int srs_generate(zkp_ctx* ctx, const fr_t& tau, size_t n, g1_affine* out_dev);
 void msm_free(zkp_ctx* ctx);

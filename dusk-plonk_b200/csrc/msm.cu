@@ -4,15 +4,24 @@
 // src/prover.rs:133-136,194,262-265,440,452; src/key.rs:138-159; src/prover/proof.rs:507-526):
 // sum_i s_i * P_i over BLS12-381 G1, returned in affine form (Commitment::new).
 //
+// KZG commits always run against the same SRS, so the window structure is moved into the
+// bases once, at load time (PlonkParams::trim): the device keeps the table
+//     T[w][i] = 2^(c w) * P_i        (affine, W = floor(255 / c) + 1 copies)
+// and every (scalar, window) pair becomes one signed digit d in [-2^(c-1), 2^(c-1)] that adds
+// +-T[w][i] to bucket |d| - 1 of a SINGLE bucket set shared by all windows.  There is no
+// per-window bucket array, no window-combine doubling chain, and the bucket reduction runs once.
+//
 // Pipeline (all on the device, one stream):
-//   1. msm_digits_kernel   Fr Montgomery -> canonical, signed c-bit digits
-//                          d in [-2^(c-1), 2^(c-1)], histogram of |d| per window
-//   2. msm_scan_kernel     exclusive scan of the W * 2^(c-1) bucket counts
-//   3. msm_scatter_kernel  counting-sort of (point index, sign) by (window, bucket)
-//   4. msm_accumulate_kernel  one thread per bucket, XYZZ mixed additions (8M + 2S each,
-//                          384-bit Montgomery on the integer pipe) -- the hot kernel
-//   5. msm_bucket_reduce_kernel + msm_tree_reduce_kernel  sum_b (b+1) * B[w][b] per window
-//   6. msm_window_combine_kernel  Horner over the windows, one Fermat inversion -> affine
+//   1. msm_digits_kernel      Fr Montgomery -> canonical, signed digits, bucket histogram
+//   2. msm_scan_kernel        bucket offsets; buckets are cut into tasks of <= CAP entries so
+//                             skewed digit distributions (top window, small coefficients,
+//                             carry-only digits) cannot serialise on one thread
+//   3. msm_scatter_kernel     counting sort of (table index, sign) by bucket
+//   4. msm_accumulate_kernel  one thread per task, XYZZ mixed additions (8M + 2S each, 384-bit
+//                             Montgomery on the integer pipe) -- the hot kernel
+//   5. msm_merge_kernel       buckets made of several tasks: one warp sums the partials
+//   6. msm_bucket_reduce_kernel + msm_tree_reduce_kernel   sum_b (b+1) * B[b]
+//   7. msm_finish_kernel      one Fermat inversion -> affine
 // Addition in G1 is commutative and the result is normalised to affine, so the output is
 // bit-identical to any correct CPU evaluation regardless of accumulation order.
 #include "common.cuh"
@@ -20,13 +29,16 @@
 namespace zkp {
 
 struct MsmScratch {
-    size_t cap_n = 0, cap_entries = 0, cap_buckets = 0, cap_partials = 0;
-    uint32_t* digits = nullptr;   // [W][n]   bucket | sign << 31, 0xffffffff = zero digit
-    uint32_t* sorted = nullptr;   // [W * n]  point index | sign << 31, grouped by bucket
-    uint32_t* counts = nullptr;   // [W * B]
-    uint32_t* offsets = nullptr;  // [W * B]
-    uint32_t* cursor = nullptr;   // [W * B]
-    g1_xyzz* buckets = nullptr;   // [W * B]
+    size_t cap_entries = 0, cap_sorted = 0, cap_buckets = 0, cap_partials = 0, cap_tasks = 0;
+    uint32_t* digits = nullptr;   // [W * n]  bucket | sign << 31, 0xffffffff = zero digit
+    uint32_t* sorted = nullptr;   // [W * n]  table index | sign << 31, grouped by bucket
+    uint32_t* counts = nullptr;   // [B]
+    uint32_t* offsets = nullptr;  // [B]
+    uint32_t* cursor = nullptr;   // [B]
+    uint32_t* task_off = nullptr; // [B + 1]  first task of each bucket; [B] = number of tasks
+    uint32_t* multi = nullptr;    // [B + 1]  buckets made of > 1 task; [B] = how many
+    g1_xyzz* buckets = nullptr;   // [B]
+    g1_xyzz* task_out = nullptr;  // [tasks] partial sums of multi-task buckets
     g1_xyzz* part_a = nullptr;    // reduction ping-pong
     g1_xyzz* part_b = nullptr;
     g1_affine* result = nullptr;
@@ -65,6 +77,7 @@ __device__ __forceinline__ uint32_t window_bits(const fr_t& s, unsigned pos, uns
     return (uint32_t)(v >> off) & ((1u << c) - 1);
 }
 
+// digits[w * n + i]: bucket | sign for scalar i, window w.
 __global__ void msm_digits_kernel(const fr_t* scalars, size_t n, unsigned c, unsigned W,
                                   uint32_t* digits, uint32_t* counts) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,75 +97,122 @@ __global__ void msm_digits_kernel(const fr_t* scalars, size_t n, unsigned c, uns
             enc = d ? (d - 1) : DIGIT_ZERO;
         }
         digits[(size_t)w * n + i] = enc;
-        if (enc != DIGIT_ZERO) atomicAdd(&counts[(size_t)w * B + (enc & 0x7fffffffu)], 1u);
+        if (enc != DIGIT_ZERO) atomicAdd(&counts[enc & 0x7fffffffu], 1u);
     }
 }
 
-// Single-block exclusive scan over m counters (m up to a few million).
-__global__ void msm_scan_kernel(const uint32_t* counts, uint32_t* offsets, uint32_t* cursor, size_t m) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t total_before;
+// Single-block exclusive scan over the B bucket counts: entry offsets, task offsets
+// (ceil(count / cap) tasks per bucket) and the list of buckets that need a merge.
+__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* counts, uint32_t* offsets, uint32_t* cursor,
+                                                        uint32_t* task_off, uint32_t* multi, uint32_t B, uint32_t cap) {
+    __shared__ uint32_t ws_e[32], ws_t[32];
+    __shared__ uint32_t n_multi;
     const unsigned T = blockDim.x, tid = threadIdx.x;
-    const size_t per = (m + T - 1) / T;
-    const size_t lo = (size_t)tid * per, hi = lo + per < m ? lo + per : m;
-    uint32_t sum = 0;
-    for (size_t i = lo; i < hi; i++) sum += counts[i];
-    // block-wide exclusive scan of the per-thread sums
-    uint32_t incl = sum;
+    const uint32_t per = (B + T - 1) / T;
+    const uint32_t lo = tid * per < B ? tid * per : B, hi = lo + per < B ? lo + per : B;
+    uint32_t se = 0, stk = 0;
+    for (uint32_t i = lo; i < hi; i++) { const uint32_t cn = counts[i]; se += cn; stk += (cn + cap - 1) / cap; }
+    uint32_t ie = se, it = stk;
     const unsigned lane = tid & 31, wid = tid >> 5;
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += v;
+        uint32_t ve = __shfl_up_sync(0xffffffffu, ie, o), vt = __shfl_up_sync(0xffffffffu, it, o);
+        if (lane >= (unsigned)o) { ie += ve; it += vt; }
     }
-    if (lane == 31) warp_sums[wid] = incl;
-    if (tid == 0) total_before = 0;
+    if (lane == 31) { ws_e[wid] = ie; ws_t[wid] = it; }
+    if (tid == 0) n_multi = 0;
     __syncthreads();
     if (wid == 0) {
-        uint32_t ws = lane < (T >> 5) ? warp_sums[lane] : 0;
-        uint32_t wincl = ws;
+        uint32_t e = lane < (T >> 5) ? ws_e[lane] : 0, t = lane < (T >> 5) ? ws_t[lane] : 0;
+        uint32_t xe = e, xt = t;
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, wincl, o);
-            if (lane >= (unsigned)o) wincl += v;
+            uint32_t ve = __shfl_up_sync(0xffffffffu, xe, o), vt = __shfl_up_sync(0xffffffffu, xt, o);
+            if (lane >= (unsigned)o) { xe += ve; xt += vt; }
         }
-        warp_sums[lane] = wincl - ws;  // exclusive
+        ws_e[lane] = xe - e;  // exclusive
+        ws_t[lane] = xt - t;
+        if (lane == 31) task_off[B] = xt;  // total number of tasks
     }
     __syncthreads();
-    uint32_t run = warp_sums[wid] + (incl - sum);
-    for (size_t i = lo; i < hi; i++) {
-        offsets[i] = run;
-        cursor[i] = run;
-        run += counts[i];
+    uint32_t re = ws_e[wid] + (ie - se), rt = ws_t[wid] + (it - stk);
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t cn = counts[i], nt = (cn + cap - 1) / cap;
+        offsets[i] = re;
+        cursor[i] = re;
+        task_off[i] = rt;
+        if (nt > 1) multi[atomicAdd(&n_multi, 1u)] = i;
+        re += cn;
+        rt += nt;
     }
+    __syncthreads();
+    if (tid == 0) multi[B] = n_multi;
 }
 
-__global__ void msm_scatter_kernel(const uint32_t* digits, size_t n, unsigned c, unsigned W,
-                                   uint32_t* cursor, uint32_t* sorted) {
+// sorted[pos] = (w * stride + i) | sign, grouped by bucket
+__global__ void msm_scatter_kernel(const uint32_t* digits, size_t n, unsigned W, uint32_t stride, uint32_t* cursor,
+                                   uint32_t* sorted) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t B = 1u << (c - 1);
     for (unsigned w = 0; w < W; w++) {
         const uint32_t enc = digits[(size_t)w * n + i];
         if (enc == DIGIT_ZERO) continue;
-        const uint32_t pos = atomicAdd(&cursor[(size_t)w * B + (enc & 0x7fffffffu)], 1u);
-        sorted[pos] = (uint32_t)i | (enc & 0x80000000u);
+        const uint32_t pos = atomicAdd(&cursor[enc & 0x7fffffffu], 1u);
+        sorted[pos] = (w * stride + (uint32_t)i) | (enc & 0x80000000u);
     }
 }
 
-// One thread per (window, bucket): sum of +-P over the bucket's sorted entries.
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1_affine* bases, const uint32_t* sorted,
+// One thread per task: sum of +-T[idx] over <= cap consecutive entries of one bucket.
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1_affine* table, const uint32_t* sorted,
                                                             const uint32_t* offsets, const uint32_t* counts,
-                                                            size_t nbuckets, g1_xyzz* buckets) {
-    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nbuckets) return;
-    const uint32_t off = offsets[g], cnt = counts[g];
+                                                            const uint32_t* task_off, uint32_t B, uint32_t cap,
+                                                            g1_xyzz* buckets, g1_xyzz* task_out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= task_off[B]) return;
+    // owner bucket: task_off[b] <= t < task_off[b + 1]
+    uint32_t lo = 0, hi = B;  // invariant: task_off[lo] <= t, task_off[hi] > t
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (task_off[mid] <= t) lo = mid; else hi = mid;
+    }
+    const uint32_t b = lo;
+    const uint32_t cnt = counts[b];
+    const uint32_t first = offsets[b] + (t - task_off[b]) * cap;
+    const uint32_t last = first + cap < offsets[b] + cnt ? first + cap : offsets[b] + cnt;
     g1_xyzz acc = g1_xyzz::inf();
-    for (uint32_t j = 0; j < cnt; j++) {
-        const uint32_t e = sorted[off + j];
-        g1_affine q = msm_ld_affine(bases + (e & 0x7fffffffu));
+    for (uint32_t j = first; j < last; j++) {
+        const uint32_t e = sorted[j];
+        g1_affine q = msm_ld_affine(table + (e & 0x7fffffffu));
         if (e & 0x80000000u) q.y = neg(q.y);
         xyzz_madd(acc, q);
     }
-    buckets[g] = acc;
+    if (cnt <= cap) buckets[b] = acc; else task_out[t] = acc;
+}
+
+// One warp per multi-task bucket: lanes stride over the bucket's partial sums, then a
+// shared-memory tree over the 32 lanes.
+__global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* multi, const uint32_t* counts,
+                                                       const uint32_t* task_off, uint32_t B, uint32_t cap,
+                                                       const g1_xyzz* task_out, g1_xyzz* buckets) {
+    extern __shared__ uint4 smem_raw[];
+    g1_xyzz* sm = reinterpret_cast<g1_xyzz*>(smem_raw);
+    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t m = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (m >= multi[B]) return;  // whole warp exits together
+    const uint32_t b = multi[m];
+    const uint32_t nt = (counts[b] + cap - 1) / cap, t0 = task_off[b];
+    g1_xyzz acc = g1_xyzz::inf();
+    for (uint32_t j = lane; j < nt; j += 32) xyzz_add(acc, task_out[t0 + j]);
+    g1_xyzz* w = sm + wib * 32;
+    w[lane] = acc;
+    __syncwarp();
+    for (unsigned s = 16; s > 0; s >>= 1) {
+        if (lane < s) {
+            g1_xyzz o = w[lane + s];
+            xyzz_add(acc, o);
+            w[lane] = acc;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) buckets[b] = acc;
 }
 
 // acc <- k * acc for a small scalar k (double-and-add)
@@ -208,14 +268,20 @@ __global__ void __launch_bounds__(128) msm_tree_reduce_kernel(const g1_xyzz* in,
     if (tid == 0) out[(size_t)w * n_out + blockIdx.x] = v;
 }
 
-// result = sum_w 2^(c w) * R[w], normalised to affine.
-__global__ void msm_window_combine_kernel(const g1_xyzz* win, unsigned W, unsigned c, g1_affine* result) {
-    g1_xyzz acc = win[W - 1];
-    for (int w = (int)W - 2; w >= 0; w--) {
-        for (unsigned i = 0; i < c; i++) xyzz_dbl(acc);
-        xyzz_add(acc, win[w]);
+__global__ void msm_finish_kernel(const g1_xyzz* sum, g1_affine* result) { *result = xyzz_to_affine(*sum); }
+
+// T[w][i] = 2^c * T[w-1][i]: one thread per point walks the windows.  The XYZZ points are kept
+// in the output rows' own storage and converted with one batched inversion per thread.
+__global__ void __launch_bounds__(128) srs_table_window_kernel(g1_affine* table, size_t n, unsigned c, unsigned W) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_affine p = msm_ld_affine(table + i);
+    g1_xyzz acc = g1_xyzz::inf();
+    xyzz_madd(acc, p);
+    for (unsigned w = 1; w < W; w++) {
+        for (unsigned j = 0; j < c; j++) xyzz_dbl(acc);
+        table[(size_t)w * n + i] = xyzz_to_affine(acc);
     }
-    *result = xyzz_to_affine(acc);
 }
 
 __global__ void msm_top_nonzero_kernel(const fr_t* scalars, size_t n, long long* top) {
@@ -286,17 +352,26 @@ int srs_generate(zkp_ctx* ctx, const fr_t& tau, size_t n, g1_affine* out_dev) {
 }
 
 // ------------------------------------------------------------------ host driver
-static unsigned choose_window(size_t n) {
-    // minimise (bucket additions) + (bucket-reduce additions, weighted for their lower
-    // parallel efficiency)
+// Window width for an SRS of n powers: minimise (n * W mixed additions) + (bucket reduction,
+// weighted for its lower parallel efficiency).
+unsigned msm_choose_window(size_t n) {
     unsigned best = 4;
     double best_cost = 1e300;
-    for (unsigned c = 4; c <= 18; c++) {
+    for (unsigned c = 4; c <= 16; c++) {
         const unsigned W = 255 / c + 1;
-        const double cost = (double)n * W + 4.0 * W * (double)(1u << (c - 1));
+        const double cost = (double)(n ? n : 1) * W + 6.0 * (double)(1u << (c - 1));
         if (cost < best_cost) { best_cost = cost; best = c; }
     }
     return best;
+}
+
+// Fills rows 1 .. W-1 of the table from row 0 (the SRS powers themselves).
+int srs_build_table(zkp_ctx* ctx, zkp_srs* srs) {
+    if (srs->n == 0 || srs->W <= 1) return ZKP_OK;
+    srs_table_window_kernel<<<(unsigned)((srs->n + 127) / 128), 128, 0, ctx->stream>>>(srs->d, srs->n, srs->c, srs->W);
+    ZKP_LAUNCHED(ctx);
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKP_OK;
 }
 
 template <class T>
@@ -323,7 +398,8 @@ void msm_free(zkp_ctx* ctx) {
     MsmScratch* s = ctx->msm;
     if (!s) return;
     cudaFree(s->digits); cudaFree(s->sorted); cudaFree(s->counts); cudaFree(s->offsets); cudaFree(s->cursor);
-    cudaFree(s->buckets); cudaFree(s->part_a); cudaFree(s->part_b); cudaFree(s->result); cudaFree(s->top);
+    cudaFree(s->task_off); cudaFree(s->multi); cudaFree(s->buckets); cudaFree(s->task_out);
+    cudaFree(s->part_a); cudaFree(s->part_b); cudaFree(s->result); cudaFree(s->top);
     delete s;
     ctx->msm = nullptr;
 }
@@ -346,64 +422,65 @@ int msm_highest_nonzero(zkp_ctx* ctx, const fr_t* scalars_dev, size_t n, long lo
     return ZKP_OK;
 }
 
-int msm_run(zkp_ctx* ctx, const g1_affine* bases, const fr_t* scalars_dev, size_t n, g1_affine* out_host) {
+int msm_run(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* scalars_dev, size_t n, g1_affine* out_host) {
     int rc;
     if ((rc = set_device(ctx))) return rc;
     if (n == 0) {
         memset(out_host, 0, sizeof(g1_affine));
         return ZKP_OK;
     }
-    if (n >= (1ull << 31)) return ZKP_ERR_INVALID;
+    const unsigned c = srs->c, W = srs->W;
+    if (n > srs->n || (size_t)W * srs->n >= (1ull << 31)) return ZKP_ERR_INVALID;
     ctx->msm_points += n;
     MsmScratch* s;
     if ((rc = msm_scratch(ctx, &s))) return rc;
 
-    const unsigned c = ctx->msm_window ? (ctx->msm_window < 2 ? 2 : ctx->msm_window) : choose_window(n);
-    const unsigned W = 255 / c + 1;
     const uint32_t B = 1u << (c - 1);
-    const size_t nb = (size_t)W * B;
+    const size_t E = (size_t)W * n;  // upper bound on the number of non-zero digits
+    // task size: >= 32 entries, and few enough tasks that the partial-sum array stays small
+    const uint32_t cap = (uint32_t)((E >> 19) > 32 ? (E >> 19) : 32);
+    const size_t max_tasks = E / cap + B + 1;
     const uint32_t seg = B < 16 ? B : 16;
     const uint32_t nseg = B / seg;
 
-    if ((rc = ensure(ctx, &s->digits, &s->cap_n, (size_t)W * n))) return rc;
-    if ((rc = ensure(ctx, &s->sorted, &s->cap_entries, (size_t)W * n))) return rc;
-    {
-        size_t cap = s->cap_buckets;
-        if (cap < nb) {
-            size_t c1 = cap, c2 = cap, c3 = cap, c4 = cap;
-            if ((rc = ensure(ctx, &s->counts, &c1, nb))) return rc;
-            if ((rc = ensure(ctx, &s->offsets, &c2, nb))) return rc;
-            if ((rc = ensure(ctx, &s->cursor, &c3, nb))) return rc;
-            if ((rc = ensure(ctx, &s->buckets, &c4, nb))) return rc;
-            s->cap_buckets = nb;
-        }
+    if ((rc = ensure(ctx, &s->digits, &s->cap_entries, E))) return rc;
+    if ((rc = ensure(ctx, &s->sorted, &s->cap_sorted, E))) return rc;
+    if (s->cap_buckets < B) {
+        size_t c1 = s->cap_buckets, c2 = c1, c3 = c1, c6 = c1;
+        size_t c4 = c1 ? c1 + 1 : 0, c5 = c4;
+        if ((rc = ensure(ctx, &s->counts, &c1, B))) return rc;
+        if ((rc = ensure(ctx, &s->offsets, &c2, B))) return rc;
+        if ((rc = ensure(ctx, &s->cursor, &c3, B))) return rc;
+        if ((rc = ensure(ctx, &s->task_off, &c4, (size_t)B + 1))) return rc;
+        if ((rc = ensure(ctx, &s->multi, &c5, (size_t)B + 1))) return rc;
+        if ((rc = ensure(ctx, &s->buckets, &c6, B))) return rc;
+        s->cap_buckets = B;
     }
-    {
-        const size_t need = (size_t)W * nseg;
-        size_t cap = s->cap_partials;
-        if (cap < need) {
-            size_t c1 = cap, c2 = cap;
-            if ((rc = ensure(ctx, &s->part_a, &c1, need))) return rc;
-            if ((rc = ensure(ctx, &s->part_b, &c2, need))) return rc;
-            s->cap_partials = need;
-        }
+    if ((rc = ensure(ctx, &s->task_out, &s->cap_tasks, max_tasks))) return rc;
+    if (s->cap_partials < nseg) {
+        size_t c1 = s->cap_partials, c2 = c1;
+        if ((rc = ensure(ctx, &s->part_a, &c1, nseg))) return rc;
+        if ((rc = ensure(ctx, &s->part_b, &c2, nseg))) return rc;
+        s->cap_partials = nseg;
     }
 
     cudaStream_t st = ctx->stream;
     {
     ProfScope prof(ctx, "msm_sort");
-    ZKP_CUDA(ctx, cudaMemsetAsync(s->counts, 0, nb * sizeof(uint32_t), st));
+    ZKP_CUDA(ctx, cudaMemsetAsync(s->counts, 0, B * sizeof(uint32_t), st));
+    ZKP_CUDA(ctx, cudaMemsetAsync(s->buckets, 0, B * sizeof(g1_xyzz), st));  // all-zero XYZZ = infinity
     msm_digits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scalars_dev, n, c, W, s->digits, s->counts);
     ZKP_LAUNCHED(ctx);
-    msm_scan_kernel<<<1, 1024, 0, st>>>(s->counts, s->offsets, s->cursor, nb);
+    msm_scan_kernel<<<1, 1024, 0, st>>>(s->counts, s->offsets, s->cursor, s->task_off, s->multi, B, cap);
     ZKP_LAUNCHED(ctx);
-    msm_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->digits, n, c, W, s->cursor, s->sorted);
+    msm_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->digits, n, W, (uint32_t)srs->n, s->cursor,
+                                                                    s->sorted);
     ZKP_LAUNCHED(ctx);
     }
     {
     ProfScope prof(ctx, "msm_accumulate");
-    msm_accumulate_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(bases, s->sorted, s->offsets, s->counts, nb,
-                                                                        s->buckets);
+    msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(
+        srs->d, s->sorted, s->offsets, s->counts, s->task_off, B, cap, s->buckets, s->task_out);
     ZKP_LAUNCHED(ctx);
     }
     g1_xyzz* cur = s->part_a;
@@ -411,14 +488,20 @@ int msm_run(zkp_ctx* ctx, const g1_affine* bases, const fr_t* scalars_dev, size_
     {
     ProfScope prof(ctx, "msm_reduce");
     {
-        const size_t t = (size_t)nseg * W;
-        msm_bucket_reduce_kernel<<<(unsigned)((t + 63) / 64), 64, 0, st>>>(s->buckets, B, seg, nseg, W, s->part_a);
-        ZKP_LAUNCHED(ctx);
+        // at most min(B, E / cap) buckets can consist of more than one task
+        const size_t mm = E / cap < B ? E / cap : B;
+        if (mm) {
+            msm_merge_kernel<<<(unsigned)((mm + 3) / 4), 128, 128 * sizeof(g1_xyzz), st>>>(
+                s->multi, s->counts, s->task_off, B, cap, s->task_out, s->buckets);
+            ZKP_LAUNCHED(ctx);
+        }
     }
+    msm_bucket_reduce_kernel<<<(unsigned)((nseg + 63) / 64), 64, 0, st>>>(s->buckets, B, seg, nseg, 1, s->part_a);
+    ZKP_LAUNCHED(ctx);
     uint32_t n_in = nseg;
     while (n_in > 1) {
         const uint32_t n_out = (n_in + 127) / 128;
-        dim3 grid(n_out, W);
+        dim3 grid(n_out, 1);
         msm_tree_reduce_kernel<<<grid, 128, 128 * sizeof(g1_xyzz), st>>>(cur, n_in, nxt, n_out);
         ZKP_LAUNCHED(ctx);
         g1_xyzz* t = cur; cur = nxt; nxt = t;
@@ -427,7 +510,7 @@ int msm_run(zkp_ctx* ctx, const g1_affine* bases, const fr_t* scalars_dev, size_
     }
     {
     ProfScope prof(ctx, "msm_combine");
-    msm_window_combine_kernel<<<1, 1, 0, st>>>(cur, W, c, s->result);
+    msm_finish_kernel<<<1, 1, 0, st>>>(cur, s->result);
     ZKP_LAUNCHED(ctx);
     }
     g1_affine* h = reinterpret_cast<g1_affine*>(ctx->pinned);

@@ -46,6 +46,8 @@ SIGNATURES = {
     "zkp_buf_download": (_int, [_vp, _vp, _sz, _vp, _sz]),
     "zkp_buf_zero": (_int, [_vp, _vp, _sz, _sz]),
     "zkp_buf_copy": (_int, [_vp, _vp, _sz, _vp, _sz, _sz]),
+    "zkp_host_alloc": (_int, [_sz, ctypes.POINTER(_vp)]),
+    "zkp_host_free": (_int, [_vp]),
     "zkp_ntt": (_int, [_vp, _vp, _sz, _uint, _int, _int]),
     "zkp_ntt_dev": (_int, [_vp, _vp, _sz, _vp, _uint, _int, _int]),
     "zkp_ntt_dev_batch": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _uint, _int, _int, _uint]),
@@ -315,6 +317,31 @@ class Context:
     def poly_div_linear(self, ref, point, out, out_off=0):
         pt = np.ascontiguousarray(point, dtype=np.uint64).reshape(4)
         self.check(self.lib.zkp_poly_div_linear_dev(self.h, ref, _ptr(pt), out.h, out_off))
+
+
+_PINNED = {}   # data address -> (ctypes buffer, raw pointer); keeps the mapping alive
+
+
+def pinned_empty(shape, dtype=np.uint64):
+    """numpy array backed by page-locked host memory (``zkp_host_alloc``).  Release with
+    ``pinned_free``; otherwise it lives until process exit."""
+    lib = load_library()
+    count = int(np.prod(shape))
+    nbytes = count * np.dtype(dtype).itemsize
+    p = _vp()
+    rc = lib.zkp_host_alloc(nbytes, ctypes.byref(p))
+    if rc:
+        raise ZkpError(rc, "zkp_host_alloc(%d bytes)" % nbytes)
+    buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+    _PINNED[arr.ctypes.data] = (buf, p)
+    return arr
+
+
+def pinned_free(arr):
+    ent = _PINNED.pop(arr.ctypes.data, None)
+    if ent is not None:
+        load_library().zkp_host_free(ent[1])
 
 
 def fft_constant(k, kind):

@@ -80,6 +80,11 @@ int zkp_buf_zero(zkp_ctx* ctx, zkp_buf* buf, size_t off, size_t n);
 int zkp_buf_copy(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const zkp_buf* src, size_t src_off,
                  size_t n);
 
+/* Page-locked host memory for vectors that cross PCIe (the host-buffer entry points copy at
+ * full link rate only from pinned memory). */
+int zkp_host_alloc(size_t bytes, void** out);
+int zkp_host_free(void* p);
+
 /* ---- NTT: poly_commit::Fft ---------------------------------------------------------- */
 /* Host vector, in place.  data holds 2^k Fr; the first len_in are inputs, the rest is
  * treated as zero (Fft pads short inputs).  inverse=0,coset=0: dft; 1,0: idft (x n^-1);
@@ -101,7 +106,8 @@ int zkp_fft_elements_dev(zkp_ctx* ctx, unsigned k, zkp_buf* out);
 
 /* ---- KZG10 commit: PlonkParams ------------------------------------------------------- */
 /* Upload n affine powers (n x 12 uint64).  Mirrors PlonkParams::trim: the handle is what
- * `keypair` holds afterwards. */
+ * `keypair` holds afterwards.  The device expands them once into the window table
+ * 2^(c w) * P_i (W = floor(255/c) + 1 rows, 96 * W * n bytes of HBM) that every later commit uses. */
 int zkp_srs_load(zkp_ctx* ctx, const uint64_t* xy, size_t n, zkp_srs** out);
 int zkp_srs_free(zkp_ctx* ctx, zkp_srs* srs);
 size_t zkp_srs_len(const zkp_srs* srs);
@@ -125,7 +131,8 @@ int zkp_commit(zkp_ctx* ctx, const zkp_srs* srs, const uint64_t* coeffs, size_t 
                uint64_t out_xy[12]);
 int zkp_commit_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* coeffs, size_t off, size_t n,
                    uint64_t out_xy[12]);
-/* MSM tuning knob (window bits c; 0 = automatic). */
+/* MSM tuning knob (window bits c; 0 = automatic).  The window structure is baked into the SRS
+ * table when it is loaded, so this applies to SRS handles created afterwards. */
 int zkp_msm_set_window(zkp_ctx* ctx, unsigned c);
 
 /* ---- prover rounds on device-resident polynomials ------------------------------------ */

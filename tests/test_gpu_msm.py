@@ -46,18 +46,43 @@ def test_small_msm_vs_python(ctx, small_srs, n):
 def test_every_window_size(ctx, small_srs, c):
     """Signed-digit decomposition and carry handling for many window widths."""
     tau, pts = small_srs
-    srs = ctx.srs_load(g1_to_mont_limbs(pts))
     rng = SplitMix64(100 + c)
     n = 200
     sc = [rng.fr() for _ in range(n)]
     # digits that hit the +2^(c-1) boundary, all-ones windows and the largest scalar
     sc[:6] = [R_MOD - 1, (1 << (c - 1)), (1 << c) - 1, (1 << 255) % R_MOD, ((1 << 254) - 1), (1 << c) + (1 << (c - 1))]
-    ctx.set_msm_window(c)
+    ctx.set_msm_window(c)   # baked into the SRS window table at load time
     try:
-        got = g1_from_mont_limbs(ctx.msm(srs, fr_to_mont_limbs(sc)))[0]
+        srs = ctx.srs_load(g1_to_mont_limbs(pts))
     finally:
         ctx.set_msm_window(0)
+    got = g1_from_mont_limbs(ctx.msm(srs, fr_to_mont_limbs(sc)))[0]
     assert got == curve.commit_known_dlog([pow(tau, i, R_MOD) for i in range(n)], sc)
+
+
+@pytest.mark.parametrize("profile", ["all_equal", "tiny_values", "carry_only_top", "one_hot"])
+def test_skewed_digit_distributions(ctx, profile):
+    """Giant buckets (every scalar sharing a digit, small selector-like coefficients, a top
+    window holding only the carry) are cut into tasks and merged; result unchanged."""
+    n = 3000
+    rng = SplitMix64(7)
+    tau = rng.fr()
+    ctx.set_msm_window(15 if profile == "carry_only_top" else 0)
+    try:
+        srs = ctx.srs_generate(fr_to_mont_limbs([tau])[0], n)
+    finally:
+        ctx.set_msm_window(0)
+    if profile == "all_equal":
+        sc = [R_MOD - 5] * n
+    elif profile == "tiny_values":
+        sc = [(i * 7) % 3 for i in range(n)]
+    elif profile == "carry_only_top":
+        sc = [R_MOD - 1 - i for i in range(n)]
+    else:
+        sc = [0] * n
+        sc[n - 1] = 12345
+    exp = curve.commit_known_dlog([pow(tau, i, R_MOD) for i in range(n)], sc)
+    assert g1_from_mont_limbs(ctx.msm(srs, fr_to_mont_limbs(sc)))[0] == exp
 
 
 def test_degenerate_bases_and_cancellation(ctx):
