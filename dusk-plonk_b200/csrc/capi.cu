@@ -189,6 +189,38 @@ int zkp_buf_copy(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const zkp_buf* src,
     return ZKP_OK;
 }
 
+/* Keccak-f[1600] for the host-side Merlin/STROBE transcript (TranscriptProtocol stays on the
+ * host; this is plain C so the Python mirror does not spend its time in a bytecode loop). */
+void zkp_keccak_f1600(uint64_t st[25]) {
+    static const uint64_t RC[24] = {
+        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL,
+        0x000000000000808BULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+        0x000000000000008AULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000AULL,
+        0x000000008000808BULL, 0x800000000000008BULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+        0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800AULL, 0x800000008000000AULL,
+        0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    static const int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39,
+                                41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+    for (int r = 0; r < 24; r++) {
+        uint64_t c[5], b[25];
+        for (int x = 0; x < 5; x++) c[x] = st[x] ^ st[x + 5] ^ st[x + 10] ^ st[x + 15] ^ st[x + 20];
+        for (int x = 0; x < 5; x++) {
+            const uint64_t t = c[(x + 1) % 5];
+            const uint64_t d = c[(x + 4) % 5] ^ ((t << 1) | (t >> 63));
+            for (int y = 0; y < 25; y += 5) st[x + y] ^= d;
+        }
+        for (int x = 0; x < 5; x++)
+            for (int y = 0; y < 5; y++) {
+                const uint64_t v = st[x + 5 * y];
+                const int k = ROT[x + 5 * y];
+                b[y + 5 * ((2 * x + 3 * y) % 5)] = k ? ((v << k) | (v >> (64 - k))) : v;
+            }
+        for (int y = 0; y < 25; y += 5)
+            for (int x = 0; x < 5; x++) st[x + y] = b[x + y] ^ (~b[(x + 1) % 5 + y] & b[(x + 2) % 5 + y]);
+        st[0] ^= RC[r];
+    }
+}
+
 int zkp_host_alloc(size_t bytes, void** out) {
     if (!out) return ZKP_ERR_INVALID;
     cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
@@ -285,6 +317,10 @@ int zkp_srs_load(zkp_ctx* ctx, const uint64_t* xy, size_t n, zkp_srs** out) {
 }
 
 int zkp_srs_generate(zkp_ctx* ctx, const uint64_t tau[4], size_t n, zkp_srs** out) {
+    return zkp_srs_generate_range(ctx, tau, 0, n, out);
+}
+
+int zkp_srs_generate_range(zkp_ctx* ctx, const uint64_t tau[4], size_t first, size_t n, zkp_srs** out) {
     if (!ctx || !out || !tau) return ZKP_ERR_INVALID;
     int rc;
     if ((rc = set_device(ctx))) return rc;
@@ -292,7 +328,7 @@ int zkp_srs_generate(zkp_ctx* ctx, const uint64_t tau[4], size_t n, zkp_srs** ou
     if ((rc = srs_alloc(ctx, n, &s))) return rc;
     fr_t t;
     memcpy(t.l, tau, 32);
-    rc = srs_generate(ctx, t, n, s->d);
+    rc = srs_generate(ctx, t, first, n, s->d);
     if (!rc) rc = srs_build_table(ctx, s);
     if (rc) { cudaFree(s->d); delete s; return rc; }
     *out = s;
@@ -340,6 +376,11 @@ int zkp_commit_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* coeffs, size
     if (rc) return rc;
     if (top >= (long long)srs->n) return ZKP_ERR_DEGREE;
     return msm_run(ctx, srs, coeffs->d + off, (size_t)(top + 1), reinterpret_cast<g1_affine*>(out_xy));
+}
+
+int zkp_poly_degree_dev(zkp_ctx* ctx, const zkp_buf* coeffs, size_t off, size_t n, long long* top) {
+    if (!ctx || !coeffs || !top || off + n > coeffs->n) return ZKP_ERR_INVALID;
+    return msm_highest_nonzero(ctx, coeffs->d + off, n, top);
 }
 
 static int with_uploaded(zkp_ctx* ctx, const uint64_t* scalars, size_t n, zkp_buf** out) {

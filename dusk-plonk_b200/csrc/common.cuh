@@ -114,7 +114,7 @@ int msm_run(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* scalars_dev, size_t n,
 unsigned msm_choose_window(size_t n);
 int srs_build_table(zkp_ctx* ctx, zkp_srs* srs);
 int msm_highest_nonzero(zkp_ctx* ctx, const fr_t* scalars_dev, size_t n, long long* out);
-int srs_generate(zkp_ctx* ctx, const fr_t& tau, size_t n, g1_affine* out_dev);
+int srs_generate(zkp_ctx* ctx, const fr_t& tau, size_t first, size_t n, g1_affine* out_dev);
 void msm_free(zkp_ctx* ctx);
 
 // prover.cu

@@ -20,8 +20,8 @@
 //   4. msm_accumulate_kernel  one thread per task, XYZZ mixed additions (8M + 2S each, 384-bit
 //                             Montgomery on the integer pipe) -- the hot kernel
 //   5. msm_merge_kernel       buckets made of several tasks: one warp sums the partials
-//   6. msm_bucket_reduce_kernel + msm_tree_reduce_kernel   sum_b (b+1) * B[b]
-//   7. msm_finish_kernel      one Fermat inversion -> affine
+//   6. msm_plane_sum / plane_combine / final_sum   sum_b (b+1) * B[b] as c bit-plane tree sums
+//   7. host: one Fermat inversion -> affine
 // Addition in G1 is commutative and the result is normalised to affine, so the output is
 // bit-identical to any correct CPU evaluation regardless of accumulation order.
 #include "common.cuh"
@@ -101,6 +101,11 @@ __global__ void msm_digits_kernel(const fr_t* scalars, size_t n, unsigned c, uns
     }
 }
 
+// A bucket of up to 2 * cap entries is one task; larger ones are cut into ceil(count / cap).
+__host__ __device__ __forceinline__ uint32_t msm_ntasks(uint32_t count, uint32_t cap) {
+    return count <= 2 * cap ? (count ? 1u : 0u) : (count + cap - 1) / cap;
+}
+
 // Single-block exclusive scan over the B bucket counts: entry offsets, task offsets
 // (ceil(count / cap) tasks per bucket) and the list of buckets that need a merge.
 __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* counts, uint32_t* offsets, uint32_t* cursor,
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* counts, 
     const uint32_t per = (B + T - 1) / T;
     const uint32_t lo = tid * per < B ? tid * per : B, hi = lo + per < B ? lo + per : B;
     uint32_t se = 0, stk = 0;
-    for (uint32_t i = lo; i < hi; i++) { const uint32_t cn = counts[i]; se += cn; stk += (cn + cap - 1) / cap; }
+    for (uint32_t i = lo; i < hi; i++) { const uint32_t cn = counts[i]; se += cn; stk += msm_ntasks(cn, cap); }
     uint32_t ie = se, it = stk;
     const unsigned lane = tid & 31, wid = tid >> 5;
     for (int o = 1; o < 32; o <<= 1) {
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* counts, 
     __syncthreads();
     uint32_t re = ws_e[wid] + (ie - se), rt = ws_t[wid] + (it - stk);
     for (uint32_t i = lo; i < hi; i++) {
-        const uint32_t cn = counts[i], nt = (cn + cap - 1) / cap;
+        const uint32_t cn = counts[i], nt = msm_ntasks(cn, cap);
         offsets[i] = re;
         cursor[i] = re;
         task_off[i] = rt;
@@ -175,8 +180,9 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1_affine* ta
     }
     const uint32_t b = lo;
     const uint32_t cnt = counts[b];
+    const bool single = cnt <= 2 * cap;
     const uint32_t first = offsets[b] + (t - task_off[b]) * cap;
-    const uint32_t last = first + cap < offsets[b] + cnt ? first + cap : offsets[b] + cnt;
+    const uint32_t last = (single || first + cap > offsets[b] + cnt) ? offsets[b] + cnt : first + cap;
     g1_xyzz acc = g1_xyzz::inf();
     for (uint32_t j = first; j < last; j++) {
         const uint32_t e = sorted[j];
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1_affine* ta
         if (e & 0x80000000u) q.y = neg(q.y);
         xyzz_madd(acc, q);
     }
-    if (cnt <= cap) buckets[b] = acc; else task_out[t] = acc;
+    if (single) buckets[b] = acc; else task_out[t] = acc;
 }
 
 // One warp per multi-task bucket: lanes stride over the bucket's partial sums, then a
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* multi, c
     const uint32_t m = blockIdx.x * (blockDim.x >> 5) + wib;
     if (m >= multi[B]) return;  // whole warp exits together
     const uint32_t b = multi[m];
-    const uint32_t nt = (counts[b] + cap - 1) / cap, t0 = task_off[b];
+    const uint32_t nt = msm_ntasks(counts[b], cap), t0 = task_off[b];
     g1_xyzz acc = g1_xyzz::inf();
     for (uint32_t j = lane; j < nt; j += 32) xyzz_add(acc, task_out[t0 + j]);
     g1_xyzz* w = sm + wib * 32;
@@ -215,49 +221,32 @@ __global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* multi, c
     if (lane == 0) buckets[b] = acc;
 }
 
-// acc <- k * acc for a small scalar k (double-and-add)
-__device__ void xyzz_mul_small(g1_xyzz& acc, uint32_t k) {
-    g1_xyzz base = acc;
-    acc = g1_xyzz::inf();
-    if (k == 0) return;
-    for (int bit = 31 - __clz(k); bit >= 0; bit--) {
-        xyzz_dbl(acc);
-        if ((k >> bit) & 1) xyzz_add(acc, base);
-    }
+// ---- bucket reduction: sum_b (b + 1) * B[b] = sum_j 2^j * S_j,  S_j = sum of the buckets whose
+// weight v = b + 1 has bit j set.  The c plane sums are independent tree reductions and the 2^j
+// factors are applied in parallel, so the dependent chain is ~ (8 + 7 + log chunks + c + log c)
+// point operations instead of a running sum over every bucket.
+static constexpr unsigned RED_T = 128, RED_L = 8;  // threads per block, buckets per thread
+
+// k-th weight (k >= 0) with bit j set
+__device__ __forceinline__ uint32_t weight_with_bit(uint32_t k, unsigned j) {
+    return ((k >> j) << (j + 1)) | (1u << j) | (k & ((1u << j) - 1));
 }
 
-// Each thread owns `seg` consecutive buckets of one window and emits
-//   sum_{b in segment} (b + 1) * B[w][b]
-// as a running-sum (weights 1..seg) plus seg_lo * (plain sum).
-__global__ void __launch_bounds__(64) msm_bucket_reduce_kernel(const g1_xyzz* buckets, uint32_t B, uint32_t seg,
-                                                              uint32_t nseg, unsigned W, g1_xyzz* parts) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (size_t)nseg * W) return;
-    const uint32_t w = (uint32_t)(t / nseg), sidx = (uint32_t)(t % nseg);
-    const uint32_t lo = sidx * seg;
-    const uint32_t hi = lo + seg < B ? lo + seg : B;
-    const g1_xyzz* bw = buckets + (size_t)w * B;
-    g1_xyzz run = g1_xyzz::inf(), sum = g1_xyzz::inf();
-    for (uint32_t b = hi; b-- > lo;) {
-        xyzz_add(run, bw[b]);
-        xyzz_add(sum, run);
-    }
-    xyzz_mul_small(run, lo);
-    xyzz_add(sum, run);
-    parts[t] = sum;
-}
-
-// Sums groups of up to blockDim.x partial points: in[w][0..n_in) -> out[w][0..ceil(n_in/blockDim))
-__global__ void __launch_bounds__(128) msm_tree_reduce_kernel(const g1_xyzz* in, uint32_t n_in, g1_xyzz* out,
-                                                             uint32_t n_out) {
+// grid (chunks, c): block (x, j) sums RED_T * RED_L selected buckets of plane j
+__global__ void __launch_bounds__(RED_T) msm_plane_sum_kernel(const g1_xyzz* buckets, uint32_t B, uint32_t chunks,
+                                                            g1_xyzz* parts) {
     extern __shared__ uint4 smem_raw[];
     g1_xyzz* sm = reinterpret_cast<g1_xyzz*>(smem_raw);
-    const unsigned tid = threadIdx.x, w = blockIdx.y;
-    const uint32_t idx = blockIdx.x * blockDim.x + tid;
-    g1_xyzz v = idx < n_in ? in[(size_t)w * n_in + idx] : g1_xyzz::inf();
+    const unsigned tid = threadIdx.x, j = blockIdx.y;
+    const uint32_t k0 = (blockIdx.x * RED_T + tid) * RED_L;
+    g1_xyzz v = g1_xyzz::inf();
+    for (unsigned i = 0; i < RED_L; i++) {
+        const uint32_t wgt = weight_with_bit(k0 + i, j);
+        if (wgt <= B) xyzz_add(v, buckets[wgt - 1]);
+    }
     sm[tid] = v;
     __syncthreads();
-    for (unsigned s = blockDim.x >> 1; s > 0; s >>= 1) {
+    for (unsigned s = RED_T >> 1; s > 0; s >>= 1) {
         if (tid < s) {
             g1_xyzz o = sm[tid + s];
             xyzz_add(v, o);
@@ -265,13 +254,51 @@ __global__ void __launch_bounds__(128) msm_tree_reduce_kernel(const g1_xyzz* in,
         }
         __syncthreads();
     }
-    if (tid == 0) out[(size_t)w * n_out + blockIdx.x] = v;
+    if (tid == 0) parts[(size_t)j * chunks + blockIdx.x] = v;
 }
 
-__global__ void msm_finish_kernel(const g1_xyzz* sum, g1_affine* result) { *result = xyzz_to_affine(*sum); }
+// block j (one warp): sums plane j's chunk partials, then lane 0 applies 2^j.
+__global__ void __launch_bounds__(32) msm_plane_combine_kernel(const g1_xyzz* parts, uint32_t chunks,
+                                                              g1_xyzz* planes) {
+    __shared__ g1_xyzz w[32];
+    const unsigned lane = threadIdx.x, j = blockIdx.x;
+    g1_xyzz v = g1_xyzz::inf();
+    for (uint32_t i = lane; i < chunks; i += 32) xyzz_add(v, parts[(size_t)j * chunks + i]);
+    w[lane] = v;
+    __syncwarp();
+    for (unsigned s = 16; s > 0; s >>= 1) {
+        if (lane < s) {
+            g1_xyzz o = w[lane + s];
+            xyzz_add(v, o);
+            w[lane] = v;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        for (unsigned i = 0; i < j; i++) xyzz_dbl(v);
+        planes[j] = v;
+    }
+}
 
-// T[w][i] = 2^c * T[w-1][i]: one thread per point walks the windows.  The XYZZ points are kept
-// in the output rows' own storage and converted with one batched inversion per thread.
+// one warp: tree over the c <= 32 weighted plane sums
+__global__ void __launch_bounds__(32) msm_final_sum_kernel(const g1_xyzz* planes, unsigned c, g1_xyzz* out) {
+    __shared__ g1_xyzz w[32];
+    const unsigned lane = threadIdx.x;
+    g1_xyzz v = lane < c ? planes[lane] : g1_xyzz::inf();
+    w[lane] = v;
+    __syncwarp();
+    for (unsigned s = 16; s > 0; s >>= 1) {
+        if (lane < s) {
+            g1_xyzz o = w[lane + s];
+            xyzz_add(v, o);
+            w[lane] = v;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) *out = v;
+}
+
+// T[w][i] = 2^c * T[w-1][i]: one thread per point walks the windows (load-time only).
 __global__ void __launch_bounds__(128) srs_table_window_kernel(g1_affine* table, size_t n, unsigned c, unsigned W) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -325,10 +352,11 @@ __global__ void srs_table_kernel(g1_affine* tbl) {
     }
 }
 
-__global__ void __launch_bounds__(128) srs_powers_kernel(const g1_affine* tbl, fr_t tau, size_t n, g1_affine* out) {
+__global__ void __launch_bounds__(128) srs_powers_kernel(const g1_affine* tbl, fr_t tau, size_t first, size_t n,
+                                                        g1_affine* out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const fr_t s = from_mont(pow_u64(tau, (uint64_t)i));
+    const fr_t s = from_mont(pow_u64(tau, (uint64_t)(first + i)));
     g1_xyzz acc = g1_xyzz::inf();
     for (unsigned w = 0; w < FB_W; w++) {
         const uint32_t d = (s.l[w >> 2] >> (8 * (w & 3))) & 255u;
@@ -337,13 +365,13 @@ __global__ void __launch_bounds__(128) srs_powers_kernel(const g1_affine* tbl, f
     out[i] = xyzz_to_affine(acc);
 }
 
-int srs_generate(zkp_ctx* ctx, const fr_t& tau, size_t n, g1_affine* out_dev) {
+int srs_generate(zkp_ctx* ctx, const fr_t& tau, size_t first, size_t n, g1_affine* out_dev) {
     g1_affine* tbl = nullptr;
     ZKP_CUDA(ctx, cudaMalloc(&tbl, sizeof(g1_affine) * FB_W * FB_D));
     srs_table_kernel<<<1, 32, 0, ctx->stream>>>(tbl);
     ZKP_LAUNCHED(ctx);
     if (n) {
-        srs_powers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(tbl, tau, n, out_dev);
+        srs_powers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(tbl, tau, first, n, out_dev);
         ZKP_LAUNCHED(ctx);
     }
     ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -352,6 +380,60 @@ int srs_generate(zkp_ctx* ctx, const fr_t& tau, size_t n, g1_affine* out_dev) {
 }
 
 // ------------------------------------------------------------------ host driver
+// Host-side Fq (6 x u64 CIOS Montgomery) for the one inversion per MSM.
+namespace hostfq {
+typedef unsigned __int128 u128;
+static const uint64_t P[6] = {0xb9feffffffffaaabULL, 0x1eabfffeb153ffffULL, 0x6730d2a0f6b0f624ULL,
+                              0x64774b84f38512bfULL, 0x4b1ba7b6434bacd7ULL, 0x1a0111ea397fe69aULL};
+static const uint64_t INV = 0x89f3fffcfffcfffdULL;
+static const uint64_t ONE[6] = {0x760900000002fffdULL, 0xebf4000bc40c0002ULL, 0x5f48985753c758baULL,
+                                0x77ce585370525745ULL, 0x5c071a97a256ec6dULL, 0x15f65ec3fa80e493ULL};
+struct fq { uint64_t l[6]; };
+static inline bool geq_p(const uint64_t* a) {
+    for (int i = 5; i >= 0; i--) { if (a[i] > P[i]) return true; if (a[i] < P[i]) return false; }
+    return true;
+}
+static inline fq mul(const fq& a, const fq& b) {
+    uint64_t t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 6; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 6; j++) { u128 s = (u128)a.l[j] * b.l[i] + t[j] + c; t[j] = (uint64_t)s; c = (uint64_t)(s >> 64); }
+        u128 s = (u128)t[6] + c; t[6] = (uint64_t)s; t[7] = (uint64_t)(s >> 64);
+        const uint64_t m = t[0] * INV;
+        s = (u128)m * P[0] + t[0]; c = (uint64_t)(s >> 64);
+        for (int j = 1; j < 6; j++) { s = (u128)m * P[j] + t[j] + c; t[j - 1] = (uint64_t)s; c = (uint64_t)(s >> 64); }
+        s = (u128)t[6] + c; t[5] = (uint64_t)s; t[6] = t[7] + (uint64_t)(s >> 64);
+    }
+    if (t[6] || geq_p(t)) {
+        uint64_t br = 0;
+        for (int i = 0; i < 6; i++) { u128 d = (u128)t[i] - P[i] - br; t[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
+    }
+    fq r; memcpy(r.l, t, 48); return r;
+}
+static inline fq inv(const fq& a) {  // a^(p-2)
+    uint64_t e[6]; memcpy(e, P, 48); e[0] -= 2;
+    fq acc; memcpy(acc.l, ONE, 48);
+    for (int i = 383; i >= 0; i--) {
+        acc = mul(acc, acc);
+        if ((e[i / 64] >> (i % 64)) & 1) acc = mul(acc, a);
+    }
+    return acc;
+}
+}  // namespace hostfq
+
+// x = X / ZZ, y = Y / ZZZ with 1/ZZ = (ZZ / ZZZ)^2
+static g1_affine host_xyzz_to_affine(const g1_xyzz& a) {
+    g1_affine r = g1_affine::inf();
+    if (a.is_inf()) return r;
+    hostfq::fq X, Y, ZZ, ZZZ;
+    memcpy(X.l, a.x.l, 48); memcpy(Y.l, a.y.l, 48); memcpy(ZZ.l, a.zz.l, 48); memcpy(ZZZ.l, a.zzz.l, 48);
+    const hostfq::fq t = hostfq::inv(ZZZ);
+    const hostfq::fq zi = hostfq::mul(ZZ, t);
+    const hostfq::fq x = hostfq::mul(X, hostfq::mul(zi, zi)), y = hostfq::mul(Y, t);
+    memcpy(r.x.l, x.l, 48); memcpy(r.y.l, y.l, 48);
+    return r;
+}
+
 // Window width for an SRS of n powers: minimise (n * W mixed additions) + (bucket reduction,
 // weighted for its lower parallel efficiency).
 unsigned msm_choose_window(size_t n) {
@@ -440,8 +522,9 @@ int msm_run(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* scalars_dev, size_t n,
     // task size: >= 32 entries, and few enough tasks that the partial-sum array stays small
     const uint32_t cap = (uint32_t)((E >> 19) > 32 ? (E >> 19) : 32);
     const size_t max_tasks = E / cap + B + 1;
-    const uint32_t seg = B < 16 ? B : 16;
-    const uint32_t nseg = B / seg;
+    // plane sums: weights with bit j set number at most B/2 (+1 for the top plane)
+    const uint32_t chunks = (uint32_t)((B / 2 + 1 + RED_T * RED_L - 1) / (RED_T * RED_L));
+    const size_t nparts = (size_t)chunks * c;
 
     if ((rc = ensure(ctx, &s->digits, &s->cap_entries, E))) return rc;
     if ((rc = ensure(ctx, &s->sorted, &s->cap_sorted, E))) return rc;
@@ -457,11 +540,11 @@ int msm_run(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* scalars_dev, size_t n,
         s->cap_buckets = B;
     }
     if ((rc = ensure(ctx, &s->task_out, &s->cap_tasks, max_tasks))) return rc;
-    if (s->cap_partials < nseg) {
-        size_t c1 = s->cap_partials, c2 = c1;
-        if ((rc = ensure(ctx, &s->part_a, &c1, nseg))) return rc;
-        if ((rc = ensure(ctx, &s->part_b, &c2, nseg))) return rc;
-        s->cap_partials = nseg;
+    if (s->cap_partials < nparts) {
+        size_t c1 = s->cap_partials, c2 = s->part_b ? 1 : 0;
+        if ((rc = ensure(ctx, &s->part_a, &c1, nparts))) return rc;
+        if ((rc = ensure(ctx, &s->part_b, &c2, 33))) return rc;
+        s->cap_partials = nparts;
     }
 
     cudaStream_t st = ctx->stream;
@@ -483,40 +566,30 @@ int msm_run(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* scalars_dev, size_t n,
         srs->d, s->sorted, s->offsets, s->counts, s->task_off, B, cap, s->buckets, s->task_out);
     ZKP_LAUNCHED(ctx);
     }
-    g1_xyzz* cur = s->part_a;
-    g1_xyzz* nxt = s->part_b;
     {
     ProfScope prof(ctx, "msm_reduce");
     {
-        // at most min(B, E / cap) buckets can consist of more than one task
-        const size_t mm = E / cap < B ? E / cap : B;
+        // at most min(B, E / (2 cap)) buckets can consist of more than one task
+        const size_t mm = E / (2 * (size_t)cap) < B ? E / (2 * (size_t)cap) : B;
         if (mm) {
             msm_merge_kernel<<<(unsigned)((mm + 3) / 4), 128, 128 * sizeof(g1_xyzz), st>>>(
                 s->multi, s->counts, s->task_off, B, cap, s->task_out, s->buckets);
             ZKP_LAUNCHED(ctx);
         }
     }
-    msm_bucket_reduce_kernel<<<(unsigned)((nseg + 63) / 64), 64, 0, st>>>(s->buckets, B, seg, nseg, 1, s->part_a);
+    msm_plane_sum_kernel<<<dim3(chunks, c), RED_T, RED_T * sizeof(g1_xyzz), st>>>(s->buckets, B, chunks, s->part_a);
     ZKP_LAUNCHED(ctx);
-    uint32_t n_in = nseg;
-    while (n_in > 1) {
-        const uint32_t n_out = (n_in + 127) / 128;
-        dim3 grid(n_out, 1);
-        msm_tree_reduce_kernel<<<grid, 128, 128 * sizeof(g1_xyzz), st>>>(cur, n_in, nxt, n_out);
-        ZKP_LAUNCHED(ctx);
-        g1_xyzz* t = cur; cur = nxt; nxt = t;
-        n_in = n_out;
-    }
-    }
-    {
-    ProfScope prof(ctx, "msm_combine");
-    msm_finish_kernel<<<1, 1, 0, st>>>(cur, s->result);
+    msm_plane_combine_kernel<<<c, 32, 0, st>>>(s->part_a, chunks, s->part_b);
+    ZKP_LAUNCHED(ctx);
+    msm_final_sum_kernel<<<1, 32, 0, st>>>(s->part_b, c, s->part_b + 32);
     ZKP_LAUNCHED(ctx);
     }
-    g1_affine* h = reinterpret_cast<g1_affine*>(ctx->pinned);
-    ZKP_CUDA(ctx, cudaMemcpyAsync(h, s->result, sizeof(g1_affine), cudaMemcpyDeviceToHost, st));
+    // the single inversion of the conversion to affine runs on the host (one Fq Fermat chain
+    // would occupy one GPU thread for ~0.6 ms)
+    g1_xyzz* h = reinterpret_cast<g1_xyzz*>(ctx->pinned);
+    ZKP_CUDA(ctx, cudaMemcpyAsync(h, s->part_b + 32, sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
     ZKP_CUDA(ctx, cudaStreamSynchronize(st));
-    memcpy(out_host, h, sizeof(g1_affine));
+    *out_host = host_xyzz_to_affine(*h);
     return ZKP_OK;
 }
 

@@ -46,6 +46,7 @@ SIGNATURES = {
     "zkp_buf_download": (_int, [_vp, _vp, _sz, _vp, _sz]),
     "zkp_buf_zero": (_int, [_vp, _vp, _sz, _sz]),
     "zkp_buf_copy": (_int, [_vp, _vp, _sz, _vp, _sz, _sz]),
+    "zkp_keccak_f1600": (None, [_vp]),
     "zkp_host_alloc": (_int, [_sz, ctypes.POINTER(_vp)]),
     "zkp_host_free": (_int, [_vp]),
     "zkp_ntt": (_int, [_vp, _vp, _sz, _uint, _int, _int]),
@@ -57,6 +58,8 @@ SIGNATURES = {
     "zkp_srs_free": (_int, [_vp, _vp]),
     "zkp_srs_len": (_sz, [_vp]),
     "zkp_srs_generate": (_int, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "zkp_srs_generate_range": (_int, [_vp, _vp, _sz, _sz, ctypes.POINTER(_vp)]),
+    "zkp_poly_degree_dev": (_int, [_vp, _vp, _sz, _sz, ctypes.POINTER(ctypes.c_longlong)]),
     "zkp_srs_download": (_int, [_vp, _vp, _sz, _vp, _sz]),
     "zkp_msm_g1": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "zkp_msm_g1_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp]),
@@ -243,8 +246,15 @@ class Context:
         xy = np.ascontiguousarray(xy, dtype=np.uint64).reshape(-1, 12)
         return Srs(self, xy=xy)
 
-    def srs_generate(self, tau_mont, n):
-        return Srs(self, tau=np.ascontiguousarray(tau_mont, dtype=np.uint64).reshape(4), n=n)
+    def srs_generate(self, tau_mont, n, first=0):
+        return Srs(self, tau=np.ascontiguousarray(tau_mont, dtype=np.uint64).reshape(4), n=n, first=first)
+
+    def poly_degree(self, buf, off=0, n=None):
+        """Highest non-zero index of buf[off .. off+n), -1 if all zero."""
+        n = buf.n - off if n is None else n
+        top = ctypes.c_longlong()
+        self.check(self.lib.zkp_poly_degree_dev(self.h, buf.h, off, n, ctypes.byref(top)))
+        return int(top.value)
 
     def msm(self, srs, scalars):
         scalars = as_fr_array(scalars)
@@ -403,14 +413,14 @@ class DeviceBuffer:
 class Srs:
     """Device-resident SRS powers (``zkp_srs``)."""
 
-    def __init__(self, ctx, xy=None, tau=None, n=None):
+    def __init__(self, ctx, xy=None, tau=None, n=None, first=0):
         self.ctx = ctx
         h = _vp()
         if xy is not None:
             ctx.check(ctx.lib.zkp_srs_load(ctx.h, _ptr(xy), xy.shape[0], ctypes.byref(h)))
             self.n = xy.shape[0]
         else:
-            ctx.check(ctx.lib.zkp_srs_generate(ctx.h, _ptr(tau), n, ctypes.byref(h)))
+            ctx.check(ctx.lib.zkp_srs_generate_range(ctx.h, _ptr(tau), first, n, ctypes.byref(h)))
             self.n = n
         self.h = h
 

@@ -60,3 +60,32 @@ def g1_from_mont(xy):
     x = int.from_bytes(raw[:48], "little") * _FQ_RINV % P_MOD
     y = int.from_bytes(raw[48:], "little") * _FQ_RINV % P_MOD
     return None if (x == 0 and y == 0) else (x, y)
+
+
+# ---- host-side G1 addition (used only to combine per-GPU partial commitments: G - 1 adds)
+def g1_add(p, q):
+    """Affine (x, y) / None points on y^2 = x^3 + 4."""
+    if p is None:
+        return q
+    if q is None:
+        return p
+    x1, y1 = p
+    x2, y2 = q
+    if x1 == x2:
+        if (y1 + y2) % P_MOD == 0:
+            return None
+        lam = 3 * x1 * x1 * pow(2 * y1, -1, P_MOD) % P_MOD
+    else:
+        lam = (y2 - y1) * pow(x2 - x1, -1, P_MOD) % P_MOD
+    x3 = (lam * lam - x1 - x2) % P_MOD
+    return (x3, (lam * (x1 - x3) - y1) % P_MOD)
+
+
+def g1_to_bytes(p):
+    """96 raw bytes (x || y big-endian, zeros for the identity): the inter-rank wire format."""
+    return bytes(96) if p is None else p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big")
+
+
+def g1_from_bytes(b):
+    x, y = int.from_bytes(b[:48], "big"), int.from_bytes(b[48:96], "big")
+    return None if x == 0 and y == 0 else (x, y)

@@ -72,7 +72,7 @@ class PlonkKey:
             buf = ctx.upload(fr_column_to_mont(col, n))
             ctx.ntt_dev(buf, n, buf, k, True, False)
             pk.poly[s] = buf
-            vk[s] = g1_from_mont(keypair.commit_or_default(buf).xy)
+            vk[s] = keypair.commit_or_default(buf).affine()
             if vk[s] is not None and s in ("q_range", "q_logic", "q_fixed_group_add", "q_variable_group_add"):
                 pk.widget_mask |= 1 << ("q_range", "q_logic", "q_fixed_group_add", "q_variable_group_add").index(s)
         # sigma polynomials (src/permutation.rs:172-200, src/key.rs:134-159)
@@ -85,7 +85,7 @@ class PlonkKey:
             buf = ctx.alloc(n)
             ctx.ntt_dev(ev, n, buf, k, True, False)
             pk.poly[nm] = buf
-            vk[nm] = g1_from_mont(keypair.commit(buf).xy)                  # `?` in the reference
+            vk[nm] = keypair.commit(buf).affine()                  # `?` in the reference
         for nm, p in pk.poly.items():
             e8 = ctx.alloc(n8)
             ctx.ntt_dev(p, n, e8, k + 3, False, True)

@@ -40,10 +40,31 @@ class PointsValue:
 
 
 class Commitment:
-    """``poly_commit::Commitment<G1Affine>(pub G1Affine)``: 12 uint64, infinity = zeros."""
+    """``poly_commit::Commitment<G1Affine>(pub G1Affine)``: 12 uint64 Montgomery limbs
+    (x || y), the identity encoded as zeros."""
 
     def __init__(self, xy):
         self.xy = np.ascontiguousarray(xy, dtype=np.uint64).reshape(12)
+        self._affine = False
+
+    @classmethod
+    def from_affine(cls, pt):
+        """From canonical coordinates ((x, y) ints or None)."""
+        from .field import P_MOD
+        c = cls(np.zeros(12, dtype=np.uint64))
+        if pt is not None:
+            r = (1 << 384) % P_MOD
+            raw = (pt[0] * r % P_MOD).to_bytes(48, "little") + (pt[1] * r % P_MOD).to_bytes(48, "little")
+            c.xy = np.frombuffer(raw, dtype="<u8").copy()
+        c._affine = pt
+        return c
+
+    def affine(self):
+        """Canonical (x, y) or None for the identity."""
+        if self._affine is False:
+            from .field import g1_from_mont
+            self._affine = g1_from_mont(self.xy)
+        return self._affine
 
     def is_identity(self):
         return not self.xy.any()

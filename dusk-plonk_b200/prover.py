@@ -56,7 +56,7 @@ class Prover:
         return self._ws
 
     def _commit(self, buf, off=0, n=None):
-        return g1_from_mont(self.keypair.commit(_View(buf, off, n)).xy)
+        return self.keypair.commit(_View(buf, off, n)).affine()
 
     # ---------------------------------------------------------------- create_proof
     def create_proof(self, blinders, circuit, trace=None):

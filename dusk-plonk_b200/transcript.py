@@ -13,6 +13,8 @@ transcript as an object, so a Rust host keeps its own and nothing on the device 
 on these encodings.
 """
 
+import ctypes
+
 _R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 _P_MOD = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
 _M64 = (1 << 64) - 1
@@ -34,6 +36,30 @@ def _rol(v, n):
 
 
 def keccak_f1600(state: bytearray) -> None:
+    """In place on a 200-byte state.  Uses the C routine of libzkp_b200.so (host code) when the
+    library is built; the pure-Python body below is the specification it is tested against."""
+    fn = _native_keccak()
+    if fn is not None:
+        buf = (ctypes.c_char * 200).from_buffer(state)
+        fn(ctypes.addressof(buf))
+        return
+    keccak_f1600_py(state)
+
+
+_NATIVE = [False]
+
+
+def _native_keccak():
+    if _NATIVE[0] is False:
+        try:
+            from .ffi import load_library
+            _NATIVE[0] = load_library().zkp_keccak_f1600
+        except Exception:
+            _NATIVE[0] = None
+    return _NATIVE[0]
+
+
+def keccak_f1600_py(state: bytearray) -> None:
     a = [[int.from_bytes(state[8 * (x + 5 * y):8 * (x + 5 * y) + 8], "little") for y in range(5)] for x in range(5)]
     for rc in _RC:
         c = [a[x][0] ^ a[x][1] ^ a[x][2] ^ a[x][3] ^ a[x][4] for x in range(5)]

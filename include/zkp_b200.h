@@ -80,6 +80,8 @@ int zkp_buf_zero(zkp_ctx* ctx, zkp_buf* buf, size_t off, size_t n);
 int zkp_buf_copy(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const zkp_buf* src, size_t src_off,
                  size_t n);
 
+/* Keccak-f[1600] permutation (host code) for the Merlin transcript the prover keeps on the host. */
+void zkp_keccak_f1600(uint64_t state[25]);
 /* Page-locked host memory for vectors that cross PCIe (the host-buffer entry points copy at
  * full link rate only from pinned memory). */
 int zkp_host_alloc(size_t bytes, void** out);
@@ -114,6 +116,8 @@ size_t zkp_srs_len(const zkp_srs* srs);
 /* Synthetic SRS [tau^i * G]_{i<n} generated on the device (PlonkParams::setup's structure,
  * tests/range.rs:26; tau is Montgomery Fr).  Used by benchmarks and full-size tests. */
 int zkp_srs_generate(zkp_ctx* ctx, const uint64_t tau[4], size_t n, zkp_srs** out);
+/* Powers [tau^(first + i) * G]_{i<n}: one rank's slice of a sharded SRS. */
+int zkp_srs_generate_range(zkp_ctx* ctx, const uint64_t tau[4], size_t first, size_t n, zkp_srs** out);
 int zkp_srs_download(zkp_ctx* ctx, const zkp_srs* srs, size_t off, uint64_t* xy, size_t n);
 
 /* msm_curve_addition(&bases[..n], &scalars[..n]) -> affine (Commitment::new).
@@ -131,6 +135,9 @@ int zkp_commit(zkp_ctx* ctx, const zkp_srs* srs, const uint64_t* coeffs, size_t 
                uint64_t out_xy[12]);
 int zkp_commit_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* coeffs, size_t off, size_t n,
                    uint64_t out_xy[12]);
+/* Index of the highest non-zero coefficient of coeffs[off .. off+n), -1 for the zero polynomial
+ * (Coefficients::degree; what commit's degree check looks at). */
+int zkp_poly_degree_dev(zkp_ctx* ctx, const zkp_buf* coeffs, size_t off, size_t n, long long* top);
 /* MSM tuning knob (window bits c; 0 = automatic).  The window structure is baked into the SRS
  * table when it is loaded, so this applies to SRS handles created afterwards. */
 int zkp_msm_set_window(zkp_ctx* ctx, unsigned c);

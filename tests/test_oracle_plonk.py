@@ -21,6 +21,22 @@ def test_merlin_known_answer():
         "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
 
 
+def test_native_keccak_equals_python_spec():
+    from dusk_plonk_b200.transcript import keccak_f1600, keccak_f1600_py
+    import hashlib
+    a = bytearray(hashlib.sha256(b"seed").digest() * 7)[:200]
+    b = bytearray(a)
+    for _ in range(3):
+        keccak_f1600(a)
+        keccak_f1600_py(b)
+        assert a == b
+    st = bytearray(200)
+    st[0] ^= 0x06
+    st[135] ^= 0x80
+    keccak_f1600(st)
+    assert st[:32].hex() == hashlib.sha3_256(b"").hexdigest()
+
+
 def test_gate_counts_match_reference():
     """m = 18 for tests/range.rs (n = 32) and 287 for the README circuit."""
     assert jubjub_on_curve(JUBJUB_GENERATOR)
