@@ -371,11 +371,28 @@ int zkp_msm_g1_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* scalars, siz
 int zkp_commit_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* coeffs, size_t off, size_t n,
                    uint64_t out_xy[12]) {
     if (!ctx || !srs || !coeffs || !out_xy || off + n > coeffs->n) return ZKP_ERR_INVALID;
-    long long top = -1;
-    int rc = msm_highest_nonzero(ctx, coeffs->d + off, n, &top);
+    const fr_t* p = coeffs->d + off;
+    int ovf = 0;
+    int rc = msm_run_batch(ctx, srs, &p, &n, 1, reinterpret_cast<g1_affine*>(out_xy), &ovf);
     if (rc) return rc;
-    if (top >= (long long)srs->n) return ZKP_ERR_DEGREE;
-    return msm_run(ctx, srs, coeffs->d + off, (size_t)(top + 1), reinterpret_cast<g1_affine*>(out_xy));
+    return ovf ? ZKP_ERR_DEGREE : ZKP_OK;
+}
+
+int zkp_commit_batch_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_poly_ref* polys, unsigned count,
+                         uint64_t* out_xy, int* status) {
+    if (!ctx || !srs || !polys || !out_xy || !status || count == 0 || count > 8) return ZKP_ERR_INVALID;
+    const fr_t* ptrs[8];
+    size_t lens[8];
+    int ovf[8];
+    for (unsigned i = 0; i < count; i++) {
+        if (!polys[i].buf || polys[i].off + polys[i].len > polys[i].buf->n) return ZKP_ERR_INVALID;
+        ptrs[i] = polys[i].buf->d + polys[i].off;
+        lens[i] = polys[i].len;
+    }
+    int rc = msm_run_batch(ctx, srs, ptrs, lens, count, reinterpret_cast<g1_affine*>(out_xy), ovf);
+    if (rc) return rc;
+    for (unsigned i = 0; i < count; i++) status[i] = ovf[i] ? ZKP_ERR_DEGREE : ZKP_OK;
+    return ZKP_OK;
 }
 
 int zkp_poly_degree_dev(zkp_ctx* ctx, const zkp_buf* coeffs, size_t off, size_t n, long long* top) {

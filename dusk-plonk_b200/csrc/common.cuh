@@ -111,6 +111,8 @@ fr_t fft_constant_host(unsigned k, int kind);
 
 // msm.cu
 int msm_run(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* scalars_dev, size_t n, g1_affine* out_host);
+int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_dev, const size_t* lens, unsigned nb,
+                  g1_affine* out_host, int* overflow);
 unsigned msm_choose_window(size_t n);
 int srs_build_table(zkp_ctx* ctx, zkp_srs* srs);
 int msm_highest_nonzero(zkp_ctx* ctx, const fr_t* scalars_dev, size_t n, long long* out);

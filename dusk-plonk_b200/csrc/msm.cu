@@ -28,21 +28,28 @@
 
 namespace zkp {
 
+static constexpr unsigned MSM_MAX_BATCH = 8;   // polynomials committed by one set of launches
+static constexpr unsigned GIANT_PARTS = 64;    // buckets with more partial sums get a whole block
+
+struct MsmBatch {
+    const fr_t* sc[MSM_MAX_BATCH];
+    uint32_t len[MSM_MAX_BATCH];
+};
+
 struct MsmScratch {
-    size_t cap_entries = 0, cap_sorted = 0, cap_buckets = 0, cap_partials = 0, cap_tasks = 0;
-    uint32_t* digits = nullptr;   // [W * n]  bucket | sign << 31, 0xffffffff = zero digit
-    uint32_t* sorted = nullptr;   // [W * n]  table index | sign << 31, grouped by bucket
-    uint32_t* counts = nullptr;   // [B]
-    uint32_t* offsets = nullptr;  // [B]
-    uint32_t* cursor = nullptr;   // [B]
-    uint32_t* task_off = nullptr; // [B + 1]  first task of each bucket; [B] = number of tasks
-    uint32_t* multi = nullptr;    // [B + 1]  buckets made of > 1 task; [B] = how many
-    g1_xyzz* buckets = nullptr;   // [B]
-    g1_xyzz* task_out = nullptr;  // [tasks] partial sums of multi-task buckets
-    g1_xyzz* part_a = nullptr;    // reduction ping-pong
-    g1_xyzz* part_b = nullptr;
-    g1_affine* result = nullptr;
+    size_t cap_entries = 0, cap_sorted = 0, cap_buckets = 0, cap_planes = 0, cap_slots = 0;
+    uint32_t* digits = nullptr;   // [nb][W * n]  bucket | sign << 31, 0xffffffff = zero digit
+    uint32_t* sorted = nullptr;   // [nb][W * n]  table index | sign << 31, grouped by bucket
+    uint32_t* counts = nullptr;   // [nb][B]
+    uint32_t* offsets = nullptr;  // [nb][B]
+    uint32_t* cursor = nullptr;   // [nb][B]
+    uint32_t* giant = nullptr;    // [nb][B]      buckets whose merge needs a whole block
+    uint32_t* meta = nullptr;     // [nb][4]      entries, giant count, overflow flag, pad
+    g1_xyzz* buckets = nullptr;   // [nb][B]
+    g1_xyzz* slots = nullptr;     // [nb][2 * chunks]  head / tail partial sums of each chunk
+    g1_xyzz* planes = nullptr;    // [nb][c * plane chunks] + [nb][32] + [nb]
     long long* top = nullptr;
+    int acc_blocks_per_sm = 0;
 };
 
 static constexpr uint32_t DIGIT_ZERO = 0xffffffffu;
@@ -77,13 +84,23 @@ __device__ __forceinline__ uint32_t window_bits(const fr_t& s, unsigned pos, uns
     return (uint32_t)(v >> off) & ((1u << c) - 1);
 }
 
-// digits[w * n + i]: bucket | sign for scalar i, window w.
-__global__ void msm_digits_kernel(const fr_t* scalars, size_t n, unsigned c, unsigned W,
-                                  uint32_t* digits, uint32_t* counts) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const fr_t s = from_mont(msm_ld_fr(scalars + i));
+// digits[b][w * n + i]: bucket | sign for scalar i of polynomial b, window w.  Coefficients at
+// indices >= srs_n must be zero (PlonkParams::commit's degree check): a non-zero one raises the
+// polynomial's overflow flag instead of producing entries.
+__global__ void msm_digits_kernel(const __grid_constant__ MsmBatch batch, uint32_t n, uint32_t srs_n, unsigned c,
+                                  unsigned W, uint32_t* digits, uint32_t* counts, uint32_t* meta) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned pb = blockIdx.y;
+    if (i >= batch.len[pb]) return;
+    const fr_t sm = msm_ld_fr(batch.sc[pb] + i);
+    if (i >= srs_n) {
+        if (!sm.is_zero()) meta[4 * pb + 2] = 1u;
+        return;
+    }
+    const fr_t s = from_mont(sm);
     const uint32_t B = 1u << (c - 1);
+    digits += (size_t)pb * W * n;
+    counts += (size_t)pb * B;
     uint32_t carry = 0;
     for (unsigned w = 0; w < W; w++) {
         uint32_t d = window_bits(s, w * c, c) + carry;
@@ -101,124 +118,157 @@ __global__ void msm_digits_kernel(const fr_t* scalars, size_t n, unsigned c, uns
     }
 }
 
-// A bucket of up to 2 * cap entries is one task; larger ones are cut into ceil(count / cap).
-__host__ __device__ __forceinline__ uint32_t msm_ntasks(uint32_t count, uint32_t cap) {
-    return count <= 2 * cap ? (count ? 1u : 0u) : (count + cap - 1) / cap;
-}
-
-// Single-block exclusive scan over the B bucket counts: entry offsets, task offsets
-// (ceil(count / cap) tasks per bucket) and the list of buckets that need a merge.
+// One block per polynomial: exclusive scan of its B bucket counts -> entry offsets; meta[0] = entries.
 __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* counts, uint32_t* offsets, uint32_t* cursor,
-                                                        uint32_t* task_off, uint32_t* multi, uint32_t B, uint32_t cap) {
-    __shared__ uint32_t ws_e[32], ws_t[32];
-    __shared__ uint32_t n_multi;
-    const unsigned T = blockDim.x, tid = threadIdx.x;
+                                                        uint32_t* meta, uint32_t B) {
+    __shared__ uint32_t ws[32];
+    const unsigned T = blockDim.x, tid = threadIdx.x, pb = blockIdx.x;
+    counts += (size_t)pb * B; offsets += (size_t)pb * B; cursor += (size_t)pb * B;
     const uint32_t per = (B + T - 1) / T;
     const uint32_t lo = tid * per < B ? tid * per : B, hi = lo + per < B ? lo + per : B;
-    uint32_t se = 0, stk = 0;
-    for (uint32_t i = lo; i < hi; i++) { const uint32_t cn = counts[i]; se += cn; stk += msm_ntasks(cn, cap); }
-    uint32_t ie = se, it = stk;
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += counts[i];
+    uint32_t incl = sum;
     const unsigned lane = tid & 31, wid = tid >> 5;
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t ve = __shfl_up_sync(0xffffffffu, ie, o), vt = __shfl_up_sync(0xffffffffu, it, o);
-        if (lane >= (unsigned)o) { ie += ve; it += vt; }
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += v;
     }
-    if (lane == 31) { ws_e[wid] = ie; ws_t[wid] = it; }
-    if (tid == 0) n_multi = 0;
+    if (lane == 31) ws[wid] = incl;
     __syncthreads();
     if (wid == 0) {
-        uint32_t e = lane < (T >> 5) ? ws_e[lane] : 0, t = lane < (T >> 5) ? ws_t[lane] : 0;
-        uint32_t xe = e, xt = t;
+        uint32_t e = lane < (T >> 5) ? ws[lane] : 0;
+        uint32_t x = e;
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t ve = __shfl_up_sync(0xffffffffu, xe, o), vt = __shfl_up_sync(0xffffffffu, xt, o);
-            if (lane >= (unsigned)o) { xe += ve; xt += vt; }
+            uint32_t v = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (unsigned)o) x += v;
         }
-        ws_e[lane] = xe - e;  // exclusive
-        ws_t[lane] = xt - t;
-        if (lane == 31) task_off[B] = xt;  // total number of tasks
+        ws[lane] = x - e;  // exclusive
+        if (lane == 31) { meta[4 * pb] = x; meta[4 * pb + 1] = 0; }
     }
     __syncthreads();
-    uint32_t re = ws_e[wid] + (ie - se), rt = ws_t[wid] + (it - stk);
+    uint32_t run = ws[wid] + (incl - sum);
     for (uint32_t i = lo; i < hi; i++) {
-        const uint32_t cn = counts[i], nt = msm_ntasks(cn, cap);
-        offsets[i] = re;
-        cursor[i] = re;
-        task_off[i] = rt;
-        if (nt > 1) multi[atomicAdd(&n_multi, 1u)] = i;
-        re += cn;
-        rt += nt;
+        offsets[i] = run;
+        cursor[i] = run;
+        run += counts[i];
     }
-    __syncthreads();
-    if (tid == 0) multi[B] = n_multi;
 }
 
 // sorted[pos] = (w * stride + i) | sign, grouped by bucket
-__global__ void msm_scatter_kernel(const uint32_t* digits, size_t n, unsigned W, uint32_t stride, uint32_t* cursor,
-                                   uint32_t* sorted) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void msm_scatter_kernel(const __grid_constant__ MsmBatch batch, const uint32_t* digits, uint32_t n,
+                                   unsigned W, uint32_t stride, uint32_t B, uint32_t* cursor, uint32_t* sorted) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned pb = blockIdx.y;
+    if (i >= n || i >= batch.len[pb]) return;
+    digits += (size_t)pb * W * n; sorted += (size_t)pb * W * n; cursor += (size_t)pb * B;
     for (unsigned w = 0; w < W; w++) {
         const uint32_t enc = digits[(size_t)w * n + i];
         if (enc == DIGIT_ZERO) continue;
         const uint32_t pos = atomicAdd(&cursor[enc & 0x7fffffffu], 1u);
-        sorted[pos] = (w * stride + (uint32_t)i) | (enc & 0x80000000u);
+        sorted[pos] = (w * stride + i) | (enc & 0x80000000u);
     }
 }
 
-// One thread per task: sum of +-T[idx] over <= cap consecutive entries of one bucket.
+// The hot kernel.  Thread t owns the L consecutive sorted entries [t L, (t+1) L) whatever buckets
+// they belong to, so every thread does the same number of mixed additions for ANY digit
+// distribution.  A bucket that lies inside one chunk is written directly; a bucket cut by a chunk
+// boundary leaves partial sums in the chunk's head slot (first segment of the chunk) or tail slot
+// (last segment), which msm_merge_kernel adds up.
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1_affine* table, const uint32_t* sorted,
                                                             const uint32_t* offsets, const uint32_t* counts,
-                                                            const uint32_t* task_off, uint32_t B, uint32_t cap,
-                                                            g1_xyzz* buckets, g1_xyzz* task_out) {
+                                                            const uint32_t* meta, uint32_t B, uint32_t L,
+                                                            uint32_t nchunks, size_t entry_stride, g1_xyzz* buckets,
+                                                            g1_xyzz* slots) {
+    const unsigned pb = blockIdx.y;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= task_off[B]) return;
-    // owner bucket: task_off[b] <= t < task_off[b + 1]
-    uint32_t lo = 0, hi = B;  // invariant: task_off[lo] <= t, task_off[hi] > t
+    const uint32_t total = meta[4 * pb];
+    const uint64_t start64 = (uint64_t)t * L;
+    if (start64 >= total) return;
+    const uint32_t start = (uint32_t)start64;
+    const uint32_t end = start + L < total ? start + L : total;
+    sorted += (size_t)pb * entry_stride;
+    offsets += (size_t)pb * B; counts += (size_t)pb * B;
+    buckets += (size_t)pb * B; slots += (size_t)pb * 2 * nchunks;
+    // bucket holding entry `start`: the last b with offsets[b] <= start
+    uint32_t lo = 0, hi = B;
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (task_off[mid] <= t) lo = mid; else hi = mid;
+        if (offsets[mid] <= start) lo = mid; else hi = mid;
     }
-    const uint32_t b = lo;
-    const uint32_t cnt = counts[b];
-    const bool single = cnt <= 2 * cap;
-    const uint32_t first = offsets[b] + (t - task_off[b]) * cap;
-    const uint32_t last = (single || first + cap > offsets[b] + cnt) ? offsets[b] + cnt : first + cap;
+    uint32_t bk = lo, bbeg = offsets[bk], bend = bbeg + counts[bk];
+    uint32_t seg = start;
+    bool first = true;
     g1_xyzz acc = g1_xyzz::inf();
-    for (uint32_t j = first; j < last; j++) {
+    for (uint32_t j = start; j < end; j++) {
+        if (j >= bend) {  // the bucket ended inside this chunk
+            if (seg == bbeg) buckets[bk] = acc;          // ... and began inside it too: complete
+            else slots[2 * t] = acc;                     // continuation from the previous chunk
+            first = false;
+            do { bk++; } while (counts[bk] == 0);
+            bbeg = offsets[bk]; bend = bbeg + counts[bk];
+            seg = j;
+            acc = g1_xyzz::inf();
+        }
         const uint32_t e = sorted[j];
         g1_affine q = msm_ld_affine(table + (e & 0x7fffffffu));
         if (e & 0x80000000u) q.y = neg(q.y);
         xyzz_madd(acc, q);
     }
-    if (single) buckets[b] = acc; else task_out[t] = acc;
+    if (seg == bbeg && end == bend) buckets[bk] = acc;
+    else slots[2 * t + (first ? 0 : 1)] = acc;
 }
 
-// One warp per multi-task bucket: lanes stride over the bucket's partial sums, then a
-// shared-memory tree over the 32 lanes.
-__global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* multi, const uint32_t* counts,
-                                                       const uint32_t* task_off, uint32_t B, uint32_t cap,
-                                                       const g1_xyzz* task_out, g1_xyzz* buckets) {
+// One thread per bucket: empty -> infinity; inside one chunk -> already written; otherwise add the
+// partial sums of the chunks it spans (buckets spanning > GIANT_PARTS chunks go to the block kernel).
+__global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* offsets, const uint32_t* counts, uint32_t B,
+                                                       uint32_t L, uint32_t nchunks, const g1_xyzz* slots,
+                                                       g1_xyzz* buckets, uint32_t* giant, uint32_t* meta) {
+    const unsigned pb = blockIdx.y;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t cnt = counts[(size_t)pb * B + b], beg = offsets[(size_t)pb * B + b];
+    g1_xyzz* out = buckets + (size_t)pb * B + b;
+    if (cnt == 0) { *out = g1_xyzz::inf(); return; }
+    const uint32_t t0 = beg / L, t1 = (beg + cnt - 1) / L;
+    if (t0 == t1) return;
+    if (t1 - t0 + 1 > GIANT_PARTS) {
+        giant[(size_t)pb * B + atomicAdd(&meta[4 * pb + 1], 1u)] = b;
+        return;
+    }
+    slots += (size_t)pb * 2 * nchunks;
+    g1_xyzz acc = slots[2 * t0 + (beg == t0 * L ? 0 : 1)];
+    for (uint32_t t = t0 + 1; t <= t1; t++) xyzz_add(acc, slots[2 * t]);
+    *out = acc;
+}
+
+// One block per giant bucket (e.g. a top window holding only the carry digit).
+__global__ void __launch_bounds__(128) msm_merge_giant_kernel(const uint32_t* offsets, const uint32_t* counts,
+                                                             uint32_t B, uint32_t L, uint32_t nchunks,
+                                                             const g1_xyzz* slots, g1_xyzz* buckets,
+                                                             const uint32_t* giant, const uint32_t* meta) {
     extern __shared__ uint4 smem_raw[];
     g1_xyzz* sm = reinterpret_cast<g1_xyzz*>(smem_raw);
-    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t m = blockIdx.x * (blockDim.x >> 5) + wib;
-    if (m >= multi[B]) return;  // whole warp exits together
-    const uint32_t b = multi[m];
-    const uint32_t nt = msm_ntasks(counts[b], cap), t0 = task_off[b];
-    g1_xyzz acc = g1_xyzz::inf();
-    for (uint32_t j = lane; j < nt; j += 32) xyzz_add(acc, task_out[t0 + j]);
-    g1_xyzz* w = sm + wib * 32;
-    w[lane] = acc;
-    __syncwarp();
-    for (unsigned s = 16; s > 0; s >>= 1) {
-        if (lane < s) {
-            g1_xyzz o = w[lane + s];
-            xyzz_add(acc, o);
-            w[lane] = acc;
+    const unsigned pb = blockIdx.y, tid = threadIdx.x;
+    if (blockIdx.x >= meta[4 * pb + 1]) return;
+    const uint32_t b = giant[(size_t)pb * B + blockIdx.x];
+    const uint32_t cnt = counts[(size_t)pb * B + b], beg = offsets[(size_t)pb * B + b];
+    const uint32_t t0 = beg / L, t1 = (beg + cnt - 1) / L;
+    slots += (size_t)pb * 2 * nchunks;
+    g1_xyzz v = g1_xyzz::inf();
+    for (uint32_t t = t0 + tid; t <= t1; t += blockDim.x)
+        xyzz_add(v, slots[2 * t + ((t == t0 && beg != t0 * L) ? 1 : 0)]);
+    sm[tid] = v;
+    __syncthreads();
+    for (unsigned s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (tid < s) {
+            g1_xyzz o = sm[tid + s];
+            xyzz_add(v, o);
+            sm[tid] = v;
         }
-        __syncwarp();
+        __syncthreads();
     }
-    if (lane == 0) buckets[b] = acc;
+    if (tid == 0) buckets[(size_t)pb * B + b] = v;
 }
 
 // ---- bucket reduction: sum_b (b + 1) * B[b] = sum_j 2^j * S_j,  S_j = sum of the buckets whose
@@ -234,10 +284,12 @@ __device__ __forceinline__ uint32_t weight_with_bit(uint32_t k, unsigned j) {
 
 // grid (chunks, c): block (x, j) sums RED_T * RED_L selected buckets of plane j
 __global__ void __launch_bounds__(RED_T) msm_plane_sum_kernel(const g1_xyzz* buckets, uint32_t B, uint32_t chunks,
-                                                            g1_xyzz* parts) {
+                                                            unsigned c, g1_xyzz* parts) {
     extern __shared__ uint4 smem_raw[];
     g1_xyzz* sm = reinterpret_cast<g1_xyzz*>(smem_raw);
-    const unsigned tid = threadIdx.x, j = blockIdx.y;
+    const unsigned tid = threadIdx.x, j = blockIdx.y, pb = blockIdx.z;
+    buckets += (size_t)pb * B;
+    parts += (size_t)pb * c * chunks;
     const uint32_t k0 = (blockIdx.x * RED_T + tid) * RED_L;
     g1_xyzz v = g1_xyzz::inf();
     for (unsigned i = 0; i < RED_L; i++) {
@@ -258,10 +310,12 @@ __global__ void __launch_bounds__(RED_T) msm_plane_sum_kernel(const g1_xyzz* buc
 }
 
 // block j (one warp): sums plane j's chunk partials, then lane 0 applies 2^j.
-__global__ void __launch_bounds__(32) msm_plane_combine_kernel(const g1_xyzz* parts, uint32_t chunks,
+__global__ void __launch_bounds__(32) msm_plane_combine_kernel(const g1_xyzz* parts, uint32_t chunks, unsigned c,
                                                               g1_xyzz* planes) {
     __shared__ g1_xyzz w[32];
-    const unsigned lane = threadIdx.x, j = blockIdx.x;
+    const unsigned lane = threadIdx.x, j = blockIdx.x, pb = blockIdx.y;
+    parts += (size_t)pb * c * chunks;
+    planes += (size_t)pb * 32;
     g1_xyzz v = g1_xyzz::inf();
     for (uint32_t i = lane; i < chunks; i += 32) xyzz_add(v, parts[(size_t)j * chunks + i]);
     w[lane] = v;
@@ -284,6 +338,8 @@ __global__ void __launch_bounds__(32) msm_plane_combine_kernel(const g1_xyzz* pa
 __global__ void __launch_bounds__(32) msm_final_sum_kernel(const g1_xyzz* planes, unsigned c, g1_xyzz* out) {
     __shared__ g1_xyzz w[32];
     const unsigned lane = threadIdx.x;
+    planes += (size_t)blockIdx.x * 32;
+    out += blockIdx.x;
     g1_xyzz v = lane < c ? planes[lane] : g1_xyzz::inf();
     w[lane] = v;
     __syncwarp();
@@ -469,8 +525,11 @@ static int ensure(zkp_ctx* ctx, T** p, size_t* cap, size_t need) {
 static int msm_scratch(zkp_ctx* ctx, MsmScratch** out) {
     if (!ctx->msm) {
         ctx->msm = new MsmScratch();
-        ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->result, sizeof(g1_affine)));
         ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->top, sizeof(long long)));
+        ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->meta, 4 * MSM_MAX_BATCH * sizeof(uint32_t)));
+        int nb = 0;
+        ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel, 128, 0));
+        ctx->msm->acc_blocks_per_sm = nb > 0 ? nb : 1;
     }
     *out = ctx->msm;
     return ZKP_OK;
@@ -480,8 +539,8 @@ void msm_free(zkp_ctx* ctx) {
     MsmScratch* s = ctx->msm;
     if (!s) return;
     cudaFree(s->digits); cudaFree(s->sorted); cudaFree(s->counts); cudaFree(s->offsets); cudaFree(s->cursor);
-    cudaFree(s->task_off); cudaFree(s->multi); cudaFree(s->buckets); cudaFree(s->task_out);
-    cudaFree(s->part_a); cudaFree(s->part_b); cudaFree(s->result); cudaFree(s->top);
+    cudaFree(s->giant); cudaFree(s->meta); cudaFree(s->buckets); cudaFree(s->slots); cudaFree(s->planes);
+    cudaFree(s->top);
     delete s;
     ctx->msm = nullptr;
 }
@@ -504,93 +563,135 @@ int msm_highest_nonzero(zkp_ctx* ctx, const fr_t* scalars_dev, size_t n, long lo
     return ZKP_OK;
 }
 
-int msm_run(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* scalars_dev, size_t n, g1_affine* out_host) {
+// nb <= MSM_MAX_BATCH commitments against the same SRS in one set of launches.  lens[b] may exceed
+// srs->n: coefficients beyond the SRS must be zero, otherwise overflow[b] = 1 (commit's Err) and
+// out_host[b] is unspecified.
+int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_dev, const size_t* lens, unsigned nb,
+                  g1_affine* out_host, int* overflow) {
     int rc;
     if ((rc = set_device(ctx))) return rc;
-    if (n == 0) {
-        memset(out_host, 0, sizeof(g1_affine));
+    if (nb == 0 || nb > MSM_MAX_BATCH) return ZKP_ERR_INVALID;
+    const unsigned c = srs->c, W = srs->W;
+    if ((size_t)W * srs->n >= (1ull << 31)) return ZKP_ERR_INVALID;
+    MsmBatch batch;
+    memset(&batch, 0, sizeof batch);
+    size_t maxlen = 0, n = 0;  // n = scalars that can produce entries (<= srs->n)
+    for (unsigned b = 0; b < nb; b++) {
+        if (lens[b] >= (1ull << 31)) return ZKP_ERR_INVALID;
+        batch.sc[b] = scalars_dev[b];
+        batch.len[b] = (uint32_t)lens[b];
+        if (lens[b] > maxlen) maxlen = lens[b];
+        const size_t eff = lens[b] < srs->n ? lens[b] : srs->n;
+        if (eff > n) n = eff;
+        ctx->msm_points += eff;
+    }
+    if (maxlen == 0 || n == 0) {
+        // nothing can be non-zero below the SRS length; still honour the overflow check
+        for (unsigned b = 0; b < nb; b++) {
+            long long top = -1;
+            if (lens[b] && (rc = msm_highest_nonzero(ctx, scalars_dev[b], lens[b], &top))) return rc;
+            overflow[b] = top >= (long long)srs->n;
+            memset(&out_host[b], 0, sizeof(g1_affine));
+        }
         return ZKP_OK;
     }
-    const unsigned c = srs->c, W = srs->W;
-    if (n > srs->n || (size_t)W * srs->n >= (1ull << 31)) return ZKP_ERR_INVALID;
-    ctx->msm_points += n;
     MsmScratch* s;
     if ((rc = msm_scratch(ctx, &s))) return rc;
 
     const uint32_t B = 1u << (c - 1);
-    const size_t E = (size_t)W * n;  // upper bound on the number of non-zero digits
-    // task size: >= 32 entries, and few enough tasks that the partial-sum array stays small
-    const uint32_t cap = (uint32_t)((E >> 19) > 32 ? (E >> 19) : 32);
-    const size_t max_tasks = E / cap + B + 1;
-    // plane sums: weights with bit j set number at most B/2 (+1 for the top plane)
-    const uint32_t chunks = (uint32_t)((B / 2 + 1 + RED_T * RED_L - 1) / (RED_T * RED_L));
-    const size_t nparts = (size_t)chunks * c;
+    const size_t E = (size_t)W * n;  // upper bound on the entries of one polynomial
+    if (E >= (1ull << 32)) return ZKP_ERR_INVALID;
+    // chunk length: one wave of resident threads when the job is small, 128-entry chunks (many
+    // waves, negligible tail) when it is large
+    const size_t resident = (size_t)ctx->sm_count * s->acc_blocks_per_sm * 128;
+    size_t L = (E * nb + resident - 1) / resident;
+    if (L < 8) L = 8;
+    if (L > 128) L = 128;
+    const uint32_t nchunks = (uint32_t)((E + L - 1) / L);
+    const uint32_t pchunks = (uint32_t)((B / 2 + 1 + RED_T * RED_L - 1) / (RED_T * RED_L));
+    const size_t nplanes = (size_t)nb * ((size_t)pchunks * c + 32 + 1);
 
-    if ((rc = ensure(ctx, &s->digits, &s->cap_entries, E))) return rc;
-    if ((rc = ensure(ctx, &s->sorted, &s->cap_sorted, E))) return rc;
-    if (s->cap_buckets < B) {
-        size_t c1 = s->cap_buckets, c2 = c1, c3 = c1, c6 = c1;
-        size_t c4 = c1 ? c1 + 1 : 0, c5 = c4;
-        if ((rc = ensure(ctx, &s->counts, &c1, B))) return rc;
-        if ((rc = ensure(ctx, &s->offsets, &c2, B))) return rc;
-        if ((rc = ensure(ctx, &s->cursor, &c3, B))) return rc;
-        if ((rc = ensure(ctx, &s->task_off, &c4, (size_t)B + 1))) return rc;
-        if ((rc = ensure(ctx, &s->multi, &c5, (size_t)B + 1))) return rc;
-        if ((rc = ensure(ctx, &s->buckets, &c6, B))) return rc;
-        s->cap_buckets = B;
+    if ((rc = ensure(ctx, &s->digits, &s->cap_entries, E * nb))) return rc;
+    if ((rc = ensure(ctx, &s->sorted, &s->cap_sorted, E * nb))) return rc;
+    if (s->cap_buckets < (size_t)B * nb) {
+        const size_t need = (size_t)B * nb;
+        size_t c1 = s->cap_buckets, c2 = c1, c3 = c1, c4 = c1, c5 = c1;
+        if ((rc = ensure(ctx, &s->counts, &c1, need))) return rc;
+        if ((rc = ensure(ctx, &s->offsets, &c2, need))) return rc;
+        if ((rc = ensure(ctx, &s->cursor, &c3, need))) return rc;
+        if ((rc = ensure(ctx, &s->giant, &c4, need))) return rc;
+        if ((rc = ensure(ctx, &s->buckets, &c5, need))) return rc;
+        s->cap_buckets = need;
     }
-    if ((rc = ensure(ctx, &s->task_out, &s->cap_tasks, max_tasks))) return rc;
-    if (s->cap_partials < nparts) {
-        size_t c1 = s->cap_partials, c2 = s->part_b ? 1 : 0;
-        if ((rc = ensure(ctx, &s->part_a, &c1, nparts))) return rc;
-        if ((rc = ensure(ctx, &s->part_b, &c2, 33))) return rc;
-        s->cap_partials = nparts;
-    }
+    if ((rc = ensure(ctx, &s->slots, &s->cap_slots, (size_t)2 * nchunks * nb))) return rc;
+    if ((rc = ensure(ctx, &s->planes, &s->cap_planes, nplanes))) return rc;
+    g1_xyzz* parts = s->planes;
+    g1_xyzz* planes = parts + (size_t)nb * pchunks * c;
+    g1_xyzz* sums = planes + (size_t)nb * 32;
 
     cudaStream_t st = ctx->stream;
     {
     ProfScope prof(ctx, "msm_sort");
-    ZKP_CUDA(ctx, cudaMemsetAsync(s->counts, 0, B * sizeof(uint32_t), st));
-    ZKP_CUDA(ctx, cudaMemsetAsync(s->buckets, 0, B * sizeof(g1_xyzz), st));  // all-zero XYZZ = infinity
-    msm_digits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scalars_dev, n, c, W, s->digits, s->counts);
+    ZKP_CUDA(ctx, cudaMemsetAsync(s->counts, 0, (size_t)B * nb * sizeof(uint32_t), st));
+    ZKP_CUDA(ctx, cudaMemsetAsync(s->meta, 0, 4 * MSM_MAX_BATCH * sizeof(uint32_t), st));
+    msm_digits_kernel<<<dim3((unsigned)((maxlen + 255) / 256), nb), 256, 0, st>>>(
+        batch, (uint32_t)n, (uint32_t)srs->n, c, W, s->digits, s->counts, s->meta);
     ZKP_LAUNCHED(ctx);
-    msm_scan_kernel<<<1, 1024, 0, st>>>(s->counts, s->offsets, s->cursor, s->task_off, s->multi, B, cap);
+    msm_scan_kernel<<<nb, 1024, 0, st>>>(s->counts, s->offsets, s->cursor, s->meta, B);
     ZKP_LAUNCHED(ctx);
-    msm_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->digits, n, W, (uint32_t)srs->n, s->cursor,
-                                                                    s->sorted);
+    msm_scatter_kernel<<<dim3((unsigned)((n + 255) / 256), nb), 256, 0, st>>>(
+        batch, s->digits, (uint32_t)n, W, (uint32_t)srs->n, B, s->cursor, s->sorted);
     ZKP_LAUNCHED(ctx);
     }
     {
     ProfScope prof(ctx, "msm_accumulate");
-    msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(
-        srs->d, s->sorted, s->offsets, s->counts, s->task_off, B, cap, s->buckets, s->task_out);
+    msm_accumulate_kernel<<<dim3((nchunks + 127) / 128, nb), 128, 0, st>>>(
+        srs->d, s->sorted, s->offsets, s->counts, s->meta, B, (uint32_t)L, nchunks, E, s->buckets, s->slots);
     ZKP_LAUNCHED(ctx);
     }
     {
     ProfScope prof(ctx, "msm_reduce");
+    msm_merge_kernel<<<dim3((B + 127) / 128, nb), 128, 0, st>>>(s->offsets, s->counts, B, (uint32_t)L, nchunks, s->slots,
+                                                               s->buckets, s->giant, s->meta);
+    ZKP_LAUNCHED(ctx);
     {
-        // at most min(B, E / (2 cap)) buckets can consist of more than one task
-        const size_t mm = E / (2 * (size_t)cap) < B ? E / (2 * (size_t)cap) : B;
-        if (mm) {
-            msm_merge_kernel<<<(unsigned)((mm + 3) / 4), 128, 128 * sizeof(g1_xyzz), st>>>(
-                s->multi, s->counts, s->task_off, B, cap, s->task_out, s->buckets);
+        // a giant bucket spans > GIANT_PARTS chunks, so there are fewer than nchunks / GIANT_PARTS
+        const uint32_t gmax = nchunks / GIANT_PARTS < B ? nchunks / GIANT_PARTS : B;
+        if (gmax) {
+            msm_merge_giant_kernel<<<dim3(gmax, nb), 128, 128 * sizeof(g1_xyzz), st>>>(
+                s->offsets, s->counts, B, (uint32_t)L, nchunks, s->slots, s->buckets, s->giant, s->meta);
             ZKP_LAUNCHED(ctx);
         }
     }
-    msm_plane_sum_kernel<<<dim3(chunks, c), RED_T, RED_T * sizeof(g1_xyzz), st>>>(s->buckets, B, chunks, s->part_a);
+    msm_plane_sum_kernel<<<dim3(pchunks, c, nb), RED_T, RED_T * sizeof(g1_xyzz), st>>>(s->buckets, B, pchunks, c, parts);
     ZKP_LAUNCHED(ctx);
-    msm_plane_combine_kernel<<<c, 32, 0, st>>>(s->part_a, chunks, s->part_b);
+    msm_plane_combine_kernel<<<dim3(c, nb), 32, 0, st>>>(parts, pchunks, c, planes);
     ZKP_LAUNCHED(ctx);
-    msm_final_sum_kernel<<<1, 32, 0, st>>>(s->part_b, c, s->part_b + 32);
+    msm_final_sum_kernel<<<nb, 32, 0, st>>>(planes, c, sums);
     ZKP_LAUNCHED(ctx);
     }
-    // the single inversion of the conversion to affine runs on the host (one Fq Fermat chain
+    // the single inversion of each conversion to affine runs on the host (one Fq Fermat chain
     // would occupy one GPU thread for ~0.6 ms)
     g1_xyzz* h = reinterpret_cast<g1_xyzz*>(ctx->pinned);
-    ZKP_CUDA(ctx, cudaMemcpyAsync(h, s->part_b + 32, sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
+    uint32_t* hm = reinterpret_cast<uint32_t*>(h + MSM_MAX_BATCH);
+    ZKP_CUDA(ctx, cudaMemcpyAsync(h, sums, nb * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(ctx, cudaMemcpyAsync(hm, s->meta, 4 * MSM_MAX_BATCH * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     ZKP_CUDA(ctx, cudaStreamSynchronize(st));
-    *out_host = host_xyzz_to_affine(*h);
+    for (unsigned b = 0; b < nb; b++) {
+        overflow[b] = hm[4 * b + 2] != 0;
+        out_host[b] = host_xyzz_to_affine(h[b]);
+    }
     return ZKP_OK;
+}
+
+// msm_curve_addition over the first n powers (n <= srs->n checked by the caller).
+int msm_run(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* scalars_dev, size_t n, g1_affine* out_host) {
+    if (n == 0) {
+        memset(out_host, 0, sizeof(g1_affine));
+        return ZKP_OK;
+    }
+    int ovf = 0;
+    return msm_run_batch(ctx, srs, &scalars_dev, &n, 1, out_host, &ovf);
 }
 
 }  // namespace zkp

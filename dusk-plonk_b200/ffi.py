@@ -84,6 +84,7 @@ class QuotientArgs(ctypes.Structure):
 
 
 SIGNATURES.update({
+    "zkp_commit_batch_dev": (_int, [_vp, _vp, ctypes.POINTER(PolyRef), _uint, _vp, ctypes.POINTER(_int)]),
     "zkp_ntt_ref_dev": (_int, [_vp, PolyRef, _vp, _sz, _uint, _int, _int]),
     "zkp_buf_fill": (_int, [_vp, _vp, _sz, _sz, _vp]),
     "zkp_poly_blind_dev": (_int, [_vp, _vp, _sz, _sz, _vp, _uint]),
@@ -280,6 +281,14 @@ class Context:
         out = np.zeros(12, dtype=np.uint64)
         self.check(self.lib.zkp_commit_dev(self.h, srs.h, buf.h, off, n, _ptr(out)))
         return out
+
+    def commit_batch_dev(self, srs, refs):
+        """-> ((count, 12) uint64 affine Montgomery, [status per polynomial])."""
+        arr = (PolyRef * len(refs))(*refs)
+        out = np.zeros((len(refs), 12), dtype=np.uint64)
+        st = (_int * len(refs))()
+        self.check(self.lib.zkp_commit_batch_dev(self.h, srs.h, arr, len(refs), _ptr(out), st))
+        return out, list(st)
 
     def set_msm_window(self, c):
         self.check(self.lib.zkp_msm_set_window(self.h, c))

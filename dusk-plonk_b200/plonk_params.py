@@ -51,6 +51,19 @@ class PlonkParams:
                 raise Error("polynomial degree exceeds the SRS") from e
             raise
 
+    def commit_batch(self, polys):
+        """Several ``commit`` calls whose results are needed together (the four wire polynomials,
+        the four quotient chunks) as one batched launch sequence.  Raises ``Error`` if any of
+        them fails the degree check, like the first ``?`` in the reference would."""
+        refs = []
+        for p in polys:
+            b, off, n = (p.buf, p.off, p.n) if isinstance(p, BufferView) else (p, 0, p.n)
+            refs.append(self.ctx.ref(b, off, n))
+        out, status = self.ctx.commit_batch_dev(self.srs, refs)
+        if any(st == ZKP_ERR_DEGREE for st in status):
+            raise Error("polynomial degree exceeds the SRS")
+        return [Commitment(out[i]) for i in range(len(polys))]
+
     def commit_or_default(self, poly):
         """``keypair.commit(&p).unwrap_or_default()`` (src/key.rs:138-154)."""
         try:

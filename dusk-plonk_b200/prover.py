@@ -87,7 +87,7 @@ class Prover:
         for j in range(4):
             ctx.ntt_dev(_View(W, j * n, n), n, ws["wp"][j], k, True, False)
             ctx.poly_blind(ws["wp"][j], 0, n, bl[2 * j:2 * j + 2])
-        comms = [self._commit(ws["wp"][j]) for j in range(4)]
+        comms = [c.affine() for c in self.keypair.commit_batch([ws["wp"][j] for j in range(4)])]
         proof.a_comm, proof.b_comm, proof.c_comm, proof.d_comm = comms
         for lab, c in zip((b"a_w", b"b_w", b"c_w", b"d_w"), comms):
             tr.append_commitment(lab, c)
@@ -143,8 +143,8 @@ class Prover:
         Tb = ws["T"]
         ctx.quotient(k8, qa, Tb)
         ctx.ntt_dev(Tb, n8, Tb, k8, True, True)   # coset_idft -> t coefficients
-        tc = [self._commit(Tb, 0, n), self._commit(Tb, n, n), self._commit(Tb, 2 * n, n),
-              self._commit(Tb, 3 * n, 5 * n)]
+        tc = [c.affine() for c in self.keypair.commit_batch(
+            [_View(Tb, 0, n), _View(Tb, n, n), _View(Tb, 2 * n, n), _View(Tb, 3 * n, 5 * n)])]
         proof.t_low_comm, proof.t_mid_comm, proof.t_high_comm, proof.t_4_comm = tc
         for lab, c in zip((b"t_low", b"t_mid", b"t_high", b"t_4"), tc):
             tr.append_commitment(lab, c)

@@ -10,7 +10,7 @@ and ``Prover.create_proof`` run unchanged and every rank derives the same transc
 """
 import numpy as np
 
-from .ffi import BufferView, DeviceBuffer
+from .ffi import BufferView
 from .field import g1_add, g1_from_bytes, g1_from_mont, g1_to_bytes
 from .plonk_params import Error
 from .poly_commit import Commitment
@@ -93,7 +93,6 @@ class ShardedPlonkParams:
 
     def commit(self, poly):
         buf, off, n = (poly.buf, poly.off, poly.n) if isinstance(poly, BufferView) else (poly, 0, poly.n)
-        assert isinstance(buf, DeviceBuffer), "sharded commits take device-resident polynomials"
         top = self.ctx.poly_degree(buf, off, n)
         if top >= self.total_len:
             raise Error("polynomial degree exceeds the SRS")   # identical decision on every rank
@@ -102,6 +101,9 @@ class ShardedPlonkParams:
         if b > a:
             part = g1_from_mont(self.ctx.msm_dev(self.srs, buf, off + a, b - a))
         return Commitment.from_affine(combine_partials(self.comm.all_gather_bytes(g1_to_bytes(part))))
+
+    def commit_batch(self, polys):
+        return [self.commit(p) for p in polys]
 
     def commit_or_default(self, poly):
         try:

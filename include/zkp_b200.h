@@ -135,6 +135,12 @@ int zkp_commit(zkp_ctx* ctx, const zkp_srs* srs, const uint64_t* coeffs, size_t 
                uint64_t out_xy[12]);
 int zkp_commit_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_buf* coeffs, size_t off, size_t n,
                    uint64_t out_xy[12]);
+/* Up to 8 commitments against the same SRS in one set of launches (the four wire commits of round
+ * 1, the four quotient chunks of round 3: src/prover.rs:133-136,262-265).  out_xy: count x 12;
+ * status[i] = ZKP_OK or ZKP_ERR_DEGREE per polynomial. */
+struct zkp_poly_ref;
+int zkp_commit_batch_dev(zkp_ctx* ctx, const zkp_srs* srs, const struct zkp_poly_ref* polys, unsigned count,
+                         uint64_t* out_xy, int* status);
 /* Index of the highest non-zero coefficient of coeffs[off .. off+n), -1 for the zero polynomial
  * (Coefficients::degree; what commit's degree check looks at). */
 int zkp_poly_degree_dev(zkp_ctx* ctx, const zkp_buf* coeffs, size_t off, size_t n, long long* top);

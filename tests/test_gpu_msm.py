@@ -164,3 +164,31 @@ def test_full_size_known_dlog(ctx, logn):
     # spot-check the generated bases themselves
     for i in (0, 1, n // 2, n - 1):
         assert g1_from_mont_limbs(srs.download(i, 1))[0] == curve.mul(curve.G1_GEN, pow(tau_i, i, R_MOD))
+
+
+def test_commit_batch_matches_single_commits(ctx):
+    """The batched launch sequence (wire / quotient-chunk commits) equals separate commits,
+    including ragged lengths, a zero polynomial, trailing zeros past the SRS and one overflow."""
+    from dusk_plonk_b200.plonk_params import PlonkParams, Error
+    n = 700
+    rng = SplitMix64(21)
+    tau = rng.fr()
+    pp = PlonkParams(ctx, ctx.srs_generate(fr_to_mont_limbs([tau])[0], n))
+    polys = [[rng.fr() for _ in range(n)], [rng.fr() for _ in range(33)], [0] * 50,
+             [rng.fr() for _ in range(n - 5)] + [0] * 400, [5], [rng.fr() % 4 for _ in range(n)]]
+    bufs = [ctx.upload(fr_to_mont_limbs(p)) for p in polys]
+    got = pp.commit_batch(bufs)
+    for p, b, g in zip(polys, bufs, got):
+        exp = curve.commit_known_dlog([pow(tau, i, R_MOD) for i in range(len(p))], p) if any(p) else None
+        assert g.affine() == exp
+        assert pp.commit(b) == g
+    # views into one buffer, like the quotient chunks t_low .. t_4
+    big = ctx.upload(fr_to_mont_limbs(polys[0] + polys[3]))
+    from dusk_plonk_b200.ffi import BufferView
+    v = pp.commit_batch([BufferView(big, 0, n), BufferView(big, n, len(polys[3]))])
+    assert v[0] == got[0] and v[1] == got[3]
+    bad = ctx.upload(fr_to_mont_limbs([1] * (n + 1)))
+    with pytest.raises(Error):
+        pp.commit_batch([bufs[0], bad])
+    with pytest.raises(Error):
+        pp.commit(bad)
