@@ -223,6 +223,9 @@ def main():
     ap.add_argument("--workload", default="prove", choices=["prove", "msm", "ntt"])
     ap.add_argument("--logn", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", action="store_true",
+                    help="N > 1: shard ONE job over the GPUs (SRS ranges + partial-sum gather for commits, four-step "
+                         "NTT with all-to-all) and report strong scaling; default is one independent job per GPU")
     args = ap.parse_args()
     if args.logn is None:
         args.logn = {"prove": 16, "msm": 22, "ntt": 24}[args.workload]
@@ -250,6 +253,19 @@ def main():
     n = 1 << args.logn
     hbm_peak, hbm_src = measured_peaks()
     imad_pk, imad_src = imad_peak()
+    shard = args.shard and world > 1
+    comm = None
+    if shard:
+        import torch
+        from dusk_plonk_b200.sharding import Communicator, FourStepNtt, ShardedPlonkParams
+        comm = Communicator(torch.device("cuda", local_rank))
+    # seeds: independent jobs differ per rank, a sharded job is the same job on every rank
+    jr = 0 if shard else rank
+
+    def pinned_copy(a):
+        p = z.pinned_empty(a.shape, a.dtype)
+        p[...] = a
+        return p
 
     if args.workload == "prove":
         from dusk_plonk_b200.composer import synthetic_circuit
@@ -259,10 +275,15 @@ def main():
         circ = synthetic_circuit(args.logn)
         rng = SplitMix64(8349)
         tau = rng.fr()
-        pp = PlonkParams.setup_synthetic(ctx, args.logn, fr_to_mont1(tau))
+        if shard:
+            pp = ShardedPlonkParams.setup_synthetic(ctx, comm, args.logn, fr_to_mont1(tau))
+        else:
+            pp = PlonkParams.setup_synthetic(ctx, args.logn, fr_to_mont1(tau))
         prover = z.PlonkKey.compile(pp, circ)
         bl = [rng.fr() for _ in range(11)]
         wa_host = z.WitnessAssignment.from_circuit(circ, circ.n)
+        wa_host.wires_mont = pinned_copy(wa_host.wires_mont)
+        wa_host.dense_pi_mont = pinned_copy(wa_host.dense_pi_mont)
         wa_dev = z.WitnessAssignment.from_circuit(circ, circ.n).to_device(ctx)
         proofs = []
         step = lambda: proofs.append(prover.create_proof(bl, wa_dev)[0])
@@ -272,22 +293,46 @@ def main():
         metric = "create_proof_throughput"
         n = 1
     elif args.workload == "msm":
-        tau = random_fr_raw_limbs(4242 + rank, 1)[0]
-        srs = ctx.srs_generate(tau, n)
-        host_scalars = random_fr_raw_limbs(8349 + rank, n)
+        tau = random_fr_raw_limbs(4242 + jr, 1)[0]
+        host_scalars = pinned_copy(random_fr_raw_limbs(8349 + jr, n))
         dev_scalars = ctx.upload(host_scalars)
-        step = lambda: ctx.msm_dev(srs, dev_scalars, 0, n)
-        e2e_step = lambda: ctx.msm(srs, host_scalars)
-        h2d, d2h = n * 32, 96
+        if shard:
+            lo, hi = z.sharding.shard_range(n, rank, world)
+            sp = ShardedPlonkParams(ctx, comm, n, lo, hi, ctx.srs_generate(tau, hi - lo, first=lo))
+            step = lambda: sp.commit(dev_scalars)
+
+            def e2e_step():
+                dev_scalars.upload(host_scalars[sp.lo:sp.hi], sp.lo)   # each rank ships only its range
+                return sp.commit(dev_scalars)
+            h2d, d2h = n * 32 // world, 96
+        else:
+            srs = ctx.srs_generate(tau, n)
+            step = lambda: ctx.msm_dev(srs, dev_scalars, 0, n)
+            e2e_step = lambda: ctx.msm(srs, host_scalars)
+            h2d, d2h = n * 32, 96
         dominant = "msm_accumulate"
         metric = "g1_msm_throughput"
     else:
-        host_data = random_fr_raw_limbs(8349 + rank, n)
-        src = ctx.upload(host_data)
-        dst = ctx.alloc(n)
-        step = lambda: ctx.ntt_dev(src, n, dst, args.logn, False, False)
-        e2e_step = lambda: ctx.ntt(host_data, args.logn, False, False)
-        h2d, d2h = n * 32, n * 32
+        host_data = pinned_copy(random_fr_raw_limbs(8349 + jr, n))
+        if shard:
+            fs = FourStepNtt(ctx, comm, args.logn)
+            fs.scatter_input(host_data)
+            step = lambda: fs.run()
+            host_out = np.zeros((n, 4), dtype=np.uint64)
+
+            def e2e_step():
+                fs.scatter_input(host_data)
+                fs.run()
+                fs.gather_output(host_out)
+            h2d, d2h = n * 32 // world, n * 32 // world
+        else:
+            src = ctx.upload(host_data)
+            dst = ctx.alloc(n)
+            step = lambda: ctx.ntt_dev(src, n, dst, args.logn, False, False)
+
+            def e2e_step():   # in place on the pinned host vector, like Fft::dft by value
+                ctx.check(ctx.lib.zkp_ntt(ctx.h, host_data.ctypes.data, n, args.logn, 0, 0))
+            h2d, d2h = n * 32, n * 32
         dominant = "ntt"
         metric = "fr_ntt_throughput"
 
@@ -340,8 +385,9 @@ def main():
 
     if rank == 0:
         ms_step = ms / args.steps
-        value = world * n / (ms_step * 1e-3) / 1e6
-        e2e_val = world * n / (e2e_ms / args.steps * 1e-3) / 1e6
+        jobs = 1 if shard else world      # sharded: ONE job over all GPUs (strong scaling)
+        value = jobs * n / (ms_step * 1e-3) / 1e6
+        e2e_val = jobs * n / (e2e_ms / args.steps * 1e-3) / 1e6
         dom_avg_ms = dom_ms / max(dom_cnt, 1)
         unit = "Melem/s"
         extra = {}
@@ -378,9 +424,13 @@ def main():
                         "imad_achieved_T": imad, "imad_frac": imad / imad_pk, "imad_peak_source": imad_src,
                         "algorithmic": "64 B per element; 68*N*log2(N) mul-adds (SURVEY 8d)"}
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong" if shard else "weak",
                 "vs_baseline": None, "dtype": "u32 limbs (modular integer)", "data": "synthetic",
-                "config": workload_config(args), "roofline": roofline,
+                "config": dict(workload_config(args), parallelism=(
+                    "one job sharded over %d GPUs (SRS ranges + 96-byte partial-sum all-gather; four-step NTT + "
+                    "all-to-all)" % world if shard else "%d independent job(s), one per GPU, no data-path collective" % world)),
+                "roofline": roofline,
                 "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clocks}
         line.update(extra)

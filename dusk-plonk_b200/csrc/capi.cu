@@ -56,6 +56,7 @@ void zkp_ctx_destroy(zkp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ntt_free_domains(ctx);
+    if (ctx->io_scratch) cudaFree(ctx->io_scratch);
     msm_free(ctx);
     prover_free(ctx);
     for (auto& s : ctx->prof_spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
@@ -147,9 +148,36 @@ int zkp_buf_free(zkp_ctx* ctx, zkp_buf* buf) {
     int rc;
     if ((rc = set_device(ctx))) return rc;
     ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ZKP_CUDA(ctx, cudaFree(buf->d));
+    if (buf->owned) ZKP_CUDA(ctx, cudaFree(buf->d));
     delete buf;
     return ZKP_OK;
+}
+
+int zkp_buf_wrap(zkp_ctx* ctx, void* device_ptr, size_t n, zkp_buf** out) {
+    if (!ctx || !out || (!device_ptr && n) || ((uintptr_t)device_ptr & 15)) return ZKP_ERR_INVALID;
+    zkp_buf* b = new zkp_buf();
+    b->d = reinterpret_cast<fr_t*>(device_ptr);
+    b->n = n;
+    b->owned = false;
+    *out = b;
+    return ZKP_OK;
+}
+
+int zkp_permute_dev(zkp_ctx* ctx, const zkp_buf* in, size_t in_off, zkp_buf* out, size_t out_off, size_t A, size_t B,
+                    size_t w) {
+    if (!ctx || !in || !out) return ZKP_ERR_INVALID;
+    const size_t total = A * B * w;
+    if (in_off + total > in->n || out_off + total > out->n || in->d + in_off == out->d + out_off) return ZKP_ERR_INVALID;
+    return ntt_permute(ctx, in->d + in_off, out->d + out_off, A, B, w);
+}
+
+int zkp_scale_matrix_dev(zkp_ctx* ctx, zkp_buf* data, size_t off, size_t rows, size_t cols, size_t a0,
+                         const uint64_t base1[4], const uint64_t base2[4], int mode) {
+    if (!ctx || !data || !base1 || !base2 || off + rows * cols > data->n || mode < 0 || mode > 1) return ZKP_ERR_INVALID;
+    fr_t b1, b2;
+    memcpy(b1.l, base1, 32);
+    memcpy(b2.l, base2, 32);
+    return ntt_scale_matrix(ctx, data->d + off, rows, cols, a0, b1, b2, mode);
 }
 
 size_t zkp_buf_len(const zkp_buf* buf) { return buf ? buf->n : 0; }
@@ -249,23 +277,37 @@ int zkp_ntt_dev(zkp_ctx* ctx, const zkp_buf* in, size_t len_in, zkp_buf* out, un
     return zkp_ntt_dev_batch(ctx, in, 0, len_in, out, 0, k, inverse, coset, 1);
 }
 
+// Device staging area of the host-buffer entry points: grown on demand, kept for the life of the
+// context so that repeated calls do not pay cudaMalloc / cudaFree (both synchronise the device).
+static int io_buffer(zkp_ctx* ctx, size_t n, fr_t** out) {
+    if (ctx->io_scratch_n < n) {
+        if (ctx->io_scratch) cudaFree(ctx->io_scratch);
+        ctx->io_scratch = nullptr;
+        ctx->io_scratch_n = 0;
+        cudaError_t e = cudaMalloc(&ctx->io_scratch, n * sizeof(fr_t));
+        if (e != cudaSuccess) {
+            cuda_fail(ctx, e, "cudaMalloc(io staging)", __FILE__, __LINE__);
+            return e == cudaErrorMemoryAllocation ? ZKP_ERR_NOMEM : ZKP_ERR_CUDA;
+        }
+        ctx->io_scratch_n = n;
+    }
+    *out = ctx->io_scratch;
+    return ZKP_OK;
+}
+
 int zkp_ntt(zkp_ctx* ctx, uint64_t* data, size_t len_in, unsigned k, int inverse, int coset) {
     if (!ctx || !data || k > 28) return ZKP_ERR_INVALID;
     const size_t n = (size_t)1 << k;
     if (len_in > n) return ZKP_ERR_INVALID;
-    zkp_buf* buf = nullptr;
-    int rc = zkp_buf_alloc(ctx, n, &buf);
-    if (rc) return rc;
-    cudaError_t e = cudaMemcpyAsync(buf->d, data, len_in * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) { zkp_buf_free(ctx, buf); return cuda_fail(ctx, e, "h2d", __FILE__, __LINE__); }
-    rc = ntt_run(ctx, buf->d, 0, len_in, buf->d, 0, k, inverse != 0, coset != 0, 1);
-    if (!rc) {
-        e = cudaMemcpyAsync(data, buf->d, n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "d2h", __FILE__, __LINE__);
-    }
-    zkp_buf_free(ctx, buf);
-    return rc;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    fr_t* buf = nullptr;
+    if ((rc = io_buffer(ctx, n, &buf))) return rc;
+    ZKP_CUDA(ctx, cudaMemcpyAsync(buf, data, len_in * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = ntt_run(ctx, buf, 0, len_in, buf, 0, k, inverse != 0, coset != 0, 1))) return rc;
+    ZKP_CUDA(ctx, cudaMemcpyAsync(data, buf, n * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKP_OK;
 }
 
 int zkp_fft_constant(unsigned k, int kind, uint64_t out[4]) {
@@ -400,35 +442,28 @@ int zkp_poly_degree_dev(zkp_ctx* ctx, const zkp_buf* coeffs, size_t off, size_t 
     return msm_highest_nonzero(ctx, coeffs->d + off, n, top);
 }
 
-static int with_uploaded(zkp_ctx* ctx, const uint64_t* scalars, size_t n, zkp_buf** out) {
-    int rc = zkp_buf_alloc(ctx, n, out);
-    if (rc) return rc;
-    cudaError_t e = cudaMemcpyAsync((*out)->d, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) {
-        zkp_buf_free(ctx, *out);
-        return cuda_fail(ctx, e, "h2d", __FILE__, __LINE__);
-    }
-    return ZKP_OK;
-}
-
 int zkp_msm_g1(zkp_ctx* ctx, const zkp_srs* srs, const uint64_t* scalars, size_t n, uint64_t out_xy[12]) {
     if (!ctx || !srs || (!scalars && n) || !out_xy || n > srs->n) return ZKP_ERR_INVALID;
-    zkp_buf* b = nullptr;
-    int rc = with_uploaded(ctx, scalars, n, &b);
-    if (rc) return rc;
-    rc = zkp_msm_g1_dev(ctx, srs, b, 0, n, out_xy);
-    zkp_buf_free(ctx, b);
-    return rc;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    fr_t* buf = nullptr;
+    if ((rc = io_buffer(ctx, n ? n : 1, &buf))) return rc;
+    ZKP_CUDA(ctx, cudaMemcpyAsync(buf, scalars, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    return msm_run(ctx, srs, buf, n, reinterpret_cast<g1_affine*>(out_xy));
 }
 
 int zkp_commit(zkp_ctx* ctx, const zkp_srs* srs, const uint64_t* coeffs, size_t n, uint64_t out_xy[12]) {
     if (!ctx || !srs || (!coeffs && n) || !out_xy) return ZKP_ERR_INVALID;
-    zkp_buf* b = nullptr;
-    int rc = with_uploaded(ctx, coeffs, n, &b);
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    fr_t* buf = nullptr;
+    if ((rc = io_buffer(ctx, n ? n : 1, &buf))) return rc;
+    ZKP_CUDA(ctx, cudaMemcpyAsync(buf, coeffs, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+    const fr_t* p = buf;
+    int ovf = 0;
+    rc = msm_run_batch(ctx, srs, &p, &n, 1, reinterpret_cast<g1_affine*>(out_xy), &ovf);
     if (rc) return rc;
-    rc = zkp_commit_dev(ctx, srs, b, 0, n, out_xy);
-    zkp_buf_free(ctx, b);
-    return rc;
+    return ovf ? ZKP_ERR_DEGREE : ZKP_OK;
 }
 
 }  // extern "C"

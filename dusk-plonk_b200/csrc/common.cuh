@@ -23,6 +23,7 @@ struct MsmScratch; // msm.cu
 struct zkp_buf {
     zkp::fr_t* d = nullptr;
     size_t n = 0;
+    bool owned = true;  // false: wraps memory owned by the caller (zkp_buf_wrap)
 };
 
 struct zkp_srs {
@@ -44,6 +45,8 @@ struct zkp_ctx {
     zkp::fr_t* ntt_scratch = nullptr;
     size_t ntt_scratch_n = 0;
     zkp::MsmScratch* msm = nullptr;
+    zkp::fr_t* io_scratch = nullptr;      // staging for the host-buffer entry points (grow-only)
+    size_t io_scratch_n = 0;
     zkp::fr_t* prover_scratch = nullptr;  // prover.cu: scan / evaluation temporaries
     size_t prover_scratch_n = 0;
     void* pinned = nullptr;       // small pinned staging area for results
@@ -108,6 +111,9 @@ int ntt_run(zkp_ctx* ctx, const fr_t* in, size_t in_stride, size_t len_in, fr_t*
 void ntt_free_domains(zkp_ctx* ctx);
 int ntt_elements(zkp_ctx* ctx, unsigned k, fr_t* out);
 fr_t fft_constant_host(unsigned k, int kind);
+int ntt_permute(zkp_ctx* ctx, const fr_t* in, fr_t* out, size_t A, size_t B, size_t w);
+int ntt_scale_matrix(zkp_ctx* ctx, fr_t* data, size_t rows, size_t cols, size_t a0, const fr_t& base1,
+                     const fr_t& base2, int mode);
 
 // msm.cu
 int msm_run(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* scalars_dev, size_t n, g1_affine* out_host);

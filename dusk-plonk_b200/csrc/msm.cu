@@ -20,7 +20,8 @@
 //   4. msm_accumulate_kernel  one thread per task, XYZZ mixed additions (8M + 2S each, 384-bit
 //                             Montgomery on the integer pipe) -- the hot kernel
 //   5. msm_merge_kernel       buckets made of several tasks: one warp sums the partials
-//   6. msm_plane_sum / plane_combine / final_sum   sum_b (b+1) * B[b] as c bit-plane tree sums
+//   6. msm_rowcol / weighted_planes / final_sum    sum_b (b+1) * B[b]: row + column sums of the
+//                             (hi, lo) weight grid, then two short bit-plane weighted sums
 //   7. host: one Fermat inversion -> affine
 // Addition in G1 is commutative and the result is normalised to affine, so the output is
 // bit-identical to any correct CPU evaluation regardless of accumulation order.
@@ -271,53 +272,13 @@ __global__ void __launch_bounds__(128) msm_merge_giant_kernel(const uint32_t* of
     if (tid == 0) buckets[(size_t)pb * B + b] = v;
 }
 
-// ---- bucket reduction: sum_b (b + 1) * B[b] = sum_j 2^j * S_j,  S_j = sum of the buckets whose
-// weight v = b + 1 has bit j set.  The c plane sums are independent tree reductions and the 2^j
-// factors are applied in parallel, so the dependent chain is ~ (8 + 7 + log chunks + c + log c)
-// point operations instead of a running sum over every bucket.
-static constexpr unsigned RED_T = 128, RED_L = 8;  // threads per block, buckets per thread
-
-// k-th weight (k >= 0) with bit j set
-__device__ __forceinline__ uint32_t weight_with_bit(uint32_t k, unsigned j) {
-    return ((k >> j) << (j + 1)) | (1u << j) | (k & ((1u << j) - 1));
-}
-
-// grid (chunks, c): block (x, j) sums RED_T * RED_L selected buckets of plane j
-__global__ void __launch_bounds__(RED_T) msm_plane_sum_kernel(const g1_xyzz* buckets, uint32_t B, uint32_t chunks,
-                                                            unsigned c, g1_xyzz* parts) {
-    extern __shared__ uint4 smem_raw[];
-    g1_xyzz* sm = reinterpret_cast<g1_xyzz*>(smem_raw);
-    const unsigned tid = threadIdx.x, j = blockIdx.y, pb = blockIdx.z;
-    buckets += (size_t)pb * B;
-    parts += (size_t)pb * c * chunks;
-    const uint32_t k0 = (blockIdx.x * RED_T + tid) * RED_L;
-    g1_xyzz v = g1_xyzz::inf();
-    for (unsigned i = 0; i < RED_L; i++) {
-        const uint32_t wgt = weight_with_bit(k0 + i, j);
-        if (wgt <= B) xyzz_add(v, buckets[wgt - 1]);
-    }
-    sm[tid] = v;
-    __syncthreads();
-    for (unsigned s = RED_T >> 1; s > 0; s >>= 1) {
-        if (tid < s) {
-            g1_xyzz o = sm[tid + s];
-            xyzz_add(v, o);
-            sm[tid] = v;
-        }
-        __syncthreads();
-    }
-    if (tid == 0) parts[(size_t)j * chunks + blockIdx.x] = v;
-}
-
-// block j (one warp): sums plane j's chunk partials, then lane 0 applies 2^j.
-__global__ void __launch_bounds__(32) msm_plane_combine_kernel(const g1_xyzz* parts, uint32_t chunks, unsigned c,
-                                                              g1_xyzz* planes) {
-    __shared__ g1_xyzz w[32];
-    const unsigned lane = threadIdx.x, j = blockIdx.x, pb = blockIdx.y;
-    parts += (size_t)pb * c * chunks;
-    planes += (size_t)pb * 32;
-    g1_xyzz v = g1_xyzz::inf();
-    for (uint32_t i = lane; i < chunks; i += 32) xyzz_add(v, parts[(size_t)j * chunks + i]);
+// ---- bucket reduction: sum_v v * Bk[v], v = b + 1 in [1, B].  Split v = hi * 2^h + lo:
+//     sum_v v Bk[v] = 2^h * sum_hi hi * R[hi] + sum_lo lo * C[lo]
+// with R[hi] / C[lo] the row / column sums of the (hi, lo) grid -- 2 B additions in total, all
+// rows and columns in parallel -- and the two short weighted sums done by bit planes
+// (sum_x x A[x] = sum_j 2^j * sum_{x: bit j} A[x]), the 2^j factors applied in parallel.
+// One warp per row / column: lanes stride, then a shared-memory tree over the 32 lanes.
+__device__ __forceinline__ g1_xyzz warp_point_sum(g1_xyzz v, g1_xyzz* w, unsigned lane) {
     w[lane] = v;
     __syncwarp();
     for (unsigned s = 16; s > 0; s >>= 1) {
@@ -328,30 +289,64 @@ __global__ void __launch_bounds__(32) msm_plane_combine_kernel(const g1_xyzz* pa
         }
         __syncwarp();
     }
-    if (lane == 0) {
-        for (unsigned i = 0; i < j; i++) xyzz_dbl(v);
-        planes[j] = v;
-    }
+    return v;
 }
 
-// one warp: tree over the c <= 32 weighted plane sums
-__global__ void __launch_bounds__(32) msm_final_sum_kernel(const g1_xyzz* planes, unsigned c, g1_xyzz* out) {
+// grid (nrows + ncols, nb), 32 threads.  rc[pb][0 .. nrows) = R, rc[pb][nrows .. nrows+ncols) = C.
+__global__ void __launch_bounds__(32) msm_rowcol_kernel(const g1_xyzz* buckets, uint32_t B, unsigned h, uint32_t nrows,
+                                                       uint32_t ncols, g1_xyzz* rc) {
+    __shared__ g1_xyzz w[32];
+    const unsigned lane = threadIdx.x, pb = blockIdx.y;
+    const uint32_t x = blockIdx.x;
+    buckets += (size_t)pb * B;
+    g1_xyzz v = g1_xyzz::inf();
+    if (x < nrows) {           // row hi = x: weights hi * 2^h + lo
+        for (uint32_t lo = lane; lo < ncols; lo += 32) {
+            const uint32_t wgt = (x << h) + lo;
+            if (wgt >= 1 && wgt <= B) xyzz_add(v, buckets[wgt - 1]);
+        }
+    } else {                   // column lo = x - nrows
+        const uint32_t lo = x - nrows;
+        for (uint32_t hi = lane; hi < nrows; hi += 32) {
+            const uint32_t wgt = (hi << h) + lo;
+            if (wgt >= 1 && wgt <= B) xyzz_add(v, buckets[wgt - 1]);
+        }
+    }
+    v = warp_point_sum(v, w, lane);
+    if (lane == 0) rc[(size_t)pb * (nrows + ncols) + x] = v;
+}
+
+// grid (planes_r + planes_c, nb), 32 threads: block j < planes_r handles bit j of the row index and
+// applies 2^(h + j); the others handle bit j - planes_r of the column index and apply 2^(j - planes_r).
+__global__ void __launch_bounds__(32) msm_weighted_planes_kernel(const g1_xyzz* rc, unsigned h, uint32_t nrows,
+                                                                uint32_t ncols, unsigned planes_r, g1_xyzz* planes) {
+    __shared__ g1_xyzz w[32];
+    const unsigned lane = threadIdx.x, pb = blockIdx.y, nplanes = gridDim.x;
+    rc += (size_t)pb * (nrows + ncols);
+    const bool is_row = blockIdx.x < planes_r;
+    const unsigned j = is_row ? blockIdx.x : blockIdx.x - planes_r;
+    const g1_xyzz* arr = is_row ? rc : rc + nrows;
+    const uint32_t len = is_row ? nrows : ncols;
+    g1_xyzz v = g1_xyzz::inf();
+    for (uint32_t x = lane; x < len; x += 32)
+        if ((x >> j) & 1u) xyzz_add(v, arr[x]);
+    v = warp_point_sum(v, w, lane);
+    if (lane == 0) {
+        const unsigned dbl_n = is_row ? h + j : j;
+        for (unsigned i = 0; i < dbl_n; i++) xyzz_dbl(v);
+        planes[(size_t)pb * 32 + blockIdx.x] = v;
+    }
+    (void)nplanes;
+}
+
+// one warp per polynomial: tree over the <= 32 weighted plane sums
+__global__ void __launch_bounds__(32) msm_final_sum_kernel(const g1_xyzz* planes, unsigned nplanes, g1_xyzz* out) {
     __shared__ g1_xyzz w[32];
     const unsigned lane = threadIdx.x;
     planes += (size_t)blockIdx.x * 32;
-    out += blockIdx.x;
-    g1_xyzz v = lane < c ? planes[lane] : g1_xyzz::inf();
-    w[lane] = v;
-    __syncwarp();
-    for (unsigned s = 16; s > 0; s >>= 1) {
-        if (lane < s) {
-            g1_xyzz o = w[lane + s];
-            xyzz_add(v, o);
-            w[lane] = v;
-        }
-        __syncwarp();
-    }
-    if (lane == 0) *out = v;
+    g1_xyzz v = lane < nplanes ? planes[lane] : g1_xyzz::inf();
+    v = warp_point_sum(v, w, lane);
+    if (lane == 0) out[blockIdx.x] = v;
 }
 
 // T[w][i] = 2^c * T[w-1][i]: one thread per point walks the windows (load-time only).
@@ -608,8 +603,13 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     if (L < 8) L = 8;
     if (L > 128) L = 128;
     const uint32_t nchunks = (uint32_t)((E + L - 1) / L);
-    const uint32_t pchunks = (uint32_t)((B / 2 + 1 + RED_T * RED_L - 1) / (RED_T * RED_L));
-    const size_t nplanes = (size_t)nb * ((size_t)pchunks * c + 32 + 1);
+    // two-level bucket reduction: weight v = hi * 2^h + lo
+    const unsigned h = c / 2;
+    const uint32_t ncols = 1u << h, nrows = (B >> h) + 1;
+    unsigned planes_r = 0, planes_c = h;
+    while ((1u << planes_r) < nrows) planes_r++;   // bits of the largest row index (nrows - 1)
+    if (planes_r + planes_c > 32) return ZKP_ERR_INVALID;
+    const size_t nplanes = (size_t)nb * ((size_t)(nrows + ncols) + 32 + 1);
 
     if ((rc = ensure(ctx, &s->digits, &s->cap_entries, E * nb))) return rc;
     if ((rc = ensure(ctx, &s->sorted, &s->cap_sorted, E * nb))) return rc;
@@ -625,8 +625,8 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     }
     if ((rc = ensure(ctx, &s->slots, &s->cap_slots, (size_t)2 * nchunks * nb))) return rc;
     if ((rc = ensure(ctx, &s->planes, &s->cap_planes, nplanes))) return rc;
-    g1_xyzz* parts = s->planes;
-    g1_xyzz* planes = parts + (size_t)nb * pchunks * c;
+    g1_xyzz* rowcol = s->planes;
+    g1_xyzz* planes = rowcol + (size_t)nb * (nrows + ncols);
     g1_xyzz* sums = planes + (size_t)nb * 32;
 
     cudaStream_t st = ctx->stream;
@@ -663,23 +663,23 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
             ZKP_LAUNCHED(ctx);
         }
     }
-    msm_plane_sum_kernel<<<dim3(pchunks, c, nb), RED_T, RED_T * sizeof(g1_xyzz), st>>>(s->buckets, B, pchunks, c, parts);
+    msm_rowcol_kernel<<<dim3(nrows + ncols, nb), 32, 0, st>>>(s->buckets, B, h, nrows, ncols, rowcol);
     ZKP_LAUNCHED(ctx);
-    msm_plane_combine_kernel<<<dim3(c, nb), 32, 0, st>>>(parts, pchunks, c, planes);
+    msm_weighted_planes_kernel<<<dim3(planes_r + planes_c, nb), 32, 0, st>>>(rowcol, h, nrows, ncols, planes_r, planes);
     ZKP_LAUNCHED(ctx);
-    msm_final_sum_kernel<<<nb, 32, 0, st>>>(planes, c, sums);
+    msm_final_sum_kernel<<<nb, 32, 0, st>>>(planes, planes_r + planes_c, sums);
     ZKP_LAUNCHED(ctx);
     }
     // the single inversion of each conversion to affine runs on the host (one Fq Fermat chain
     // would occupy one GPU thread for ~0.6 ms)
-    g1_xyzz* h = reinterpret_cast<g1_xyzz*>(ctx->pinned);
-    uint32_t* hm = reinterpret_cast<uint32_t*>(h + MSM_MAX_BATCH);
-    ZKP_CUDA(ctx, cudaMemcpyAsync(h, sums, nb * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
+    g1_xyzz* hs = reinterpret_cast<g1_xyzz*>(ctx->pinned);
+    uint32_t* hm = reinterpret_cast<uint32_t*>(hs + MSM_MAX_BATCH);
+    ZKP_CUDA(ctx, cudaMemcpyAsync(hs, sums, nb * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
     ZKP_CUDA(ctx, cudaMemcpyAsync(hm, s->meta, 4 * MSM_MAX_BATCH * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     ZKP_CUDA(ctx, cudaStreamSynchronize(st));
     for (unsigned b = 0; b < nb; b++) {
         overflow[b] = hm[4 * b + 2] != 0;
-        out_host[b] = host_xyzz_to_affine(h[b]);
+        out_host[b] = host_xyzz_to_affine(hs[b]);
     }
     return ZKP_OK;
 }

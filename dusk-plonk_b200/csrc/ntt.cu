@@ -345,6 +345,85 @@ int ntt_run(zkp_ctx* ctx, const fr_t* in, size_t in_stride, size_t len_in, fr_t*
     return ZKP_OK;
 }
 
+// ------------------------------------------------------------------ four-step helpers (multi-GPU)
+// out[a][b][0..w) = in[b][a][0..w): transpose of a B x A matrix of w-element blocks.  w == 1 goes
+// through a shared-memory tile so both sides stay coalesced.
+__global__ void __launch_bounds__(256) permute_blocks_kernel(const fr_t* in, fr_t* out, size_t A, size_t B, size_t w) {
+    const size_t total = A * B * w;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = idx % w, ab = idx / w;
+        const size_t b = ab % B, a = ab / B;  // idx enumerates out[a][b][e]
+        st_fr(out + idx, ld_fr(in + (b * A + a) * w + e));
+    }
+}
+
+__global__ void __launch_bounds__(256) transpose_tile_kernel(const fr_t* in, fr_t* out, size_t A, size_t B) {
+    // in: B x A row-major, out: A x B row-major; 16 x 16 tiles
+    __shared__ uint4 t_lo[16][17], t_hi[16][17];
+    const unsigned tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const size_t a0 = (size_t)blockIdx.x * 16, b0 = (size_t)blockIdx.y * 16;
+    if (b0 + ty < B && a0 + tx < A) {
+        const uint4* q = reinterpret_cast<const uint4*>(in + (b0 + ty) * A + a0 + tx);
+        t_lo[ty][tx] = q[0];
+        t_hi[ty][tx] = q[1];
+    }
+    __syncthreads();
+    if (a0 + ty < A && b0 + tx < B) {
+        uint4* q = reinterpret_cast<uint4*>(out + (a0 + ty) * B + b0 + tx);
+        q[0] = t_lo[tx][ty];
+        q[1] = t_hi[tx][ty];
+    }
+}
+
+// data[a][b] *= f(a, b) over a rows x cols matrix, 16 consecutive b per thread.
+//   mode 0 (four-step twiddle):  f = base1 ^ ((a0 + a) * b)
+//   mode 1 (coset / scaling):    f = base1 ^ (a0 + a) * base2 ^ b
+__global__ void __launch_bounds__(128) scale_matrix_kernel(fr_t* data, size_t rows, size_t cols, size_t a0, fr_t base1,
+                                                          fr_t base2, int mode) {
+    constexpr size_t RUN = 16;
+    const size_t runs = (cols + RUN - 1) / RUN;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * runs) return;
+    const size_t a = t / runs, b0 = (t % runs) * RUN;
+    const fr_t pa = pow_u64(base1, (uint64_t)(a0 + a));
+    const fr_t ratio = mode == 0 ? pa : base2;
+    fr_t f = mode == 0 ? pow_u64(pa, (uint64_t)b0) : pa * pow_u64(base2, (uint64_t)b0);
+    fr_t* row = data + a * cols;
+    for (size_t b = b0; b < b0 + RUN && b < cols; b++) {
+        st_fr(row + b, ld_fr(row + b) * f);
+        f = f * ratio;
+    }
+}
+
+int ntt_permute(zkp_ctx* ctx, const fr_t* in, fr_t* out, size_t A, size_t B, size_t w) {
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    if (A == 0 || B == 0 || w == 0) return ZKP_OK;
+    if (w == 1) {
+        dim3 grid((unsigned)((A + 15) / 16), (unsigned)((B + 15) / 16));
+        transpose_tile_kernel<<<grid, 256, 0, ctx->stream>>>(in, out, A, B);
+    } else {
+        const size_t total = A * B * w;
+        size_t blocks = (total + 255) / 256;
+        if (blocks > 148 * 64) blocks = 148 * 64;
+        permute_blocks_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, out, A, B, w);
+    }
+    ZKP_LAUNCHED(ctx);
+    return ZKP_OK;
+}
+
+int ntt_scale_matrix(zkp_ctx* ctx, fr_t* data, size_t rows, size_t cols, size_t a0, const fr_t& base1,
+                     const fr_t& base2, int mode) {
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    if (rows == 0 || cols == 0) return ZKP_OK;
+    const size_t threads = rows * ((cols + 15) / 16);
+    scale_matrix_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(data, rows, cols, a0, base1, base2,
+                                                                                   mode);
+    ZKP_LAUNCHED(ctx);
+    return ZKP_OK;
+}
+
 int ntt_elements(zkp_ctx* ctx, unsigned k, fr_t* out) {
     int rc;
     if ((rc = set_device(ctx))) return rc;

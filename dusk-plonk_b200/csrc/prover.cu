@@ -165,15 +165,56 @@ __global__ void prod_apply_kernel(const fr_t* in, size_t n, const fr_t* carry, i
     }
 }
 
-__global__ void fr_inverse_kernel(const fr_t* in, fr_t* out) { pst(out, inverse(pld(in))); }
+// Host-side Fr inversion (4 x u64 CIOS Montgomery, Fermat): the one inversion of the permutation
+// accumulator would keep a single GPU thread busy for ~0.2 ms.
+namespace hostfr {
+typedef unsigned __int128 u128;
+static const uint64_t P[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL,
+                              0x73eda753299d7d48ULL};
+static const uint64_t INV = 0xfffffffeffffffffULL;
+static const uint64_t ONE[4] = {0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL,
+                                0x1824b159acc5056fULL};
+struct fr { uint64_t l[4]; };
+static inline fr mul(const fr& a, const fr& b) {
+    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 4; j++) { u128 s = (u128)a.l[j] * b.l[i] + t[j] + c; t[j] = (uint64_t)s; c = (uint64_t)(s >> 64); }
+        u128 s = (u128)t[4] + c; t[4] = (uint64_t)s; t[5] = (uint64_t)(s >> 64);
+        const uint64_t m = t[0] * INV;
+        s = (u128)m * P[0] + t[0]; c = (uint64_t)(s >> 64);
+        for (int j = 1; j < 4; j++) { s = (u128)m * P[j] + t[j] + c; t[j - 1] = (uint64_t)s; c = (uint64_t)(s >> 64); }
+        s = (u128)t[4] + c; t[3] = (uint64_t)s; t[4] = t[5] + (uint64_t)(s >> 64);
+    }
+    bool ge = t[4] != 0;
+    if (!ge) {
+        ge = true;
+        for (int i = 3; i >= 0; i--) { if (t[i] > P[i]) break; if (t[i] < P[i]) { ge = false; break; } }
+    }
+    if (ge) {
+        uint64_t br = 0;
+        for (int i = 0; i < 4; i++) { u128 d = (u128)t[i] - P[i] - br; t[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
+    }
+    fr r; memcpy(r.l, t, 32); return r;
+}
+static inline fr inv(const fr& a) {  // a^(r-2)
+    uint64_t e[4]; memcpy(e, P, 32); e[0] -= 2;
+    fr acc; memcpy(acc.l, ONE, 32);
+    for (int i = 255; i >= 0; i--) {
+        acc = mul(acc, acc);
+        if ((e[i / 64] >> (i % 64)) & 1) acc = mul(acc, a);
+    }
+    return acc;
+}
+}  // namespace hostfr
 
 // z[0] = 1, z[i] = P[i-1] * S[i] * inv   (P inclusive prefix of num, S inclusive suffix of den,
 // inv = 1 / prod(den)):  prod_{j<i} num_j / den_j
-__global__ void perm_z_combine_kernel(const fr_t* P, const fr_t* S, const fr_t* inv, size_t n, fr_t* z) {
+__global__ void perm_z_combine_kernel(const fr_t* P, const fr_t* S, fr_t inv, size_t n, fr_t* z) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (i == 0) { pst(z, fr_t::one()); return; }
-    pst(z + i, pld(P + i - 1) * pld(S + i) * pld(inv));
+    pst(z + i, pld(P + i - 1) * pld(S + i) * inv);
 }
 
 // ------------------------------------------------------------------ quotient
@@ -530,9 +571,15 @@ int zkp_perm_z_dev(zkp_ctx* ctx, size_t n, const zkp_poly_ref wires[4], const zk
     ZKP_LAUNCHED(ctx);
     prod_apply_kernel<<<cb, 128, 0, st>>>(den, n, c2, 1, S);
     ZKP_LAUNCHED(ctx);
-    fr_inverse_kernel<<<1, 1, 0, st>>>(S, inv);
-    ZKP_LAUNCHED(ctx);
-    perm_z_combine_kernel<<<blocks_for(n, 128), 128, 0, st>>>(P, S, inv, n, out->d + out_off);
+    // 1 / prod(den) on the host: S[0] is the product of every denominator
+    hostfr::fr* hp = reinterpret_cast<hostfr::fr*>(ctx->pinned);
+    ZKP_CUDA(ctx, cudaMemcpyAsync(hp, S, sizeof(fr_t), cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(ctx, cudaStreamSynchronize(st));
+    const hostfr::fr hi = hostfr::inv(*hp);
+    fr_t inv_v;
+    memcpy(inv_v.l, hi.l, 32);
+    (void)inv;
+    perm_z_combine_kernel<<<blocks_for(n, 128), 128, 0, st>>>(P, S, inv_v, n, out->d + out_off);
     ZKP_LAUNCHED(ctx);
     return ZKP_OK;
 }

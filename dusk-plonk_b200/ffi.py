@@ -44,6 +44,9 @@ SIGNATURES = {
     "zkp_buf_len": (_sz, [_vp]),
     "zkp_buf_upload": (_int, [_vp, _vp, _sz, _vp, _sz]),
     "zkp_buf_download": (_int, [_vp, _vp, _sz, _vp, _sz]),
+    "zkp_buf_wrap": (_int, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "zkp_permute_dev": (_int, [_vp, _vp, _sz, _vp, _sz, _sz, _sz, _sz]),
+    "zkp_scale_matrix_dev": (_int, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _vp, _int]),
     "zkp_buf_zero": (_int, [_vp, _vp, _sz, _sz]),
     "zkp_buf_copy": (_int, [_vp, _vp, _sz, _vp, _sz, _sz]),
     "zkp_keccak_f1600": (None, [_vp]),
@@ -237,6 +240,18 @@ class Context:
         self.check(self.lib.zkp_ntt_dev_batch(self.h, src.h, in_stride, len_in, dst.h, out_stride, k,
                                               int(inverse), int(coset), batch))
 
+    def wrap(self, device_ptr, n):
+        """DeviceBuffer over caller-owned device memory (``zkp_buf_wrap``)."""
+        return DeviceBuffer(self, n, device_ptr=device_ptr)
+
+    def permute(self, src, src_off, dst, dst_off, A, B, w=1):
+        self.check(self.lib.zkp_permute_dev(self.h, src.h, src_off, dst.h, dst_off, A, B, w))
+
+    def scale_matrix(self, buf, off, rows, cols, a0, base1, base2, mode):
+        b1 = np.ascontiguousarray(base1, dtype=np.uint64).reshape(4)
+        b2 = np.ascontiguousarray(base2, dtype=np.uint64).reshape(4)
+        self.check(self.lib.zkp_scale_matrix_dev(self.h, buf.h, off, rows, cols, a0, _ptr(b1), _ptr(b2), mode))
+
     def fft_elements(self, k):
         b = DeviceBuffer(self, 1 << k)
         self.check(self.lib.zkp_fft_elements_dev(self.h, k, b.h))
@@ -383,11 +398,14 @@ class BufferView:
 class DeviceBuffer:
     """Device-resident Fr vector (``zkp_buf``)."""
 
-    def __init__(self, ctx, n):
+    def __init__(self, ctx, n, device_ptr=None):
         self.ctx = ctx
         self.n = n
         h = _vp()
-        ctx.check(ctx.lib.zkp_buf_alloc(ctx.h, n, ctypes.byref(h)))
+        if device_ptr is None:
+            ctx.check(ctx.lib.zkp_buf_alloc(ctx.h, n, ctypes.byref(h)))
+        else:
+            ctx.check(ctx.lib.zkp_buf_wrap(ctx.h, _vp(device_ptr), n, ctypes.byref(h)))
         self.h = h
 
     def upload(self, arr, off=0):

@@ -56,7 +56,7 @@ def combine_partials(blobs):
 
 
 class ShardedPlonkParams:
-    def __init__(self, ctx, comm, total_len, lo, hi, srs, tau_mont=None):
+    def __init__(self, ctx, comm, total_len, lo, hi, srs=None, tau_mont=None):
         self.ctx, self.comm = ctx, comm
         self.total_len, self.lo, self.hi = total_len, lo, hi
         self.srs = srs          # this rank's powers [lo, hi) with their window table
@@ -110,3 +110,101 @@ class ShardedPlonkParams:
             return self.commit(poly)
         except Error:
             return Commitment(np.zeros(12, dtype=np.uint64))
+
+
+# ====================================================================== four-step NTT
+class FourStepNtt:
+    """Fr NTT of 2^k points over G GPUs with one all-to-all: N = R x C.
+
+    With i = r C + c and j = jc R + jr,
+        X[jc R + jr] = sum_c w_C^(c jc) * w_N^(c jr) * sum_r x[r C + c] w_R^(r jr).
+    Rank s owns the columns c in [s C/G, (s+1) C/G) on input and the rows jr in
+    [s R/G, (s+1) R/G) on output:
+
+        in_buf   [c_loc][r]     this rank's columns, each contiguous   (``scatter_input`` lays it out)
+        step 1   C/G size-R NTTs over r (batched single-GPU kernels)   -> [c_loc][jr]
+        step 2   * w_N^(c jr), transpose to [jr][c_loc]
+        step 3   all-to-all: rows jr of rank t's slab go to rank t     (NCCL over NVLink)
+        step 4   regroup to [jr_loc][c], R/G size-C NTTs over c        -> out_buf [jr_loc][jc]
+
+    so ``out_buf[jr_loc][jc] = X[jc R + jr]``.  The reference-facing call hands over / receives host
+    vectors in natural order (``Fft::dft`` by value), and host <-> device copies can place elements
+    anywhere, so the column / row slabs cost nothing extra there (``scatter_input`` /
+    ``gather_output``).  Inverse and coset variants follow ``Fft::{idft, coset_dft, coset_idft}``:
+    1/N falls out of the two inverse sub-transforms, the coset factors g^i / g^-j are separable
+    (g^(r C + c) = (g^C)^r g^c) and applied by ``zkp_scale_matrix_dev``.
+    """
+
+    def __init__(self, ctx, comm, k, torch_device=None):
+        import torch
+        self.torch = torch
+        self.ctx, self.comm, self.k = ctx, comm, k
+        G = comm.world
+        self.kr = k - k // 2            # R = 2^kr rows, C = 2^kc columns
+        self.kc = k // 2
+        self.R, self.C = 1 << self.kr, 1 << self.kc
+        assert self.C % G == 0 and self.R % G == 0, "world size must divide both factors"
+        self.Cl, self.Rl = self.C // G, self.R // G
+        self.nloc = (1 << k) // G
+        dev = torch_device if torch_device is not None else torch.device("cuda", ctx.device)
+        # two ping-pong slabs that NCCL and the kernels both address
+        self.ta = torch.empty(self.nloc * 4, dtype=torch.int64, device=dev)
+        self.tb = torch.empty(self.nloc * 4, dtype=torch.int64, device=dev)
+        self.a = ctx.wrap(self.ta.data_ptr(), self.nloc)
+        self.b = ctx.wrap(self.tb.data_ptr(), self.nloc)
+
+    # ---- host <-> device placement (natural-order host vector)
+    def scatter_input(self, host):
+        """host: (N, 4) uint64 natural order -> in_buf [c_loc][r] of this rank."""
+        s = self.comm.rank
+        m = host.reshape(self.R, self.C, 4)[:, s * self.Cl:(s + 1) * self.Cl, :]
+        self.a.upload(np.ascontiguousarray(m.transpose(1, 0, 2)).reshape(self.nloc, 4))
+
+    def gather_output(self, host_out):
+        """out_buf [jr_loc][jc] -> host_out[jc R + jr] for this rank's rows (other ranks' stay)."""
+        s = self.comm.rank
+        loc = self.a.download().reshape(self.Rl, self.C, 4)
+        host_out.reshape(self.C, self.R, 4)[:, s * self.Rl:(s + 1) * self.Rl, :] = loc.transpose(1, 0, 2)
+
+    # ---- the transform: in_buf (self.a) -> out_buf (self.a)
+    def run(self, inverse=False, coset=False):
+        from .ffi import fft_constant
+        ctx, G, s = self.ctx, self.comm.world, self.comm.rank
+        R, C, Rl, Cl, k = self.R, self.C, self.Rl, self.Cl, self.k
+        a, b = self.a, self.b
+        one = fft_constant(0, 0)                        # w_1 = 1 in Montgomery form
+        wN = fft_constant(k, 1 if inverse else 0)
+        g, gi = fft_constant(k, 3), fft_constant(k, 4)
+        if coset and not inverse:
+            # x[r C + c] *= g^(r C + c): rows a = c_loc, columns b = r
+            ctx.scale_matrix(a, 0, Cl, R, s * Cl, g, _pow_mont(ctx, g, C), 1)
+        # step 1: size-R transforms of the Cl local columns
+        ctx.ntt_dev_batch(a, R, R, a, R, self.kr, inverse, False, Cl)
+        # step 2: twiddle, then rows <-> columns so that a destination's rows are contiguous
+        ctx.scale_matrix(a, 0, Cl, R, s * Cl, wN, one, 0)
+        ctx.permute(a, 0, b, 0, R, Cl, 1)                # b[jr][c_loc]
+        # step 3: all-to-all (rank t receives its rows jr from every source)
+        ctx.sync()
+        if G > 1:
+            self.comm.dist.all_to_all_single(self.ta, self.tb)
+            self.torch.cuda.synchronize()
+            src = a                                      # [src][jr_loc][c_loc]
+            dst = b
+        else:
+            src, dst = b, a
+        # step 4: regroup to [jr_loc][c = src * Cl + c_loc] and transform over c
+        if G > 1:
+            ctx.permute(src, 0, dst, 0, Rl, G, Cl)       # dst[jr_loc][src][c_loc]
+            work = dst
+        else:
+            work = src
+        ctx.ntt_dev_batch(work, C, C, a, C, self.kc, inverse, False, Rl)
+        if coset and inverse:
+            # X[jc R + jr] *= g^-(jc R + jr): rows a = jr_loc, columns b = jc
+            ctx.scale_matrix(a, 0, Rl, C, s * Rl, gi, _pow_mont(ctx, gi, R), 1)
+        ctx.sync()
+
+
+def _pow_mont(ctx, base_mont, e):
+    from .field import fr_from_mont, fr_to_mont1, R_MOD
+    return fr_to_mont1(pow(fr_from_mont([base_mont])[0], e, R_MOD))

@@ -12,3 +12,4 @@ from .composer import Plonk, Constraint, SynthesizedCircuit  # noqa: E402,F401
 from .key import PlonkKey  # noqa: E402,F401
 from .prover import Prover, Proof, WitnessAssignment  # noqa: E402,F401
 from .transcript import Transcript  # noqa: E402,F401
+from . import sharding  # noqa: E402,F401

@@ -76,6 +76,9 @@ int zkp_buf_free(zkp_ctx* ctx, zkp_buf* buf);
 size_t zkp_buf_len(const zkp_buf* buf);
 int zkp_buf_upload(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const uint64_t* src, size_t n);
 int zkp_buf_download(zkp_ctx* ctx, const zkp_buf* src, size_t src_off, uint64_t* dst, size_t n);
+/* Wrap device memory owned by the caller (e.g. the tensor an NCCL collective reads and writes) as
+ * a zkp_buf; zkp_buf_free on it releases only the handle. */
+int zkp_buf_wrap(zkp_ctx* ctx, void* device_ptr, size_t n, zkp_buf** out);
 int zkp_buf_zero(zkp_ctx* ctx, zkp_buf* buf, size_t off, size_t n);
 int zkp_buf_copy(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const zkp_buf* src, size_t src_off,
                  size_t n);
@@ -101,6 +104,14 @@ int zkp_ntt_dev(zkp_ctx* ctx, const zkp_buf* in, size_t len_in, zkp_buf* out, un
 int zkp_ntt_dev_batch(zkp_ctx* ctx, const zkp_buf* in, size_t in_stride, size_t len_in,
                       zkp_buf* out, size_t out_stride, unsigned k, int inverse, int coset,
                       unsigned batch);
+/* Building blocks of the multi-GPU four-step NTT (sharding.py FourStepNtt):
+ * zkp_permute_dev   out[a][b][0..w) = in[b][a][0..w)   (B x A matrix of w-element blocks, not in place)
+ * zkp_scale_matrix_dev  data[a][b] *= base1^((a0+a) b)            (mode 0: four-step twiddle)
+ *                       data[a][b] *= base1^(a0+a) * base2^b      (mode 1: coset scaling) */
+int zkp_permute_dev(zkp_ctx* ctx, const zkp_buf* in, size_t in_off, zkp_buf* out, size_t out_off, size_t A, size_t B,
+                    size_t w);
+int zkp_scale_matrix_dev(zkp_ctx* ctx, zkp_buf* data, size_t off, size_t rows, size_t cols, size_t a0,
+                         const uint64_t base1[4], const uint64_t base2[4], int mode);
 /* Fft accessors: generator w (kind 0), w^-1 (1), n^-1 (2), coset g (3), g^-1 (4) */
 int zkp_fft_constant(unsigned k, int kind, uint64_t out[4]);
 /* Fft::elements: out[i] = w^i, i < 2^k (device buffer) */

@@ -1,0 +1,72 @@
+"""torchrun worker (one rank per GPU, NCCL): multi-GPU parity checks against the oracle.
+Launched by tests/test_gpu_sharding.py or by hand:
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multigpu_worker.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import dusk_plonk_b200 as z
+    from dusk_plonk_b200.sharding import Communicator, FourStepNtt, ShardedPlonkParams
+    from dusk_plonk_b200.plonk_params import PlonkParams
+    from dusk_plonk_b200.composer import SynthesizedCircuit
+    from oracle import cport, plonk as oplonk
+    from oracle.fields import fr_to_mont_limbs
+    from oracle.rng import SplitMix64, random_fr_raw_limbs
+    import circuits
+
+    ctx = z.Context(local)
+    comm = Communicator(torch.device("cuda", local))
+    # 1. four-step NTT, every kind, natural order in / out
+    for k in (10, 15, 20):
+        n = 1 << k
+        host = random_fr_raw_limbs(k, n)
+        fs = FourStepNtt(ctx, comm, k)
+        for inverse, coset in ((False, False), (True, False), (False, True), (True, True)):
+            fs.scatter_input(host)
+            fs.run(inverse=inverse, coset=coset)
+            out = np.zeros((n, 4), dtype=np.uint64)
+            fs.gather_output(out)
+            t = torch.from_numpy(out.view(np.int64)).cuda()
+            dist.all_reduce(t)                                   # disjoint row slabs: sum = union
+            got = t.cpu().numpy().view(np.uint64)
+            assert np.array_equal(got, cport.ntt(host, k, inverse=inverse, coset=coset)), (k, inverse, coset)
+    # 2. sharded commit and a whole proof with sharded commits: bit-identical to one GPU / the oracle
+    rng = SplitMix64(8349)
+    tau = rng.fr()
+    taum = fr_to_mont_limbs([tau])[0]
+    cs = circuits.readme_circuit()
+    circ = SynthesizedCircuit.from_composer(cs)
+    k = circ.n.bit_length() - 1
+    sp = ShardedPlonkParams.setup_synthetic(ctx, comm, k + 1, taum)
+    prover = z.PlonkKey.compile_with_circuit(sp, b"demo", circ)
+    commit = oplonk.default_commit(tau=tau)
+    opk, ovk = oplonk.compile_circuit(circ, commit, sp.total_len)
+    otr = z.Transcript.base(b"demo", oplonk.vk_transcript_list(ovk), circ.m)
+    bl = [rng.fr() for _ in range(11)]
+    gproof, gpi = prover.create_proof(bl, circ)
+    oproof, opi = oplonk.create_proof(opk, circ, commit, otr, bl)
+    for c in oplonk.Proof.COMM_NAMES:
+        assert getattr(gproof, c) == getattr(oproof, c), c
+    assert gproof.evaluations == oproof.evaluations
+    assert oplonk.verify(ovk, circ.n, gproof, circ.pi_indexes, gpi, otr, oplonk.trapdoor_kzg_check(tau))
+    dist.barrier()
+    if rank == 0:
+        print("MULTIGPU OK world=%d" % world, flush=True)
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
