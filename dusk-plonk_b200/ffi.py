@@ -237,6 +237,7 @@ class Context:
                                             int(coset)))
 
     def ntt_dev_batch(self, src, in_stride, len_in, dst, out_stride, k, inverse, coset, batch):
+        """``batch`` same-shape transforms; src / dst must be whole DeviceBuffers (offset 0)."""
         self.check(self.lib.zkp_ntt_dev_batch(self.h, src.h, in_stride, len_in, dst.h, out_stride, k,
                                               int(inverse), int(coset), batch))
 
@@ -311,15 +312,19 @@ class Context:
     # ---- prover rounds (device-resident)
     @staticmethod
     def ref(buf, off=0, n=None):
-        return PolyRef(buf.h, off, (buf.n - off) if n is None else n)
+        n = (buf.n - off) if n is None else n
+        base, boff = _base(buf)
+        return PolyRef(base.h, boff + off, n)
 
     def fill(self, buf, off, n, value):
         v = np.ascontiguousarray(value, dtype=np.uint64).reshape(4)
-        self.check(self.lib.zkp_buf_fill(self.h, buf.h, off, n, _ptr(v)))
+        base, boff = _base(buf)
+        self.check(self.lib.zkp_buf_fill(self.h, base.h, boff + off, n, _ptr(v)))
 
     def poly_blind(self, buf, off, n, blinders):
         b = as_fr_array(blinders)
-        self.check(self.lib.zkp_poly_blind_dev(self.h, buf.h, off, n, _ptr(b), b.shape[0]))
+        base, boff = _base(buf)
+        self.check(self.lib.zkp_poly_blind_dev(self.h, base.h, boff + off, n, _ptr(b), b.shape[0]))
 
     def perm_lagrange(self, k, enc, roots, out, out_off=0):
         enc = np.ascontiguousarray(enc, dtype=np.uint32)
@@ -391,8 +396,24 @@ class BufferView:
     """buf[off .. off+n): a polynomial living inside a larger device buffer."""
 
     def __init__(self, buf, off=0, n=None):
+        if isinstance(buf, BufferView):
+            buf, off = buf.buf, buf.off + off
         self.buf, self.off = buf, off
         self.n = (buf.n - off) if n is None else n
+
+    def upload(self, arr, off=0):
+        self.buf.upload(arr, self.off + off)
+
+    def download(self, off=0, n=None):
+        return self.buf.download(self.off + off, (self.n - off) if n is None else n)
+
+    def zero(self, off=0, n=None):
+        self.buf.zero(self.off + off, (self.n - off) if n is None else n)
+
+
+def _base(b):
+    """(DeviceBuffer, element offset) of a DeviceBuffer or BufferView."""
+    return (b.buf, b.off) if isinstance(b, BufferView) else (b, 0)
 
 
 class DeviceBuffer:

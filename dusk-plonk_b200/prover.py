@@ -47,10 +47,17 @@ class Prover:
     def _workspace(self):
         if self._ws is None:
             n, c = self.size, self.ctx
-            ws = {"W": c.alloc(4 * n), "Z": c.alloc(n), "PI": c.alloc(n), "L1": c.alloc(n),
-                  "wp": [c.alloc(n + 2) for _ in range(4)], "zp": c.alloc(n + 3),
-                  "e8": [c.alloc(8 * n) for _ in range(4)], "z8": c.alloc(8 * n), "pi8": c.alloc(8 * n),
-                  "l18": c.alloc(8 * n), "T": c.alloc(8 * n), "R": c.alloc(n + 3),
+            # the seven polynomials that go to the 8n coset live side by side (stride S) so their
+            # transforms run as batched launches: a, b, c, d, z, PI, L1
+            S = n + 8
+            P7, E7 = c.alloc(7 * S), c.alloc(7 * 8 * n)
+            P7.zero()
+            ws = {"W": c.alloc(4 * n), "Z": c.alloc(n), "P7": P7, "E7": E7, "S": S,
+                  "wp": [_View(P7, j * S, n + 2) for j in range(4)], "zp": _View(P7, 4 * S, n + 3),
+                  "PI": _View(P7, 5 * S, n), "L1": _View(P7, 6 * S, n),
+                  "e8": [_View(E7, j * 8 * n, 8 * n) for j in range(4)], "z8": _View(E7, 4 * 8 * n, 8 * n),
+                  "pi8": _View(E7, 5 * 8 * n, 8 * n), "l18": _View(E7, 6 * 8 * n, 8 * n),
+                  "T": c.alloc(8 * n), "R": c.alloc(n + 3),
                   "AGG": c.alloc(5 * n), "WZ": c.alloc(5 * n), "SAGG": c.alloc(n + 3), "WZW": c.alloc(n + 3)}
             self._ws = ws
         return self._ws
@@ -84,8 +91,8 @@ class Prover:
         else:
             W = ws["W"]
             W.upload(wa.wires_mont.reshape(4 * n, 4))
+        ctx.ntt_dev_batch(W, n, n, ws["P7"], ws["S"], k, True, False, 4)     # 4 wire iNTTs, one launch set
         for j in range(4):
-            ctx.ntt_dev(_View(W, j * n, n), n, ws["wp"][j], k, True, False)
             ctx.poly_blind(ws["wp"][j], 0, n, bl[2 * j:2 * j + 2])
         comms = [c.affine() for c in self.keypair.commit_batch([ws["wp"][j] for j in range(4)])]
         proof.a_comm, proof.b_comm, proof.c_comm, proof.d_comm = comms
@@ -117,13 +124,10 @@ class Prover:
             PI.upload(wa.dense_pi_mont)
             ctx.ntt_dev(PI, n, PI, k, True, False)
         k8, n8 = k + 3, 8 * n
-        for j in range(4):
-            ctx.ntt_dev(ws["wp"][j], n + 2, ws["e8"][j], k8, False, True)
-        ctx.ntt_dev(ws["zp"], n + 3, ws["z8"], k8, False, True)
-        ctx.ntt_dev(PI, n, ws["pi8"], k8, False, True)
         # L1 * alpha^2: idft of (alpha^2, 0, ..) has every coefficient alpha^2 / n (quotient_poly.rs:264-272)
         ctx.fill(ws["L1"], 0, n, fr_to_mont1(alpha * alpha % _r * pow(n, -1, _r) % _r))
-        ctx.ntt_dev(ws["L1"], n, ws["l18"], k8, False, True)
+        # a, b, c, d, z, PI, L1 -> 8n coset in one batched launch set (slots beyond each length are zero)
+        ctx.ntt_dev_batch(ws["P7"], ws["S"], n + 3, ws["E7"], n8, k8, False, True, 7)
         qa = QuotientArgs()
         for j in range(4):
             qa.wires[j] = ref(ws["e8"][j], 0, n8)

@@ -92,18 +92,24 @@ class ShardedPlonkParams:
         return p
 
     def commit(self, poly):
-        buf, off, n = (poly.buf, poly.off, poly.n) if isinstance(poly, BufferView) else (poly, 0, poly.n)
-        top = self.ctx.poly_degree(buf, off, n)
-        if top >= self.total_len:
-            raise Error("polynomial degree exceeds the SRS")   # identical decision on every rank
-        a, b = self.lo, min(self.hi, top + 1)
-        part = None
-        if b > a:
-            part = g1_from_mont(self.ctx.msm_dev(self.srs, buf, off + a, b - a))
-        return Commitment.from_affine(combine_partials(self.comm.all_gather_bytes(g1_to_bytes(part))))
+        return self.commit_batch([poly])[0]
 
     def commit_batch(self, polys):
-        return [self.commit(p) for p in polys]
+        """Local batched MSM over each polynomial's [lo, hi) coefficients, ONE all-gather of
+        len(polys) x 96 bytes, G - 1 host additions per commitment."""
+        refs, views = [], []
+        for p in polys:
+            buf, off, n = (p.buf, p.off, p.n) if isinstance(p, BufferView) else (p, 0, p.n)
+            views.append((buf, off, n))
+            if n > self.total_len and self.ctx.poly_degree(buf, off + self.total_len, n - self.total_len) >= 0:
+                raise Error("polynomial degree exceeds the SRS")   # identical decision on every rank
+            cnt = max(0, min(self.hi, n) - self.lo)
+            refs.append(self.ctx.ref(buf, off + (self.lo if cnt else 0), cnt))
+        out, _ = self.ctx.commit_batch_dev(self.srs, refs)
+        blob = b"".join(g1_to_bytes(g1_from_mont(out[i])) for i in range(len(polys)))
+        parts = self.comm.all_gather_bytes(blob)
+        return [Commitment.from_affine(combine_partials([pb[96 * i:96 * (i + 1)] for pb in parts]))
+                for i in range(len(polys))]
 
     def commit_or_default(self, poly):
         try:

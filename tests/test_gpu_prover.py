@@ -168,6 +168,10 @@ def test_compile_and_prove_bit_exact(ctx, name):
     assert gproof.evaluations == oproof.evaluations
     # and the restated verifier accepts the GPU proof
     assert oplonk.verify(ovk, n, gproof, circ.pi_indexes, gpi, otr, oplonk.trapdoor_kzg_check(tau))
+    if name == "readme":   # once with the real two-pairing batch_check (src/commitment_scheme.rs:52-64)
+        from oracle import pairing
+        assert oplonk.verify(ovk, n, gproof, circ.pi_indexes, gpi, otr,
+                             pairing.kzg_pairing_check(pairing.g2_mul(pairing.G2_GEN, tau)))
 
 
 def test_unsatisfied_circuit_errs(ctx):
@@ -191,3 +195,35 @@ def test_prover_is_deterministic_and_blinders_matter(ctx):
     p3, pi = prover.create_proof([b + 1 for b in bl], circ)
     assert p3.a_comm != p1.a_comm
     assert oplonk.verify(ovk, circ.n, p3, circ.pi_indexes, pi, otr, oplonk.trapdoor_kzg_check(tau))
+
+
+def test_prove_2p16_gates_bit_exact_vs_c_prover(ctx, cport):
+    """BASELINE config 2: the synthetic 2^16-gate circuit.  Every commitment of the key and the whole
+    proof (11 commitments + 16 evaluations) equal the threaded C restatement; the restated verifier
+    accepts the GPU proof."""
+    from dusk_plonk_b200.composer import synthetic_circuit
+    from oracle import cprover, curve
+    from oracle.fields import fr_to_raw_limbs, g1_to_mont_limbs
+    k = 16
+    circ = synthetic_circuit(k)
+    rng = SplitMix64(8349)
+    tau = rng.fr()
+    pp = PlonkParams.setup_synthetic(ctx, k, fr_to_mont1(tau))
+    prover = z.PlonkKey.compile(pp, circ)
+    # the CPU side gets the very same SRS points the GPU generated
+    cp = cprover.CProver(circ, pp.srs.download(), b"plonk", z.Transcript)
+    for nm in list(oplonk.SELECTORS) + ["s_sigma_%d" % i for i in (1, 2, 3, 4)]:
+        assert prover.verifier_key[nm] == cp.vk[nm], nm
+    bl = [rng.fr() for _ in range(11)]
+    ctrace = {}
+    cproof, cpi = cp.create_proof(bl, circ, trace=ctrace)
+    gtrace = {}
+    gproof, gpi = prover.create_proof(bl, circ, trace=gtrace)
+    assert gpi == cpi
+    assert np.array_equal(gtrace["workspace"]["T"].download(), ctrace["t_poly"])
+    for c in oplonk.Proof.COMM_NAMES:
+        assert getattr(gproof, c) == getattr(cproof, c), c
+    assert gproof.evaluations == cproof.evaluations
+    vk = dict(cp.vk)
+    tr = z.Transcript.base(b"plonk", oplonk.vk_transcript_list(vk), circ.m)
+    assert oplonk.verify(vk, circ.n, gproof, circ.pi_indexes, gpi, tr, oplonk.trapdoor_kzg_check(tau))

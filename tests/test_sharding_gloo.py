@@ -37,14 +37,20 @@ class FakeCtx:
         nz = [i for i in range(n) if buf.vals[off + i]]
         return nz[-1] if nz else -1
 
-    def msm_dev(self, srs, buf, off, n):
+    def ref(self, buf, off=0, n=None):
+        return (buf, off, n)
+
+    def commit_batch_dev(self, srs, refs):
         from oracle import curve
         from oracle.fields import R_MOD, g1_to_mont_limbs
-        assert n <= srs.n
-        acc = 0
-        for i in range(n):
-            acc = (acc + buf.vals[off + i] * pow(srs.tau, srs.first + i, R_MOD)) % R_MOD
-        return g1_to_mont_limbs([curve.mul(curve.G1_GEN, acc)])[0]
+        out = []
+        for buf, off, n in refs:
+            assert n <= srs.n
+            acc = 0
+            for i in range(n):
+                acc = (acc + buf.vals[off + i] * pow(srs.tau, srs.first + i, R_MOD)) % R_MOD
+            out.append(g1_to_mont_limbs([curve.mul(curve.G1_GEN, acc)])[0])
+        return np.stack(out), [0] * len(refs)
 
 
 def _worker(rank, world, port, q):
