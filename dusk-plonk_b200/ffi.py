@@ -396,10 +396,11 @@ class BufferView:
     """buf[off .. off+n): a polynomial living inside a larger device buffer."""
 
     def __init__(self, buf, off=0, n=None):
+        if n is None:
+            n = buf.n - off
         if isinstance(buf, BufferView):
             buf, off = buf.buf, buf.off + off
-        self.buf, self.off = buf, off
-        self.n = (buf.n - off) if n is None else n
+        self.buf, self.off, self.n = buf, off, n
 
     def upload(self, arr, off=0):
         self.buf.upload(arr, self.off + off)
