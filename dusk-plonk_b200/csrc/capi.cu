@@ -399,7 +399,7 @@ int zkp_srs_free(zkp_ctx* ctx, zkp_srs* srs) {
 size_t zkp_srs_len(const zkp_srs* srs) { return srs ? srs->n : 0; }
 
 int zkp_msm_set_window(zkp_ctx* ctx, unsigned c) {
-    if (!ctx || c > 20) return ZKP_ERR_INVALID;
+    if (!ctx || c > 22) return ZKP_ERR_INVALID;
     ctx->msm_window = c;
     return ZKP_OK;
 }

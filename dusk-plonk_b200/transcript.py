@@ -6,7 +6,7 @@ The reference drives a ``zksnarks::plonk::Transcript`` through ``TranscriptProto
 ``src/prover.rs:54-55``).  That crate is absent from the reference tree; upstream dusk-plonk
 0.13 builds it on Merlin (STROBE-128 over Keccak-f[1600]).  This module restates Merlin
 from its published specification -- pinned by Merlin's own "test protocol" known-answer
-vector in ``tests/test_transcript.py`` -- and the dusk encodings on top of it
+vector in ``tests/test_oracle_plonk.py`` -- and the dusk encodings on top of it
 ([EXT-RECALL]: scalars as 32-byte little-endian canonical, commitments as 48-byte
 compressed G1, challenges as 64 squeezed bytes reduced mod r).  The prover takes the
 transcript as an object, so a Rust host keeps its own and nothing on the device depends
