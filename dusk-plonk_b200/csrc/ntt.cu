@@ -204,7 +204,25 @@ __device__ __forceinline__ fr_t scale_factor(const PassParams& p, size_t i) {
     return f;
 }
 
-__global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
+// One radix-2 DIF butterfly on the pair (u, v) with twiddle index widx (w^widx; the inverse
+// transform uses w^-widx = -w^(N/2 - widx)): u <- u + v, v <- (u - v) w^(+-widx).
+__device__ __forceinline__ void dif_butterfly(fr_t& u, fr_t& v, size_t widx, const PassParams& p, size_t half) {
+    const fr_t sum = u + v;
+    if (widx == 0) {
+        v = u - v;
+    } else if (p.inverse) {
+        v = (v - u) * ldg_fr(p.tw + (half - widx));
+    } else {
+        v = (u - v) * ldg_fr(p.tw + widx);
+    }
+    u = sum;
+}
+
+// blockDim = T / 4 threads for a tile of T = 2^(s + c_log) elements: every thread keeps four
+// elements in registers and runs TWO butterfly stages on them (a radix-4 step: 4 multiplications,
+// 3 distinct twiddles) between shared-memory exchanges, halving the shared-memory traffic and
+// the barriers of a stage-per-barrier radix-2 loop; an odd stage count ends with one radix-2 step.
+__global__ void __launch_bounds__(256) ntt_pass_kernel(PassParams p) {
     extern __shared__ uint4 smem[];
     const unsigned T = 1u << (p.s + p.c_log);
     uint4* s_lo = smem;
@@ -228,32 +246,44 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(PassParams p) {
     __syncthreads();
 
     {
-        const bool active = tid < (T >> 1);
-        const unsigned c = tid & (C - 1), q = tid >> p.c_log;
         // index bits below the digit (zero on the last pass)
-        const size_t low = p.last ? 0 : ((rest & (((size_t)1 << (p.lo - p.c_log)) - 1)) << p.c_log) | c;
         const size_t half = ((size_t)1 << p.k) >> 1;
-        for (unsigned t = 0; t < p.s; t++) {
-            if (active) {
-                const unsigned span_log = p.s - 1 - t;
-                const unsigned j = q & ((1u << span_log) - 1);
-                const unsigned d0 = ((q >> span_log) << (span_log + 1)) | j;
-                const unsigned e0 = (d0 << p.c_log) | c;
-                const unsigned e1 = e0 + (1u << (span_log + p.c_log));
-                const fr_t u = lds_fr(s_lo, s_hi, e0);
-                const fr_t v = lds_fr(s_lo, s_hi, e1);
-                fr_t diff;
-                if (p.lo == 0 && span_log == 0) {
-                    diff = u - v;  // the last stage of the transform has twiddle 1 everywhere
-                } else {
-                    size_t widx = ((((size_t)j << p.lo) | low) << t) << p.tw_shift;
-                    const bool flip = p.inverse && widx != 0;  // w^-j = -w^(N/2-j)
-                    diff = flip ? v - u : u - v;
-                    widx = flip ? half - widx : widx;
-                    diff = diff * ldg_fr(p.tw + widx);
-                }
-                sts_fr(s_lo, s_hi, e0, u + v);
-                sts_fr(s_lo, s_hi, e1, diff);
+        unsigned t = 0;
+        for (; t + 1 < p.s; t += 2) {  // radix-4 step: stages t and t + 1
+            const unsigned span = p.s - 1 - t;  // >= 1
+            for (unsigned g = tid; g < (T >> 2); g += blockDim.x) {
+                const unsigned c = g & (C - 1), q = g >> p.c_log;
+                const size_t low = p.last ? 0 : ((rest & (((size_t)1 << (p.lo - p.c_log)) - 1)) << p.c_log) | c;
+                const unsigned j0 = q & ((1u << (span - 1)) - 1);
+                const unsigned d0 = ((q >> (span - 1)) << (span + 1)) | j0;
+                const unsigned hstep = 1u << (span - 1 + p.c_log);
+                const unsigned e0 = (d0 << p.c_log) | c, e1 = e0 + hstep, e2 = e0 + 2 * hstep, e3 = e2 + hstep;
+                fr_t x0 = lds_fr(s_lo, s_hi, e0), x1 = lds_fr(s_lo, s_hi, e1);
+                fr_t x2 = lds_fr(s_lo, s_hi, e2), x3 = lds_fr(s_lo, s_hi, e3);
+                const size_t ja = ((size_t)j0 << p.lo) | low;
+                const size_t jb = ((size_t)(j0 + (1u << (span - 1))) << p.lo) | low;
+                // stage t: (x0, x2) and (x1, x3)
+                dif_butterfly(x0, x2, (ja << t) << p.tw_shift, p, half);
+                dif_butterfly(x1, x3, (jb << t) << p.tw_shift, p, half);
+                // stage t + 1: (x0, x1) and (x2, x3); the very last stage of the transform has w = 1
+                const size_t w1 = (p.lo == 0 && span == 1) ? 0 : ((ja << (t + 1)) << p.tw_shift);
+                dif_butterfly(x0, x1, w1, p, half);
+                dif_butterfly(x2, x3, w1, p, half);
+                sts_fr(s_lo, s_hi, e0, x0); sts_fr(s_lo, s_hi, e1, x1);
+                sts_fr(s_lo, s_hi, e2, x2); sts_fr(s_lo, s_hi, e3, x3);
+            }
+            __syncthreads();
+        }
+        if (t < p.s) {  // one radix-2 stage left (span = 0)
+            for (unsigned b = tid; b < (T >> 1); b += blockDim.x) {
+                const unsigned c = b & (C - 1), q = b >> p.c_log;
+                const size_t low = p.last ? 0 : ((rest & (((size_t)1 << (p.lo - p.c_log)) - 1)) << p.c_log) | c;
+                const unsigned e0 = ((q << 1) << p.c_log) | c, e1 = e0 + C;
+                fr_t u = lds_fr(s_lo, s_hi, e0), v = lds_fr(s_lo, s_hi, e1);
+                const size_t widx = p.lo == 0 ? 0 : ((low << t) << p.tw_shift);
+                dif_butterfly(u, v, widx, p, half);
+                sts_fr(s_lo, s_hi, e0, u);
+                sts_fr(s_lo, s_hi, e1, v);
             }
             __syncthreads();
         }
@@ -335,7 +365,7 @@ int ntt_run(zkp_ctx* ctx, const fr_t* in, size_t in_stride, size_t len_in, fr_t*
             if (coset) { p.sc_lo = dom->gi_lo; p.sc_hi = dom->gi_hi; }
         }
         const unsigned tlog = p.s + p.c_log;
-        const unsigned threads = tlog ? (1u << (tlog - 1)) : 1;
+        const unsigned threads = tlog >= 2 ? (1u << (tlog - 2)) : 1;
         const size_t smem = ((size_t)2 << tlog) * sizeof(uint4);
         dim3 grid((unsigned)(n >> tlog), batch);
         ntt_pass_kernel<<<grid, threads < 32 ? 32 : threads, smem, ctx->stream>>>(p);
