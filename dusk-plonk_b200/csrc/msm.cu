@@ -25,6 +25,8 @@
 //   7. host: one Fermat inversion -> affine
 // Addition in G1 is commutative and the result is normalised to affine, so the output is
 // bit-identical to any correct CPU evaluation regardless of accumulation order.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace zkp {
@@ -51,6 +53,7 @@ struct MsmScratch {
     g1_xyzz* planes = nullptr;    // [nb][c * plane chunks] + [nb][32] + [nb]
     long long* top = nullptr;
     int acc_blocks_per_sm = 0;
+    int acc_variant = 4;
 };
 
 static constexpr uint32_t DIGIT_ZERO = 0xffffffffu;
@@ -176,7 +179,11 @@ __global__ void msm_scatter_kernel(const __grid_constant__ MsmBatch batch, const
 // distribution.  A bucket that lies inside one chunk is written directly; a bucket cut by a chunk
 // boundary leaves partial sums in the chunk's head slot (first segment of the chunk) or tail slot
 // (last segment), which msm_merge_kernel adds up.
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1_affine* table, const uint32_t* sorted,
+// MB = resident blocks per SM the register allocation is bounded for (2: 172 registers, 4: 128
+// registers with ~70 bytes of spill): more warps hide the dependent IMAD chains (ncu: `wait`
+// stalls dominate at 2 blocks / SM).
+template <int MB>
+__global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const g1_affine* table, const uint32_t* sorted,
                                                             const uint32_t* offsets, const uint32_t* counts,
                                                             const uint32_t* meta, uint32_t B, uint32_t L,
                                                             uint32_t nchunks, size_t entry_stride, g1_xyzz* buckets,
@@ -192,12 +199,12 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const g1_affine* ta
     offsets += (size_t)pb * B; counts += (size_t)pb * B;
     buckets += (size_t)pb * B; slots += (size_t)pb * 2 * nchunks;
     // bucket holding entry `start`: the last b with offsets[b] <= start
-    uint32_t lo = 0, hi = B;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (offsets[mid] <= start) lo = mid; else hi = mid;
+    uint32_t blo = 0, bhi = B;
+    while (bhi - blo > 1) {
+        const uint32_t mid = (blo + bhi) >> 1;
+        if (offsets[mid] <= start) blo = mid; else bhi = mid;
     }
-    uint32_t bk = lo, bbeg = offsets[bk], bend = bbeg + counts[bk];
+    uint32_t bk = blo, bbeg = offsets[bk], bend = bbeg + counts[bk];
     uint32_t seg = start;
     bool first = true;
     g1_xyzz acc = g1_xyzz::inf();
@@ -523,8 +530,19 @@ static int msm_scratch(zkp_ctx* ctx, MsmScratch** out) {
         ctx->msm = new MsmScratch();
         ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->top, sizeof(long long)));
         ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->meta, 4 * MSM_MAX_BATCH * sizeof(uint32_t)));
+        int mb = 4;
+        if (const char* e = getenv("ZKP_MSM_BLOCKS_PER_SM")) mb = atoi(e);  // tuning knob: 2..6
+        if (mb < 2) mb = 2;
+        if (mb > 6) mb = 6;
+        ctx->msm->acc_variant = mb;
         int nb = 0;
-        ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel, 128, 0));
+        switch (mb) {
+            case 2: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<2>, 128, 0)); break;
+            case 3: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<3>, 128, 0)); break;
+            case 4: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<4>, 128, 0)); break;
+            case 5: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<5>, 128, 0)); break;
+            default: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<6>, 128, 0)); break;
+        }
         ctx->msm->acc_blocks_per_sm = nb > 0 ? nb : 1;
     }
     *out = ctx->msm;
@@ -646,8 +664,17 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     }
     {
     ProfScope prof(ctx, "msm_accumulate");
-    msm_accumulate_kernel<<<dim3((nchunks + 127) / 128, nb), 128, 0, st>>>(
-        srs->d, s->sorted, s->offsets, s->counts, s->meta, B, (uint32_t)L, nchunks, E, s->buckets, s->slots);
+    const dim3 agrid((nchunks + 127) / 128, nb);
+#define ZKP_ACC(MB) msm_accumulate_kernel<MB><<<agrid, 128, 0, st>>>( \
+        srs->d, s->sorted, s->offsets, s->counts, s->meta, B, (uint32_t)L, nchunks, E, s->buckets, s->slots)
+    switch (s->acc_variant) {
+        case 2: ZKP_ACC(2); break;
+        case 3: ZKP_ACC(3); break;
+        case 4: ZKP_ACC(4); break;
+        case 5: ZKP_ACC(5); break;
+        default: ZKP_ACC(6); break;
+    }
+#undef ZKP_ACC
     ZKP_LAUNCHED(ctx);
     }
     {

@@ -22,6 +22,8 @@
 //  * Zero padding is applied on load; coset scaling (g^i on input of the forward
 //    transform, g^-i n^-1 on output of the inverse) is fused into the first / last pass
 //    through two-level power tables (g^i = lo[i & 1023] * hi[i >> 10]).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace zkp {
@@ -222,7 +224,9 @@ __device__ __forceinline__ void dif_butterfly(fr_t& u, fr_t& v, size_t widx, con
 // elements in registers and runs TWO butterfly stages on them (a radix-4 step: 4 multiplications,
 // 3 distinct twiddles) between shared-memory exchanges, halving the shared-memory traffic and
 // the barriers of a stage-per-barrier radix-2 loop; an odd stage count ends with one radix-2 step.
-__global__ void __launch_bounds__(256) ntt_pass_kernel(PassParams p) {
+// MB bounds the register allocation for MB resident blocks per SM (3: 80 registers, no spill).
+template <int MB>
+__global__ void __launch_bounds__(256, MB) ntt_pass_kernel(PassParams p) {
     extern __shared__ uint4 smem[];
     const unsigned T = 1u << (p.s + p.c_log);
     uint4* s_lo = smem;
@@ -368,7 +372,17 @@ int ntt_run(zkp_ctx* ctx, const fr_t* in, size_t in_stride, size_t len_in, fr_t*
         const unsigned threads = tlog >= 2 ? (1u << (tlog - 2)) : 1;
         const size_t smem = ((size_t)2 << tlog) * sizeof(uint4);
         dim3 grid((unsigned)(n >> tlog), batch);
-        ntt_pass_kernel<<<grid, threads < 32 ? 32 : threads, smem, ctx->stream>>>(p);
+        static int mb = 0;
+        if (!mb) {
+            mb = 3;
+            if (const char* e = getenv("ZKP_NTT_BLOCKS_PER_SM")) mb = atoi(e);  // tuning knob: 2..4
+            if (mb < 2) mb = 2;
+            if (mb > 4) mb = 4;
+        }
+        const unsigned nthreads = threads < 32 ? 32 : threads;
+        if (mb == 2) ntt_pass_kernel<2><<<grid, nthreads, smem, ctx->stream>>>(p);
+        else if (mb == 3) ntt_pass_kernel<3><<<grid, nthreads, smem, ctx->stream>>>(p);
+        else ntt_pass_kernel<4><<<grid, nthreads, smem, ctx->stream>>>(p);
         ZKP_LAUNCHED(ctx);
         src = p.out; src_stride = p.out_stride;
     }
