@@ -53,7 +53,7 @@ struct MsmScratch {
     g1_xyzz* planes = nullptr;    // [nb][c * plane chunks] + [nb][32] + [nb]
     long long* top = nullptr;
     int acc_blocks_per_sm = 0;
-    int acc_variant = 4;
+    int acc_variant = 3;
 };
 
 static constexpr uint32_t DIGIT_ZERO = 0xffffffffu;
@@ -530,7 +530,7 @@ static int msm_scratch(zkp_ctx* ctx, MsmScratch** out) {
         ctx->msm = new MsmScratch();
         ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->top, sizeof(long long)));
         ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->meta, 4 * MSM_MAX_BATCH * sizeof(uint32_t)));
-        int mb = 4;
+        int mb = 3;  // measured best on B200 (2^22: 22.3 / 21.8 / 23.1 / 23.7 / 24.4 ms for 2..6)
         if (const char* e = getenv("ZKP_MSM_BLOCKS_PER_SM")) mb = atoi(e);  // tuning knob: 2..6
         if (mb < 2) mb = 2;
         if (mb > 6) mb = 6;
