@@ -1,4 +1,5 @@
 // extern "C" boundary of libzkp_b200.so (declared in include/zkp_b200.h).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -327,7 +328,11 @@ int zkp_fft_elements_dev(zkp_ctx* ctx, unsigned k, zkp_buf* out) {
 static int srs_alloc(zkp_ctx* ctx, size_t n, zkp_srs** out) {
     zkp_srs* s = new zkp_srs();
     s->n = n;
-    s->c = ctx->msm_window ? (ctx->msm_window < 2 ? 2 : ctx->msm_window) : msm_choose_window(n);
+    unsigned forced = ctx->msm_window;
+    if (!forced)
+        if (const char* e = getenv("ZKP_MSM_WINDOW")) forced = (unsigned)atoi(e);  // tuning knob
+    if (forced > 22) forced = 22;
+    s->c = forced ? (forced < 2 ? 2 : forced) : msm_choose_window(n);
     s->W = 255 / s->c + 1;
     if ((size_t)s->W * n >= (1ull << 31)) { delete s; return ZKP_ERR_INVALID; }
     cudaError_t e = cudaMalloc(&s->d, (n ? (size_t)s->W * n : 1) * sizeof(g1_affine));

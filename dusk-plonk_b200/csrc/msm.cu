@@ -13,13 +13,14 @@
 //
 // Pipeline (all on the device, one stream):
 //   1. msm_digits_kernel      Fr Montgomery -> canonical, signed digits, bucket histogram
-//   2. msm_scan_kernel        bucket offsets; buckets are cut into tasks of <= CAP entries so
-//                             skewed digit distributions (top window, small coefficients,
-//                             carry-only digits) cannot serialise on one thread
+//   2. msm_scan_*_kernel      bucket offsets (three-launch tiled exclusive scan)
 //   3. msm_scatter_kernel     counting sort of (table index, sign) by bucket
-//   4. msm_accumulate_kernel  one thread per task, XYZZ mixed additions (8M + 2S each, 384-bit
-//                             Montgomery on the integer pipe) -- the hot kernel
-//   5. msm_merge_kernel       buckets made of several tasks: one warp sums the partials
+//   4. msm_accumulate_kernel  one thread per chunk of L consecutive sorted entries, whatever
+//                             buckets they fall in: XYZZ mixed additions (8M + 2S each, 384-bit
+//                             Montgomery on the integer pipe) -- the hot kernel; equal work per
+//                             thread for ANY digit distribution (top window, tiny coefficients,
+//                             carry-only digits)
+//   5. msm_merge[_giant]_kernel  buckets cut by chunk boundaries: add their partial sums
 //   6. msm_rowcol / weighted_planes / final_sum    sum_b (b+1) * B[b]: row + column sums of the
 //                             (hi, lo) weight grid, then two short bit-plane weighted sums
 //   7. host: one Fermat inversion -> affine
@@ -48,6 +49,7 @@ struct MsmScratch {
     uint32_t* cursor = nullptr;   // [nb][B]
     uint32_t* giant = nullptr;    // [nb][B]      buckets whose merge needs a whole block
     uint32_t* meta = nullptr;     // [nb][4]      entries, giant count, overflow flag, pad
+    uint32_t* tile_sums = nullptr;  // [MSM_MAX_BATCH][1024] scan scratch
     g1_xyzz* buckets = nullptr;   // [nb][B]
     g1_xyzz* slots = nullptr;     // [nb][2 * chunks]  head / tail partial sums of each chunk
     g1_xyzz* planes = nullptr;    // [nb][c * plane chunks] + [nb][32] + [nb]
@@ -122,40 +124,88 @@ __global__ void msm_digits_kernel(const __grid_constant__ MsmBatch batch, uint32
     }
 }
 
-// One block per polynomial: exclusive scan of its B bucket counts -> entry offsets; meta[0] = entries.
-__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* counts, uint32_t* offsets, uint32_t* cursor,
-                                                        uint32_t* meta, uint32_t B) {
-    __shared__ uint32_t ws[32];
-    const unsigned T = blockDim.x, tid = threadIdx.x, pb = blockIdx.x;
-    counts += (size_t)pb * B; offsets += (size_t)pb * B; cursor += (size_t)pb * B;
-    const uint32_t per = (B + T - 1) / T;
-    const uint32_t lo = tid * per < B ? tid * per : B, hi = lo + per < B ? lo + per : B;
-    uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += counts[i];
-    uint32_t incl = sum;
-    const unsigned lane = tid & 31, wid = tid >> 5;
+// Exclusive scan of the B bucket counts of every polynomial -> entry offsets (and the scatter
+// cursors), meta[4 pb] = number of entries.  Three small launches: per-tile sums, scan of the tile
+// sums, per-tile rescan -- all loads and stores coalesced 16-byte accesses.
+static constexpr unsigned SCAN_T = 256, SCAN_PER = 8, SCAN_TILE = SCAN_T * SCAN_PER;  // 2048 counters / block
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* ws, uint32_t* total) {
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t incl = v;
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (unsigned)o) incl += v;
+        uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += x;
     }
     if (lane == 31) ws[wid] = incl;
     __syncthreads();
     if (wid == 0) {
-        uint32_t e = lane < (T >> 5) ? ws[lane] : 0;
-        uint32_t x = e;
+        uint32_t e = lane < nw ? ws[lane] : 0, x = e;
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= (unsigned)o) x += v;
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (unsigned)o) x += y;
         }
-        ws[lane] = x - e;  // exclusive
-        if (lane == 31) { meta[4 * pb] = x; meta[4 * pb + 1] = 0; }
+        ws[lane] = x - e;
+        if (lane == 31) ws[32] = x;
     }
     __syncthreads();
-    uint32_t run = ws[wid] + (incl - sum);
-    for (uint32_t i = lo; i < hi; i++) {
-        offsets[i] = run;
-        cursor[i] = run;
-        run += counts[i];
+    *total = ws[32];
+    return ws[wid] + incl - v;
+}
+
+// grid (tiles, nb): tile_sums[pb][tile] = sum of the tile's counters
+__global__ void __launch_bounds__(SCAN_T) msm_scan_tiles_kernel(const uint32_t* counts, uint32_t B, uint32_t tiles,
+                                                               uint32_t* tile_sums) {
+    __shared__ uint32_t ws[33];
+    const unsigned pb = blockIdx.y;
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER;
+    const uint32_t* c = counts + (size_t)pb * B;
+    uint32_t sum = 0;
+    if (base + SCAN_PER <= B) {
+        const uint4 a = *reinterpret_cast<const uint4*>(c + base), b2 = *reinterpret_cast<const uint4*>(c + base + 4);
+        sum = a.x + a.y + a.z + a.w + b2.x + b2.y + b2.z + b2.w;
+    } else {
+        for (uint32_t i = base; i < B && i < base + SCAN_PER; i++) sum += c[i];
+    }
+    uint32_t total;
+    block_exclusive_scan(sum, ws, &total);
+    if (threadIdx.x == 0) tile_sums[(size_t)pb * tiles + blockIdx.x] = total;
+}
+
+// one block per polynomial: exclusive scan of its <= 1024 tile sums in place; meta[4 pb] = entries
+__global__ void __launch_bounds__(1024) msm_scan_sums_kernel(uint32_t* tile_sums, uint32_t tiles, uint32_t* meta) {
+    __shared__ uint32_t ws[33];
+    const unsigned pb = blockIdx.x;
+    uint32_t* t = tile_sums + (size_t)pb * tiles;
+    const uint32_t v = threadIdx.x < tiles ? t[threadIdx.x] : 0;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, ws, &total);
+    if (threadIdx.x < tiles) t[threadIdx.x] = ex;
+    if (threadIdx.x == 0) { meta[4 * pb] = total; meta[4 * pb + 1] = 0; }
+}
+
+// grid (tiles, nb): offsets / cursor of the tile's buckets
+__global__ void __launch_bounds__(SCAN_T) msm_scan_apply_kernel(const uint32_t* counts, uint32_t B, uint32_t tiles,
+                                                               const uint32_t* tile_sums, uint32_t* offsets,
+                                                               uint32_t* cursor) {
+    __shared__ uint32_t ws[33];
+    const unsigned pb = blockIdx.y;
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER;
+    const uint32_t* c = counts + (size_t)pb * B;
+    uint32_t v[SCAN_PER];
+    uint32_t sum = 0;
+#pragma unroll
+    for (unsigned i = 0; i < SCAN_PER; i++) {
+        v[i] = base + i < B ? c[base + i] : 0;
+        sum += v[i];
+    }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(sum, ws, &total) + tile_sums[(size_t)pb * tiles + blockIdx.x];
+    uint32_t* o = offsets + (size_t)pb * B;
+    uint32_t* cu = cursor + (size_t)pb * B;
+#pragma unroll
+    for (unsigned i = 0; i < SCAN_PER; i++) {
+        if (base + i < B) { o[base + i] = run; cu[base + i] = run; }
+        run += v[i];
     }
 }
 
@@ -229,7 +279,7 @@ __global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const g1_affine
 
 // One thread per bucket: empty -> infinity; inside one chunk -> already written; otherwise add the
 // partial sums of the chunks it spans (buckets spanning > GIANT_PARTS chunks go to the block kernel).
-__global__ void __launch_bounds__(128) msm_merge_kernel(const uint32_t* offsets, const uint32_t* counts, uint32_t B,
+__global__ void __launch_bounds__(128, 4) msm_merge_kernel(const uint32_t* offsets, const uint32_t* counts, uint32_t B,
                                                        uint32_t L, uint32_t nchunks, const g1_xyzz* slots,
                                                        g1_xyzz* buckets, uint32_t* giant, uint32_t* meta) {
     const unsigned pb = blockIdx.y;
@@ -300,7 +350,8 @@ __device__ __forceinline__ g1_xyzz warp_point_sum(g1_xyzz v, g1_xyzz* w, unsigne
 }
 
 // grid (nrows + ncols, nb), 32 threads.  rc[pb][0 .. nrows) = R, rc[pb][nrows .. nrows+ncols) = C.
-__global__ void __launch_bounds__(32) msm_rowcol_kernel(const g1_xyzz* buckets, uint32_t B, unsigned h, uint32_t nrows,
+// 16 resident one-warp blocks per SM (128 registers): all rows + columns of a 4-polynomial batch in one wave
+__global__ void __launch_bounds__(32, 16) msm_rowcol_kernel(const g1_xyzz* buckets, uint32_t B, unsigned h, uint32_t nrows,
                                                        uint32_t ncols, g1_xyzz* rc) {
     __shared__ g1_xyzz w[32];
     const unsigned lane = threadIdx.x, pb = blockIdx.y;
@@ -530,6 +581,7 @@ static int msm_scratch(zkp_ctx* ctx, MsmScratch** out) {
         ctx->msm = new MsmScratch();
         ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->top, sizeof(long long)));
         ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->meta, 4 * MSM_MAX_BATCH * sizeof(uint32_t)));
+        ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->tile_sums, 1024 * MSM_MAX_BATCH * sizeof(uint32_t)));
         int mb = 3;  // measured best on B200 (2^22: 22.3 / 21.8 / 23.1 / 23.7 / 24.4 ms for 2..6)
         if (const char* e = getenv("ZKP_MSM_BLOCKS_PER_SM")) mb = atoi(e);  // tuning knob: 2..6
         if (mb < 2) mb = 2;
@@ -553,7 +605,7 @@ void msm_free(zkp_ctx* ctx) {
     MsmScratch* s = ctx->msm;
     if (!s) return;
     cudaFree(s->digits); cudaFree(s->sorted); cudaFree(s->counts); cudaFree(s->offsets); cudaFree(s->cursor);
-    cudaFree(s->giant); cudaFree(s->meta); cudaFree(s->buckets); cudaFree(s->slots); cudaFree(s->planes);
+    cudaFree(s->giant); cudaFree(s->meta); cudaFree(s->tile_sums); cudaFree(s->buckets); cudaFree(s->slots); cudaFree(s->planes);
     cudaFree(s->top);
     delete s;
     ctx->msm = nullptr;
@@ -656,8 +708,15 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     msm_digits_kernel<<<dim3((unsigned)((maxlen + 255) / 256), nb), 256, 0, st>>>(
         batch, (uint32_t)n, (uint32_t)srs->n, c, W, s->digits, s->counts, s->meta);
     ZKP_LAUNCHED(ctx);
-    msm_scan_kernel<<<nb, 1024, 0, st>>>(s->counts, s->offsets, s->cursor, s->meta, B);
-    ZKP_LAUNCHED(ctx);
+    {
+        const uint32_t tiles = (B + SCAN_TILE - 1) / SCAN_TILE;  // <= 1024 for c <= 22
+        msm_scan_tiles_kernel<<<dim3(tiles, nb), SCAN_T, 0, st>>>(s->counts, B, tiles, s->tile_sums);
+        ZKP_LAUNCHED(ctx);
+        msm_scan_sums_kernel<<<nb, 1024, 0, st>>>(s->tile_sums, tiles, s->meta);
+        ZKP_LAUNCHED(ctx);
+        msm_scan_apply_kernel<<<dim3(tiles, nb), SCAN_T, 0, st>>>(s->counts, B, tiles, s->tile_sums, s->offsets, s->cursor);
+        ZKP_LAUNCHED(ctx);
+    }
     msm_scatter_kernel<<<dim3((unsigned)((n + 255) / 256), nb), 256, 0, st>>>(
         batch, s->digits, (uint32_t)n, W, (uint32_t)srs->n, B, s->cursor, s->sorted);
     ZKP_LAUNCHED(ctx);
