@@ -543,15 +543,29 @@ static g1_affine host_xyzz_to_affine(const g1_xyzz& a) {
     return r;
 }
 
-// Window width for an SRS of n powers: minimise Fq multiplications of (n * W mixed additions,
-// 10 each) + (bucket reduction: 2 * 2^(c-1) full additions, 14 each, weighted 2x for its lower
-// parallel efficiency).  Wide windows pay off for large n: c = 20 at 2^22 (13 table rows instead of 16).
+// Window width for an SRS of n powers, calibrated on B200 (bench/sweep_window.sh): the n * W mixed
+// additions (10 Fq mul each) dominate; the sort / merge / bucket-reduction side is latency-bound and
+// roughly constant up to 2^16 buckets, then grows ~160 Fq-mul-equivalents per extra bucket.
+//   measured best: c = 16 for 2^16 .. 2^21 (W = 16), c = 20 from 2^22 (W = 13).
 unsigned msm_choose_window(size_t n) {
+    if (n == 0) n = 1;
     unsigned best = 4;
     double best_cost = 1e300;
-    for (unsigned c = 4; c <= 22; c++) {
+    if (n < (1u << 14)) {
+        for (unsigned c = 4; c <= 16; c++) {
+            const unsigned W = 255 / c + 1;
+            const double cost = 10.0 * (double)n * W + 56.0 * (double)(1u << (c - 1));
+            if (cost < best_cost) { best_cost = cost; best = c; }
+        }
+        return best;
+    }
+    // only widths whose top window keeps >= 8 scalar bits (255 mod c): a short top window
+    // funnels n / 2^bits entries into a handful of buckets (c = 17: the carry alone)
+    static const unsigned cand[] = {13, 16, 20, 22};
+    for (unsigned c : cand) {
         const unsigned W = 255 / c + 1;
-        const double cost = 10.0 * (double)(n ? n : 1) * W + 2.0 * 14.0 * 2.0 * (double)(1u << (c - 1));
+        const double B = (double)(1u << (c - 1));
+        const double cost = 10.0 * (double)n * W + 160.0 * (B > 65536.0 ? B - 65536.0 : 0.0);
         if (cost < best_cost) { best_cost = cost; best = c; }
     }
     return best;
