@@ -95,6 +95,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload, logn):
+    """DRAM bytes of the dominant kernel from the committed ncu --set full capture, if one exists for
+    this workload/size (profiles/traffic.json); else None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        ent = json.load(open(p)).get("%s:%d" % (workload, logn))
+        if ent:
+            return ent["dram_bytes_per_launch"]
+    return None
+
+
 def imad_peak():
     """Integer multiply-add peak: measured by bench/imad_peak.cu if a result is committed
     under profiles/, else nominal 148 SM x 64 lanes x 1.965 GHz."""
@@ -423,6 +434,7 @@ def main():
                         "peak_source": hbm_src, "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_avg_ms / ms_step,
                         "imad_achieved_T": imad, "imad_frac": imad / imad_pk, "imad_peak_source": imad_src,
                         "algorithmic": "64 B per element; 68*N*log2(N) mul-adds (SURVEY 8d)"}
+        roofline["traffic"] = measured_traffic(args.workload, args.logn)
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong" if shard else "weak",

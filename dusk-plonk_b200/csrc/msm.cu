@@ -56,6 +56,7 @@ struct MsmScratch {
     long long* top = nullptr;
     int acc_blocks_per_sm = 0;
     int acc_variant = 3;
+    int acc_blocks_per_sm2 = 0;   // occupancy of the 2-blocks/SM build used for small jobs
 };
 
 static constexpr uint32_t DIGIT_ZERO = 0xffffffffu;
@@ -610,6 +611,9 @@ static int msm_scratch(zkp_ctx* ctx, MsmScratch** out) {
             default: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<6>, 128, 0)); break;
         }
         ctx->msm->acc_blocks_per_sm = nb > 0 ? nb : 1;
+        int nb2 = 0;
+        ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, msm_accumulate_kernel<2>, 128, 0));
+        ctx->msm->acc_blocks_per_sm2 = nb2 > 0 ? nb2 : 1;
     }
     *out = ctx->msm;
     return ZKP_OK;
@@ -683,7 +687,10 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     if (E >= (1ull << 32)) return ZKP_ERR_INVALID;
     // chunk length: one wave of resident threads when the job is small, 128-entry chunks (many
     // waves, negligible tail) when it is large
-    const size_t resident = (size_t)ctx->sm_count * s->acc_blocks_per_sm * 128;
+    // small jobs (about one wave) run best with the unconstrained 2-blocks/SM build, large ones with 3
+    const int variant = (getenv("ZKP_MSM_BLOCKS_PER_SM") || E * nb >= ((size_t)1 << 23)) ? s->acc_variant : 2;
+    const size_t resident =
+        (size_t)ctx->sm_count * (variant == 2 ? s->acc_blocks_per_sm2 : s->acc_blocks_per_sm) * 128;
     size_t L = (E * nb + resident - 1) / resident;
     if (L < 8) L = 8;
     if (L > 128) L = 128;
@@ -740,7 +747,7 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     const dim3 agrid((nchunks + 127) / 128, nb);
 #define ZKP_ACC(MB) msm_accumulate_kernel<MB><<<agrid, 128, 0, st>>>( \
         srs->d, s->sorted, s->offsets, s->counts, s->meta, B, (uint32_t)L, nchunks, E, s->buckets, s->slots)
-    switch (s->acc_variant) {
+    switch (variant) {
         case 2: ZKP_ACC(2); break;
         case 3: ZKP_ACC(3); break;
         case 4: ZKP_ACC(4); break;
