@@ -257,6 +257,40 @@ class Plonk:
         one_min_bit_b = self.gate_mul(Constraint().mult(1).a(one_min_bit).b(b))
         return self.gate_add(Constraint().left(1).right(1).a(one_min_bit_b).b(bit_times_a))
 
+    def assert_equal_point(self, a, b):
+        self.assert_equal(a[0], b[0])
+        self.assert_equal(a[1], b[1])
+
+    def component_select_point(self, bit, a, b):
+        return (self.component_select(bit, a[0], b[0]), self.component_select(bit, a[1], b[1]))
+
+    def component_select_identity(self, bit, a):
+        return (self.component_select_zero(bit, a[0]), self.component_select_one(bit, a[1]))
+
+    # src/lib.rs:881-917: N bits, little-endian, 2 N + 1 gates
+    def component_decomposition(self, scalar, n_bits):
+        assert 0 < n_bits <= 256
+        v = self[scalar]
+        acc = self.ZERO
+        decomposition = []
+        for i in range(n_bits):
+            d = self.append_witness((v >> i) & 1)
+            self.component_boolean(d)
+            acc = self.gate_add(Constraint().left(pow(2, i, R_MOD)).right(1).a(d).b(acc))
+            decomposition.append(d)
+        self.assert_equal(acc, scalar)
+        return decomposition
+
+    # src/lib.rs:937-957: double-and-add over the 252 bits of the scalar
+    def component_mul_point(self, jubjub, point):
+        bits = self.component_decomposition(jubjub, 252)
+        result = (self.ZERO, self.ONE)
+        for bit in reversed(bits):
+            result = self.component_add_point(result, result)
+            to_add = self.component_select_identity(bit, point)
+            result = self.component_add_point(result, to_add)
+        return result
+
     # src/lib.rs:1041-1163
     def component_range(self, witness, num_bits):
         bits = _bits_msb_first(self[witness])

@@ -89,3 +89,17 @@ def g1_to_bytes(p):
 def g1_from_bytes(b):
     x, y = int.from_bytes(b[:48], "big"), int.from_bytes(b[48:96], "big")
     return None if x == 0 and y == 0 else (x, y)
+
+
+def g1_decompress(b):
+    """Inverse of ``transcript.g1_compress`` (48-byte zcash-style compressed G1)."""
+    assert len(b) == 48 and b[0] & 0x80, "not a compressed point"
+    if b[0] & 0x40:
+        return None
+    x = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:], "big")
+    y2 = (pow(x, 3, P_MOD) + 4) % P_MOD
+    y = pow(y2, (P_MOD + 1) // 4, P_MOD)          # p = 3 mod 4
+    assert y * y % P_MOD == y2, "x is not on the curve"
+    if (y > P_MOD - y) != bool(b[0] & 0x20):
+        y = P_MOD - y
+    return (x, y)

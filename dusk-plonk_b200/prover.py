@@ -31,6 +31,33 @@ class Proof:
         return all(getattr(self, c) == getattr(o, c) for c in COMM_NAMES) and \
             dict(self.evaluations) == dict(o.evaluations)
 
+    # Wire format (src/prover/proof.rs:36 derives SCALE Encode/Decode; fixed-size fields encode as their
+    # bytes in declaration order): 11 compressed G1 points (48 B) then the 16 evaluations (32 B LE) in
+    # the field order of ``Evaluations`` (src/prover/linearization_poly.rs:113-130) = 1040 bytes.
+    # [EXT-RECALL] for the per-type encodings (zcash-style compressed G1, canonical little-endian Fr).
+    WIRE_EVAL_ORDER = ("a_eval", "b_eval", "c_eval", "d_eval", "a_next_eval", "b_next_eval", "d_next_eval",
+                       "q_arith_eval", "q_c_eval", "q_l_eval", "q_r_eval", "s_sigma_1_eval", "s_sigma_2_eval",
+                       "s_sigma_3_eval", "r_poly_eval", "perm_eval")
+
+    def to_bytes(self):
+        from .transcript import g1_compress
+        out = b"".join(g1_compress(getattr(self, c)) for c in COMM_NAMES)
+        return out + b"".join((self.evaluations[k] % _r).to_bytes(32, "little") for k in self.WIRE_EVAL_ORDER)
+
+    @classmethod
+    def from_bytes(cls, data):
+        from .field import g1_decompress
+        assert len(data) == 48 * 11 + 32 * 16
+        p = cls()
+        for i, c in enumerate(COMM_NAMES):
+            setattr(p, c, g1_decompress(data[48 * i:48 * (i + 1)]))
+        off = 48 * 11
+        for i, k in enumerate(cls.WIRE_EVAL_ORDER):
+            v = int.from_bytes(data[off + 32 * i:off + 32 * (i + 1)], "little")
+            assert v < _r, "non-canonical scalar"
+            p.evaluations[k] = v
+        return p
+
 
 class Prover:
     def __init__(self, ctx, keypair, prover_key, verifier_key, transcript, pi_indexes):

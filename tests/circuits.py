@@ -60,3 +60,44 @@ def arithmetic_chain(m_target, seed=3):
         i += 1
     pub = cs.append_public(cs[x]) if cs.m() < m_target else None
     return cs
+
+
+def boolean_select_circuit(bit=1, a=11, b=22):
+    """tests/boolean.rs: component_boolean + the select family."""
+    cs = Plonk.initialize()
+    wbit = cs.append_witness(bit)
+    cs.component_boolean(wbit)
+    wa, wb = cs.append_witness(a), cs.append_witness(b)
+    x = cs.component_select(wbit, wa, wb)
+    cs.assert_equal_constant(x, a if bit else b, None)
+    z0 = cs.component_select_zero(wbit, wa)
+    cs.assert_equal_constant(z0, a if bit else 0, None)
+    o1 = cs.component_select_one(wbit, wa)
+    cs.assert_equal_constant(o1, a if bit else 1, None)
+    p1 = cs.append_point(jubjub_mul(JUBJUB_GENERATOR, 5))
+    p2 = cs.append_point(jubjub_mul(JUBJUB_GENERATOR, 9))
+    sp = cs.component_select_point(wbit, p1, p2)
+    cs.assert_equal_public_point(sp, jubjub_mul(JUBJUB_GENERATOR, 5 if bit else 9))
+    si = cs.component_select_identity(wbit, p1)
+    cs.assert_equal_public_point(si, jubjub_mul(JUBJUB_GENERATOR, 5) if bit else (0, 1))
+    return cs
+
+
+def decomposition_circuit(a=23, n_bits=64):
+    """tests/decomposition.rs: bits of a, asserted against witnesses."""
+    cs = Plonk.initialize()
+    wa = cs.append_witness(a)
+    bits = cs.component_decomposition(wa, n_bits)
+    for i, w in enumerate(bits):
+        cs.assert_equal_constant(w, (a >> i) & 1, None)
+    return cs
+
+
+def mul_point_circuit(scalar=0x1234567890ABCDEF1234567, base_mult=7):
+    """tests/ecc.rs mul_point: variable-base scalar multiplication (decomposition + curve-add gates)."""
+    cs = Plonk.initialize()
+    ws = cs.append_witness(scalar)
+    pt = cs.append_point(jubjub_mul(JUBJUB_GENERATOR, base_mult))
+    res = cs.component_mul_point(ws, pt)
+    cs.assert_equal_public_point(res, jubjub_mul(JUBJUB_GENERATOR, base_mult * scalar))
+    return cs

@@ -119,6 +119,8 @@ CIRCUITS = {
     "logic_curve": circuits.logic_curve_circuit,
     "readme": circuits.readme_circuit,
     "chain": lambda: circuits.arithmetic_chain(1000),
+    "boolean_select": circuits.boolean_select_circuit,
+    "decomposition": circuits.decomposition_circuit,
 }
 
 
@@ -227,3 +229,27 @@ def test_prove_2p16_gates_bit_exact_vs_c_prover(ctx, cport):
     vk = dict(cp.vk)
     tr = z.Transcript.base(b"plonk", oplonk.vk_transcript_list(vk), circ.m)
     assert oplonk.verify(vk, circ.n, gproof, circ.pi_indexes, gpi, tr, oplonk.trapdoor_kzg_check(tau))
+
+
+def test_mul_point_circuit_bit_exact_vs_c_prover(ctx, cport):
+    """tests/ecc.rs mul_point: 2025 gates of boolean / arithmetic / curve-addition rows (n = 2^11)."""
+    from oracle import cprover
+    circ = SynthesizedCircuit.from_composer(circuits.mul_point_circuit())
+    rng = SplitMix64(8349)
+    tau = rng.fr()
+    pp = PlonkParams.setup_synthetic(ctx, 12, fr_to_mont1(tau))
+    prover = z.PlonkKey.compile_with_circuit(pp, b"demo", circ)
+    cp = cprover.CProver(circ, prover.keypair.srs.download(), b"demo", z.Transcript)
+    for nm in list(oplonk.SELECTORS) + ["s_sigma_%d" % i for i in (1, 2, 3, 4)]:
+        assert prover.verifier_key[nm] == cp.vk[nm], nm
+    bl = [rng.fr() for _ in range(11)]
+    cproof, cpi = cp.create_proof(bl, circ)
+    gproof, gpi = prover.create_proof(bl, circ)
+    assert gpi == cpi and len(gpi) == 2
+    for c in oplonk.Proof.COMM_NAMES:
+        assert getattr(gproof, c) == getattr(cproof, c), c
+    assert gproof.evaluations == cproof.evaluations
+    vk = dict(cp.vk)
+    tr = z.Transcript.base(b"demo", oplonk.vk_transcript_list(vk), circ.m)
+    assert oplonk.verify(vk, circ.n, gproof, circ.pi_indexes, gpi, tr, oplonk.trapdoor_kzg_check(tau))
+    assert z.Proof.from_bytes(gproof.to_bytes()) == gproof

@@ -58,11 +58,37 @@ def rows_violated(cs):
     return bad
 
 
-@pytest.mark.parametrize("name", ["range", "readme", "logic_curve", "chain"])
+@pytest.mark.parametrize("name", ["range", "readme", "logic_curve", "chain", "boolean_select", "decomposition",
+                                  "mul_point"])
 def test_widget_identities_vanish_on_honest_rows(name):
     cs = {"range": lambda: circuits.range_circuit((1 << 64) - 1), "readme": circuits.readme_circuit,
-          "logic_curve": circuits.logic_curve_circuit, "chain": lambda: circuits.arithmetic_chain(64)}[name]()
+          "logic_curve": circuits.logic_curve_circuit, "chain": lambda: circuits.arithmetic_chain(64),
+          "boolean_select": circuits.boolean_select_circuit, "decomposition": circuits.decomposition_circuit,
+          "mul_point": circuits.mul_point_circuit}[name]()
     assert rows_violated(cs) == []
+
+
+def test_gadget_gate_counts_match_reference_docs():
+    """component_decomposition consumes 2 N + 1 gates (src/lib.rs:879); boolean is one gate."""
+    base = circuits.range_circuit(1, 8).m() - 2 - 1      # initialize() alone: range(8 bits) adds 2 + assert 1
+    assert base == 6
+    assert circuits.decomposition_circuit(23, 64).m() == 6 + (2 * 64 + 1) + 64
+
+
+def test_proof_wire_format_roundtrip():
+    from dusk_plonk_b200.prover import Proof, COMM_NAMES
+    circ, tau, commit, pk, vk, tr, bl = setup(circuits.range_circuit(12345))
+    op, _ = plonk.create_proof(pk, circ, commit, tr, bl)
+    p = Proof()
+    for c in COMM_NAMES:
+        setattr(p, c, getattr(op, c))
+    p.evaluations = dict(op.evaluations)
+    raw = p.to_bytes()
+    assert len(raw) == 11 * 48 + 16 * 32
+    q = Proof.from_bytes(raw)
+    assert q == p and q.to_bytes() == raw
+    ident = Proof.from_bytes(bytes([0xC0]) + bytes(47) + raw[48:])
+    assert ident.a_comm is None
 
 
 def test_widget_identities_catch_bad_witness():
@@ -81,10 +107,11 @@ def setup(cs, label=b"demo", seed=8349):
     return circ, tau, commit, pk, vk, tr, bl
 
 
-@pytest.mark.parametrize("name", ["range", "logic_curve", "readme"])
+@pytest.mark.parametrize("name", ["range", "logic_curve", "readme", "boolean_select", "decomposition"])
 def test_prove_and_verify(name):
     cs = {"range": lambda: circuits.range_circuit((1 << 64) - 1), "readme": circuits.readme_circuit,
-          "logic_curve": circuits.logic_curve_circuit}[name]()
+          "logic_curve": circuits.logic_curve_circuit, "boolean_select": circuits.boolean_select_circuit,
+          "decomposition": circuits.decomposition_circuit}[name]()
     circ, tau, commit, pk, vk, tr, bl = setup(cs)
     proof, pi = plonk.create_proof(pk, circ, commit, tr, bl)
     assert plonk.verify(vk, pk.n, proof, circ.pi_indexes, pi, tr, plonk.trapdoor_kzg_check(tau))
