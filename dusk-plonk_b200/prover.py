@@ -75,19 +75,26 @@ class Prover:
         if self._ws is None:
             n, c = self.size, self.ctx
             # the seven polynomials that go to the 8n coset live side by side (stride S) so their
-            # transforms run as batched launches: a, b, c, d, z, PI, L1
+            # transforms run as batched launches: a, b, c, d, PI (known after round 1) | z, L1
             S = n + 8
             P7, E7 = c.alloc(7 * S), c.alloc(7 * 8 * n)
             P7.zero()
             ws = {"W": c.alloc(4 * n), "Z": c.alloc(n), "P7": P7, "E7": E7, "S": S,
-                  "wp": [_View(P7, j * S, n + 2) for j in range(4)], "zp": _View(P7, 4 * S, n + 3),
-                  "PI": _View(P7, 5 * S, n), "L1": _View(P7, 6 * S, n),
-                  "e8": [_View(E7, j * 8 * n, 8 * n) for j in range(4)], "z8": _View(E7, 4 * 8 * n, 8 * n),
-                  "pi8": _View(E7, 5 * 8 * n, 8 * n), "l18": _View(E7, 6 * 8 * n, 8 * n),
+                  "wp": [_View(P7, j * S, n + 2) for j in range(4)], "PI": _View(P7, 4 * S, n),
+                  "zp": _View(P7, 5 * S, n + 3), "L1": _View(P7, 6 * S, n),
+                  "e8": [_View(E7, j * 8 * n, 8 * n) for j in range(4)], "pi8": _View(E7, 4 * 8 * n, 8 * n),
+                  "z8": _View(E7, 5 * 8 * n, 8 * n), "l18": _View(E7, 6 * 8 * n, 8 * n),
                   "T": c.alloc(8 * n), "R": c.alloc(n + 3),
                   "AGG": c.alloc(5 * n), "WZ": c.alloc(5 * n), "SAGG": c.alloc(n + 3), "WZW": c.alloc(n + 3)}
             self._ws = ws
         return self._ws
+
+    def _side_context(self):
+        """Second stream on the same device for work that does not depend on the transcript."""
+        if getattr(self, "_side", None) is None:
+            from .ffi import Context
+            self._side = Context(self.ctx.device)
+        return self._side
 
     def _commit(self, buf, off=0, n=None):
         return self.keypair.commit(_View(buf, off, n)).affine()
@@ -121,6 +128,20 @@ class Prover:
         ctx.ntt_dev_batch(W, n, n, ws["P7"], ws["S"], k, True, False, 4)     # 4 wire iNTTs, one launch set
         for j in range(4):
             ctx.poly_blind(ws["wp"][j], 0, n, bl[2 * j:2 * j + 2])
+        # The 8n-coset evaluations of a, b, c, d and PI depend on nothing the transcript still has to
+        # produce: run them on a second stream while the wire commitments (whose bucket-reduction tail
+        # leaves most of the GPU idle) are computed.  (reference order: src/prover.rs:229,
+        # quotient_poly.rs:54-58,145 -- same values, earlier.)
+        PI = ws["PI"]
+        if wa.pi_dev is not None:
+            ctx.ntt_dev(wa.pi_dev, n, PI, k, True, False)
+        else:
+            PI.upload(wa.dense_pi_mont)
+            ctx.ntt_dev(PI, n, PI, k, True, False)
+        k8, n8 = k + 3, 8 * n
+        side = self._side_context()
+        ctx.sync()
+        side.ntt_dev_batch(ws["P7"], ws["S"], n + 3, ws["E7"], n8, k8, False, True, 5)
         comms = [c.affine() for c in self.keypair.commit_batch([ws["wp"][j] for j in range(4)])]
         proof.a_comm, proof.b_comm, proof.c_comm, proof.d_comm = comms
         for lab, c in zip((b"a_w", b"b_w", b"c_w", b"d_w"), comms):
@@ -144,17 +165,12 @@ class Prover:
         fs = tr.challenge_scalar(b"fixed base separation challenge")
         vs = tr.challenge_scalar(b"variable base separation challenge")
         ch7 = (alpha, beta, gamma, rs, ls, fs, vs)
-        PI = ws["PI"]
-        if wa.pi_dev is not None:
-            ctx.ntt_dev(wa.pi_dev, n, PI, k, True, False)
-        else:
-            PI.upload(wa.dense_pi_mont)
-            ctx.ntt_dev(PI, n, PI, k, True, False)
-        k8, n8 = k + 3, 8 * n
         # L1 * alpha^2: idft of (alpha^2, 0, ..) has every coefficient alpha^2 / n (quotient_poly.rs:264-272)
         ctx.fill(ws["L1"], 0, n, fr_to_mont1(alpha * alpha % _r * pow(n, -1, _r) % _r))
-        # a, b, c, d, z, PI, L1 -> 8n coset in one batched launch set (slots beyond each length are zero)
-        ctx.ntt_dev_batch(ws["P7"], ws["S"], n + 3, ws["E7"], n8, k8, False, True, 7)
+        # z and L1 -> 8n coset (a, b, c, d, PI were transformed on the side stream during round 1)
+        ctx.ntt_dev(ws["zp"], n + 3, ws["z8"], k8, False, True)
+        ctx.ntt_dev(ws["L1"], n, ws["l18"], k8, False, True)
+        side.sync()
         qa = QuotientArgs()
         for j in range(4):
             qa.wires[j] = ref(ws["e8"][j], 0, n8)
@@ -213,13 +229,16 @@ class Prover:
         sc = [1, z_n, z_n * z_n % _r, pow(z_n, 3, _r)] + vp[1:]
         ctx.poly_lincomb(refs, fr_to_mont(sc), ws["AGG"], 0, 5 * n)
         ctx.poly_div_linear(ref(ws["AGG"], 0, 5 * n), fr_to_mont1(zc), ws["WZ"])
-        proof.w_z_chall_comm = self._commit(ws["WZ"], 0, 5 * n - 1)
+        # The second v_challenge follows the first with no transcript append in between
+        # (src/prover.rs:435-450: the opening commitments are never appended by the prover), so both
+        # witnesses can be built first and committed as one batch of two.
         v2 = tr.challenge_scalar(b"v_challenge")
         refs = [ref(ws["zp"], 0, n + 3), ref(ws["wp"][0], 0, n + 2), ref(ws["wp"][1], 0, n + 2),
                 ref(ws["wp"][3], 0, n + 2)]
         ctx.poly_lincomb(refs, fr_to_mont([pow(v2, i, _r) for i in range(4)]), ws["SAGG"], 0, n + 3)
         ctx.poly_div_linear(ref(ws["SAGG"], 0, n + 3), fr_to_mont1(zw), ws["WZW"])
-        proof.w_z_chall_w_comm = self._commit(ws["WZW"], 0, n + 2)
+        wc = self.keypair.commit_batch([_View(ws["WZ"], 0, 5 * n - 1), _View(ws["WZW"], 0, n + 2)])
+        proof.w_z_chall_comm, proof.w_z_chall_w_comm = wc[0].affine(), wc[1].affine()
         proof.evaluations = {nm: ev[nm] for nm in EVAL_NAMES}
         if T is not None:
             T.update({"challenges": ch7, "z_challenge": zc, "t_eval": t_eval, "workspace": ws})
