@@ -97,12 +97,13 @@ struct PermArgs {
 __global__ void __launch_bounds__(128) perm_numden_kernel(PermArgs a) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    const fr_t root = pld(a.roots + i);
+    const fr_t br = a.beta * pld(a.roots + i);  // beta w^i; beta K_j w^i by additions (K = 1, 7, 13, 17)
+    const fr_t bkr[4] = {br, mul_small<7>(br), mul_small<13>(br), mul_small<17>(br)};
     fr_t nu, de;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const fr_t w = pld(a.w[j] + i) + a.gamma;
-        const fr_t f = w + a.bk[j] * root;
+        const fr_t f = w + bkr[j];
         const fr_t g = w + a.beta * pld(a.sigma[j] + i);
         nu = j ? nu * f : f;
         de = j ? de * g : g;
@@ -300,7 +301,9 @@ __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ Q
     {
         const fr_t z = pld(q.z + i), zn = pld(q.z + in), x = pld(q.linear + i);
         const fr_t ag = a + q.gamma, bg = b + q.gamma, cg = c + q.gamma, dg = d + q.gamma;
-        fr_t ident = (ag + q.beta * x) * (bg + q.bk1 * x) * ((cg + q.bk2 * x) * (dg + q.bk3 * x)) * z;
+        // beta K_j x = K_j (beta x) with K = 7, 13, 17 (src/permutation.rs:28-30): additions, not multiplications
+        const fr_t bx = q.beta * x;
+        fr_t ident = (ag + bx) * (bg + mul_small<7>(bx)) * ((cg + mul_small<13>(bx)) * (dg + mul_small<17>(bx))) * z;
         fr_t copy = (ag + q.beta * pld(q.sigma[0] + i)) * (bg + q.beta * pld(q.sigma[1] + i)) *
                     ((cg + q.beta * pld(q.sigma[2] + i)) * (dg + q.beta * pld(q.sigma[3] + i))) * zn;
         t = t + (ident - copy) * q.alpha + (z - one) * pld(q.l1 + i);
@@ -404,11 +407,21 @@ __global__ void div_chunk_kernel(const fr_t* c, size_t n, fr_t point, fr_t* chun
     pst(chunk + t, s);
 }
 
-// single block: chunk[t] <- sum_{t' > t} chunk[t'] X^(t'-t-1), X = point^DV_L  (carry into chunk t)
-__global__ void __launch_bounds__(512) div_carry_kernel(fr_t* chunk, size_t nc, fr_t X) {
+// Block b owns the chunks [b * tile, (b + 1) * tile) (the whole array when tile >= nc):
+// chunk[t] <- sum_{t' > t, t' in the tile} chunk[t'] X^(t'-t-1)   (carry into chunk t from inside its tile)
+// tile_val[b] <- value of the whole tile relative to its lowest chunk (if tile_val != nullptr).
+// Two levels (tiles, then the same kernel over tile_val with X^tile) keep every block short.
+static constexpr size_t DV_TILE = 2048;
+
+__global__ void __launch_bounds__(512) div_carry_kernel(fr_t* chunk, size_t nc_all, size_t tile, fr_t X,
+                                                       fr_t* tile_val) {
     __shared__ fr_t sm[512];
     __shared__ fr_t xp[512];
     const unsigned T = blockDim.x, tid = threadIdx.x;
+    const size_t base = (size_t)blockIdx.x * tile;
+    if (base >= nc_all) return;
+    const size_t nc = nc_all - base < tile ? nc_all - base : tile;
+    chunk += base;
     const size_t per = (nc + T - 1) / T;
     // reversed logical order: j = 0 is the top chunk
     const size_t lo = (size_t)tid * per, hi = lo + per < nc ? lo + per : nc;
@@ -434,14 +447,22 @@ __global__ void __launch_bounds__(512) div_carry_kernel(fr_t* chunk, size_t nc, 
         pst(chunk + idx, run);
         run = run * X + cv;
     }
+    if (tile_val && lo < hi && hi == nc) pst(tile_val + blockIdx.x, run);
 }
 
-__global__ void div_apply_kernel(const fr_t* c, size_t n, fr_t point, const fr_t* carry, fr_t* out) {
+// carry: in-tile carries; tile_carry (may be null): carry into each tile from the tiles above.
+__global__ void div_apply_kernel(const fr_t* c, size_t n, fr_t point, const fr_t* carry, const fr_t* tile_carry,
+                                 size_t nc, fr_t X, fr_t* out) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t lo = t * DV_L;
     if (lo >= n) return;
     size_t hi = lo + DV_L < n ? lo + DV_L : n;
-    fr_t h = pld(carry + t);  // h_{hi}
+    fr_t h = pld(carry + t);  // h_{hi} from inside the tile
+    if (tile_carry) {
+        const size_t b = t / DV_TILE;
+        const size_t tile_end = (b + 1) * DV_TILE < nc ? (b + 1) * DV_TILE : nc;
+        h = h + pld(tile_carry + b) * pow_u64(X, (uint64_t)(tile_end - 1 - t));
+    }
     for (size_t i = hi; i-- > lo;) {
         if (i + 1 < n) pst(out + i, h);  // q_i = h_{i+1}
         h = h * point + pld(c + i);
@@ -689,7 +710,7 @@ int zkp_poly_div_linear_dev(zkp_ctx* ctx, zkp_poly_ref in, const uint64_t point[
     if (n == 1) return ZKP_OK;
     const size_t nc = (n + DV_L - 1) / DV_L;
     fr_t* s;
-    if ((rc = scratch(ctx, nc, &s))) return rc;
+    if ((rc = scratch(ctx, nc + (nc + DV_TILE - 1) / DV_TILE, &s))) return rc;
     const fr_t pt = fr_from_host(point);
     const fr_t X = pow_u64(pt, DV_L);
     const fr_t* c = in.buf->d + in.off;
@@ -697,10 +718,21 @@ int zkp_poly_div_linear_dev(zkp_ctx* ctx, zkp_poly_ref in, const uint64_t point[
     ProfScope prof(ctx, "poly_div");
     div_chunk_kernel<<<blocks_for(nc, 128), 128, 0, st>>>(c, n, pt, s);
     ZKP_LAUNCHED(ctx);
-    div_carry_kernel<<<1, 512, 0, st>>>(s, nc, X);
-    ZKP_LAUNCHED(ctx);
-    div_apply_kernel<<<blocks_for(nc, 128), 128, 0, st>>>(c, n, pt, s, out->d + out_off);
-    ZKP_LAUNCHED(ctx);
+    if (nc <= DV_TILE) {
+        div_carry_kernel<<<1, 512, 0, st>>>(s, nc, nc, X, nullptr);
+        ZKP_LAUNCHED(ctx);
+        div_apply_kernel<<<blocks_for(nc, 128), 128, 0, st>>>(c, n, pt, s, nullptr, nc, X, out->d + out_off);
+        ZKP_LAUNCHED(ctx);
+    } else {
+        const size_t ntiles = (nc + DV_TILE - 1) / DV_TILE;
+        fr_t* tv = s + nc;
+        div_carry_kernel<<<(unsigned)ntiles, 512, 0, st>>>(s, nc, DV_TILE, X, tv);
+        ZKP_LAUNCHED(ctx);
+        div_carry_kernel<<<1, 512, 0, st>>>(tv, ntiles, ntiles, pow_u64(X, DV_TILE), nullptr);
+        ZKP_LAUNCHED(ctx);
+        div_apply_kernel<<<blocks_for(nc, 128), 128, 0, st>>>(c, n, pt, s, tv, nc, X, out->d + out_off);
+        ZKP_LAUNCHED(ctx);
+    }
     return ZKP_OK;
 }
 

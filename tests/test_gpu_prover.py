@@ -45,7 +45,7 @@ def test_poly_eval_large_and_offsets(ctx):
     assert got == [poly_eval(p, pt), poly_eval(p[100:5100], pt), p[-1]]
 
 
-@pytest.mark.parametrize("n", [2, 3, 16, 17, 33, 1000, 16385])
+@pytest.mark.parametrize("n", [2, 3, 16, 17, 33, 1000, 16385, 32768 + 5, 100003])
 def test_div_linear_is_ruffini(ctx, n):
     p = rand_vec(n, n)
     pt = rand_vec(n + 1, 1)[0]
