@@ -56,6 +56,7 @@ struct MsmScratch {
     long long* top = nullptr;
     int acc_blocks_per_sm = 0;
     int acc_variant = 3;
+    bool acc_variant_forced = false;
     int acc_blocks_per_sm2 = 0;   // occupancy of the 2-blocks/SM build used for small jobs
 };
 
@@ -598,7 +599,10 @@ static int msm_scratch(zkp_ctx* ctx, MsmScratch** out) {
         ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->meta, 4 * MSM_MAX_BATCH * sizeof(uint32_t)));
         ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->tile_sums, 1024 * MSM_MAX_BATCH * sizeof(uint32_t)));
         int mb = 3;  // measured best on B200 (2^22: 22.3 / 21.8 / 23.1 / 23.7 / 24.4 ms for 2..6)
-        if (const char* e = getenv("ZKP_MSM_BLOCKS_PER_SM")) mb = atoi(e);  // tuning knob: 2..6
+        if (const char* e = getenv("ZKP_MSM_BLOCKS_PER_SM")) {  // tuning knob: 2..6, applies to every job size
+            mb = atoi(e);
+            ctx->msm->acc_variant_forced = true;
+        }
         if (mb < 2) mb = 2;
         if (mb > 6) mb = 6;
         ctx->msm->acc_variant = mb;
@@ -688,7 +692,7 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     // chunk length: one wave of resident threads when the job is small, 128-entry chunks (many
     // waves, negligible tail) when it is large
     // small jobs (about one wave) run best with the unconstrained 2-blocks/SM build, large ones with 3
-    const int variant = (getenv("ZKP_MSM_BLOCKS_PER_SM") || E * nb >= ((size_t)1 << 23)) ? s->acc_variant : 2;
+    const int variant = (s->acc_variant_forced || E * nb >= ((size_t)1 << 23)) ? s->acc_variant : 2;
     const size_t resident =
         (size_t)ctx->sm_count * (variant == 2 ? s->acc_blocks_per_sm2 : s->acc_blocks_per_sm) * 128;
     size_t L = (E * nb + resident - 1) / resident;

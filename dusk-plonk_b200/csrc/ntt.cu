@@ -449,7 +449,8 @@ int ntt_permute(zkp_ctx* ctx, const fr_t* in, fr_t* out, size_t A, size_t B, siz
     } else {
         const size_t total = A * B * w;
         size_t blocks = (total + 255) / 256;
-        if (blocks > 148 * 64) blocks = 148 * 64;
+        const size_t cap = (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 64;
+        if (blocks > cap) blocks = cap;
         permute_blocks_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, out, A, B, w);
     }
     ZKP_LAUNCHED(ctx);

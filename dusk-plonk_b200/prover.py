@@ -96,6 +96,13 @@ class Prover:
             self._side = Context(self.ctx.device)
         return self._side
 
+    def close(self):
+        """Release the workspace and the side stream (the proving key stays with its buffers)."""
+        if getattr(self, "_side", None) is not None:
+            self._side.close()
+            self._side = None
+        self._ws = None
+
     def _commit(self, buf, off=0, n=None):
         return self.keypair.commit(_View(buf, off, n)).affine()
 
