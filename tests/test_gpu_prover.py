@@ -253,3 +253,38 @@ def test_mul_point_circuit_bit_exact_vs_c_prover(ctx, cport):
     tr = z.Transcript.base(b"demo", oplonk.vk_transcript_list(vk), circ.m)
     assert oplonk.verify(vk, circ.n, gproof, circ.pi_indexes, gpi, tr, oplonk.trapdoor_kzg_check(tau))
     assert z.Proof.from_bytes(gproof.to_bytes()) == gproof
+
+
+@pytest.mark.parametrize("name", ["logic", "boolean", "decomposition_bit", "public_input"])
+def test_negative_cases_of_the_reference_suites(ctx, name):
+    """tests/logic.rs:109-111, tests/boolean.rs:90, tests/decomposition.rs:101-103: a prover compiled for the
+    honest circuit errs on an unsatisfying witness of the same shape; a wrong public input makes the
+    verifier reject."""
+    if name == "logic":
+        good, bad = circuits.logic_curve_circuit(), circuits.logic_curve_circuit(bad=True)
+    elif name == "boolean":
+        good, bad = circuits.boolean_select_circuit(bit=1), circuits.boolean_select_circuit(bit=2)
+    elif name == "decomposition_bit":
+        good = circuits.decomposition_circuit(23, 64)
+        bad = circuits.decomposition_circuit(23, 64)
+        # corrupt one bit witness after synthesis: same gates, unsatisfied boolean + sum rows
+        bit_w = bad.constraints[6].w_a
+        bad.witness[bit_w] = 2
+    else:
+        good = bad = circuits.range_circuit(99)
+    circ, tau, prover, commit, opk, ovk, otr, bl = both_sides(ctx, good)
+    if name == "public_input":
+        good2 = circuits.readme_circuit()
+        circ, tau, prover, commit, opk, ovk, otr, bl = both_sides(ctx, good2)
+        proof, pi = prover.create_proof(bl, circ)
+        assert oplonk.verify(ovk, circ.n, proof, circ.pi_indexes, pi, otr, oplonk.trapdoor_kzg_check(tau))
+        wrong = [(pi[0] + 1) % R_MOD] + pi[1:]
+        with pytest.raises(oplonk.VerifyError):
+            oplonk.verify(ovk, circ.n, proof, circ.pi_indexes, wrong, otr, oplonk.trapdoor_kzg_check(tau))
+        return
+    badc = SynthesizedCircuit.from_composer(bad)
+    assert badc.m == circ.m
+    with pytest.raises(Error):
+        prover.create_proof(bl, badc)
+    with pytest.raises(oplonk.ProverError):
+        oplonk.create_proof(opk, badc, commit, otr, bl)
