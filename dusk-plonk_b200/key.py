@@ -72,8 +72,20 @@ class PlonkKey:
             buf = ctx.upload(fr_column_to_mont(col, n))
             ctx.ntt_dev(buf, n, buf, k, True, False)
             pk.poly[s] = buf
-            vk[s] = keypair.commit_or_default(buf).affine()
-            if vk[s] is not None and s in ("q_range", "q_logic", "q_fixed_group_add", "q_variable_group_add"):
+        # the 11 selector commitments as two batched launch sets; a selector polynomial has n
+        # coefficients and the trimmed SRS at least n + 7 powers, so `.unwrap_or_default()`
+        # (src/key.rs:138-154) can only ever see Ok here
+        names = list(SELECTORS)
+        for lo in range(0, len(names), 8):
+            grp = names[lo:lo + 8]
+            try:
+                comms = keypair.commit_batch([pk.poly[s] for s in grp])
+            except Error:   # SRS shorter than the circuit: keep the reference's per-selector default
+                comms = [keypair.commit_or_default(pk.poly[s]) for s in grp]
+            for s, c in zip(grp, comms):
+                vk[s] = c.affine()
+        for s in ("q_range", "q_logic", "q_fixed_group_add", "q_variable_group_add"):
+            if vk[s] is not None:
                 pk.widget_mask |= 1 << ("q_range", "q_logic", "q_fixed_group_add", "q_variable_group_add").index(s)
         # sigma polynomials (src/permutation.rs:172-200, src/key.rs:134-159)
         for i, nm in enumerate(SIGMAS):
@@ -85,7 +97,8 @@ class PlonkKey:
             buf = ctx.alloc(n)
             ctx.ntt_dev(ev, n, buf, k, True, False)
             pk.poly[nm] = buf
-            vk[nm] = keypair.commit(buf).affine()                  # `?` in the reference
+        for nm, c in zip(SIGMAS, keypair.commit_batch([pk.poly[nm] for nm in SIGMAS])):   # `?` in the reference
+            vk[nm] = c.affine()
         for nm, p in pk.poly.items():
             e8 = ctx.alloc(n8)
             ctx.ntt_dev(p, n, e8, k + 3, False, True)
