@@ -24,8 +24,15 @@ for logn in [int(a) for a in sys.argv[1:]] or [16]:
     ctx.sync()
     t2 = time.perf_counter()
     l0 = ctx.launches
+    import cProfile, pstats, io
+    pr = cProfile.Profile()
+    pr.enable()
     prover = z.PlonkKey.compile(pp, circ)
     ctx.sync()
+    pr.disable()
     t3 = time.perf_counter()
+    sio = io.StringIO()
+    pstats.Stats(pr, stream=sio).sort_stats("tottime").print_stats(10)
+    sys.stderr.write(sio.getvalue())
     print(json.dumps({"log2_gates": logn, "srs_setup_ms": (t1 - t0) * 1e3, "compile_first_ms": (t2 - t1) * 1e3,
                       "compile_ms": (t3 - t2) * 1e3, "gpu_launches": ctx.launches - l0}), flush=True)

@@ -233,6 +233,7 @@ struct QuotArgs {
     fr_t zh_inv[8];
     uint32_t mask;
     size_t n8;
+    size_t first, count;  // evaluate indices [first, first + count) (a rank's slice when sharded)
     fr_t* out;
 };
 
@@ -241,8 +242,9 @@ __device__ __forceinline__ fr_t delta4(const fr_t& f, const fr_t& one, const fr_
 }
 
 __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ QuotArgs q) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= q.n8) return;
+    const size_t t_ = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t_ >= q.count) return;
+    const size_t i = q.first + t_;
     const size_t in = (i + 8) & (q.n8 - 1);  // "next gate" on the 8n coset (quotient_poly.rs:60-66)
     const fr_t one = fr_t::one(), two = dbl(one), three = two + one;
     const fr_t a = pld(q.w[0] + i), b = pld(q.w[1] + i), c = pld(q.w[2] + i), d = pld(q.w[3] + i);
@@ -606,9 +608,15 @@ int zkp_perm_z_dev(zkp_ctx* ctx, size_t n, const zkp_poly_ref wires[4], const zk
 }
 
 int zkp_quotient_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* q, zkp_buf* out, size_t out_off) {
+    if (k8 > 28) return ZKP_ERR_INVALID;
+    return zkp_quotient_range_dev(ctx, k8, q, 0, (size_t)1 << k8, out, out_off);
+}
+
+int zkp_quotient_range_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* q, size_t first, size_t count,
+                           zkp_buf* out, size_t out_off) {
     if (!ctx || !q || !out || k8 < 3 || k8 > 28) return ZKP_ERR_INVALID;
     const size_t n8 = (size_t)1 << k8;
-    if (out_off + n8 > out->n) return ZKP_ERR_INVALID;
+    if (out_off + n8 > out->n || first + count > n8) return ZKP_ERR_INVALID;
     QuotArgs a;
     auto ptr = [&](const zkp_poly_ref& r, const fr_t** p) {
         if (!CHECK_REF(r) || r.len < n8) return false;
@@ -637,9 +645,12 @@ int zkp_quotient_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* q, zkp_
     for (int j = 0; j < 8; j++) a.zh_inv[j] = fr_from_host(q->zh_inv[j]);
     a.mask = q->widget_mask;
     a.n8 = n8;
+    a.first = first;
+    a.count = count;
     a.out = out->d + out_off;
+    if (count == 0) return ZKP_OK;
     ProfScope prof(ctx, "quotient");
-    quotient_kernel<<<blocks_for(n8, 128), 128, 0, ctx->stream>>>(a);
+    quotient_kernel<<<blocks_for(count, 128), 128, 0, ctx->stream>>>(a);
     ZKP_LAUNCHED(ctx);
     return ZKP_OK;
 }

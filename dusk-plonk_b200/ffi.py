@@ -94,6 +94,7 @@ SIGNATURES.update({
     "zkp_perm_lagrange_dev": (_int, [_vp, _uint, _vp, _sz, _vp, _vp, _sz]),
     "zkp_perm_z_dev": (_int, [_vp, _sz, ctypes.POINTER(PolyRef), ctypes.POINTER(PolyRef), _vp, _vp, _vp, _vp, _sz]),
     "zkp_quotient_dev": (_int, [_vp, _uint, ctypes.POINTER(QuotientArgs), _vp, _sz]),
+    "zkp_quotient_range_dev": (_int, [_vp, _uint, ctypes.POINTER(QuotientArgs), _sz, _sz, _vp, _sz]),
     "zkp_poly_eval_dev": (_int, [_vp, ctypes.POINTER(PolyRef), _uint, _vp, _vp]),
     "zkp_poly_lincomb_dev": (_int, [_vp, ctypes.POINTER(PolyRef), _vp, _uint, _vp, _sz, _sz]),
     "zkp_poly_div_linear_dev": (_int, [_vp, PolyRef, _vp, _vp, _sz]),
@@ -337,8 +338,11 @@ class Context:
         g = np.ascontiguousarray(gamma, dtype=np.uint64).reshape(4)
         self.check(self.lib.zkp_perm_z_dev(self.h, n, w, s, roots.h, _ptr(b), _ptr(g), out.h, out_off))
 
-    def quotient(self, k8, args, out, out_off=0):
-        self.check(self.lib.zkp_quotient_dev(self.h, k8, ctypes.byref(args), out.h, out_off))
+    def quotient(self, k8, args, out, out_off=0, first=None, count=None):
+        if first is None:
+            self.check(self.lib.zkp_quotient_dev(self.h, k8, ctypes.byref(args), out.h, out_off))
+        else:
+            self.check(self.lib.zkp_quotient_range_dev(self.h, k8, ctypes.byref(args), first, count, out.h, out_off))
 
     def poly_eval(self, refs, point):
         arr = (PolyRef * len(refs))(*refs)

@@ -77,17 +77,37 @@ class Prover:
             # the seven polynomials that go to the 8n coset live side by side (stride S) so their
             # transforms run as batched launches: a, b, c, d, PI (known after round 1) | z, L1
             S = n + 8
-            P7, E7 = c.alloc(7 * S), c.alloc(7 * 8 * n)
+            P7 = c.alloc(7 * S)
             P7.zero()
+            comm = self._comm()
+            if comm is not None:
+                # sharded proof: the buffers NCCL gathers into are torch tensors the kernels address too;
+                # E7 is padded to a whole number of rounds of `world` polynomials
+                torch = comm.torch
+                G = comm.world
+                slots = -(-7 // G) * G
+                dev = torch.device("cuda", c.device)
+                self._t_E7 = torch.empty(slots * 8 * n * 4, dtype=torch.int64, device=dev)
+                self._t_T = torch.empty(8 * n * 4, dtype=torch.int64, device=dev)
+                self._t_stage = torch.empty(8 * n * 4, dtype=torch.int64, device=dev)
+                E7 = c.wrap(self._t_E7.data_ptr(), slots * 8 * n)
+                Tbuf = c.wrap(self._t_T.data_ptr(), 8 * n)
+            else:
+                E7, Tbuf = c.alloc(7 * 8 * n), c.alloc(8 * n)
             ws = {"W": c.alloc(4 * n), "Z": c.alloc(n), "P7": P7, "E7": E7, "S": S,
                   "wp": [_View(P7, j * S, n + 2) for j in range(4)], "PI": _View(P7, 4 * S, n),
                   "zp": _View(P7, 5 * S, n + 3), "L1": _View(P7, 6 * S, n),
                   "e8": [_View(E7, j * 8 * n, 8 * n) for j in range(4)], "pi8": _View(E7, 4 * 8 * n, 8 * n),
                   "z8": _View(E7, 5 * 8 * n, 8 * n), "l18": _View(E7, 6 * 8 * n, 8 * n),
-                  "T": c.alloc(8 * n), "R": c.alloc(n + 3),
+                  "T": Tbuf, "R": c.alloc(n + 3),
                   "AGG": c.alloc(5 * n), "WZ": c.alloc(5 * n), "SAGG": c.alloc(n + 3), "WZW": c.alloc(n + 3)}
             self._ws = ws
         return self._ws
+
+    def _comm(self):
+        """The communicator when the commit key is sharded over several GPUs, else None."""
+        comm = getattr(self.keypair, "comm", None)
+        return comm if comm is not None and getattr(comm, "world", 1) > 1 and hasattr(comm, "dist") else None
 
     def _side_context(self):
         """Second stream on the same device for work that does not depend on the transcript."""
@@ -146,9 +166,12 @@ class Prover:
             PI.upload(wa.dense_pi_mont)
             ctx.ntt_dev(PI, n, PI, k, True, False)
         k8, n8 = k + 3, 8 * n
-        side = self._side_context()
-        ctx.sync()
-        side.ntt_dev_batch(ws["P7"], ws["S"], n + 3, ws["E7"], n8, k8, False, True, 5)
+        comm = self._comm()
+        side = None
+        if comm is None:
+            side = self._side_context()
+            ctx.sync()
+            side.ntt_dev_batch(ws["P7"], ws["S"], n + 3, ws["E7"], n8, k8, False, True, 5)
         comms = [c.affine() for c in self.keypair.commit_batch([ws["wp"][j] for j in range(4)])]
         proof.a_comm, proof.b_comm, proof.c_comm, proof.d_comm = comms
         for lab, c in zip((b"a_w", b"b_w", b"c_w", b"d_w"), comms):
@@ -174,10 +197,22 @@ class Prover:
         ch7 = (alpha, beta, gamma, rs, ls, fs, vs)
         # L1 * alpha^2: idft of (alpha^2, 0, ..) has every coefficient alpha^2 / n (quotient_poly.rs:264-272)
         ctx.fill(ws["L1"], 0, n, fr_to_mont1(alpha * alpha % _r * pow(n, -1, _r) % _r))
-        # z and L1 -> 8n coset (a, b, c, d, PI were transformed on the side stream during round 1)
-        ctx.ntt_dev(ws["zp"], n + 3, ws["z8"], k8, False, True)
-        ctx.ntt_dev(ws["L1"], n, ws["l18"], k8, False, True)
-        side.sync()
+        if comm is None:
+            # z and L1 -> 8n coset (a, b, c, d, PI were transformed on the side stream during round 1)
+            ctx.ntt_dev(ws["zp"], n + 3, ws["z8"], k8, False, True)
+            ctx.ntt_dev(ws["L1"], n, ws["l18"], k8, False, True)
+            side.sync()
+        else:
+            # sharded proof: the seven coset transforms are dealt out one per GPU and all-gathered
+            # over NVLink (each is as large as the whole proving-key column it will meet)
+            G, rank = comm.world, comm.rank
+            for r0 in range(0, 7, G):
+                j = r0 + rank
+                if j < 7:
+                    ctx.ntt_dev(_View(ws["P7"], j * ws["S"], n + 3), n + 3, _View(ws["E7"], j * n8, n8), k8, False, True)
+                ctx.sync()
+                comm.all_gather_device(self._t_E7[r0 * n8 * 4:(r0 + G) * n8 * 4],
+                                       self._t_E7[(r0 + rank) * n8 * 4:(r0 + rank + 1) * n8 * 4], self._t_stage)
         qa = QuotientArgs()
         for j in range(4):
             qa.wires[j] = ref(ws["e8"][j], 0, n8)
@@ -195,7 +230,14 @@ class Prover:
                 qa.zh_inv[j][l] = int(pk.zh_inv[j, l])
         qa.widget_mask = pk.widget_mask
         Tb = ws["T"]
-        ctx.quotient(k8, qa, Tb)
+        if comm is None:
+            ctx.quotient(k8, qa, Tb)
+        else:
+            # each GPU evaluates its slice of the 8n points; slices are all-gathered
+            per = n8 // comm.world
+            ctx.quotient(k8, qa, Tb, 0, comm.rank * per, per)
+            ctx.sync()
+            comm.all_gather_device(self._t_T, self._t_T[comm.rank * per * 4:(comm.rank + 1) * per * 4], self._t_stage)
         ctx.ntt_dev(Tb, n8, Tb, k8, True, True)   # coset_idft -> t coefficients
         tc = [c.affine() for c in self.keypair.commit_batch(
             [_View(Tb, 0, n), _View(Tb, n, n), _View(Tb, 2 * n, n), _View(Tb, 3 * n, 5 * n)])]

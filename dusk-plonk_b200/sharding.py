@@ -17,8 +17,8 @@ from .poly_commit import Commitment
 
 
 class Communicator:
-    """All-gather of small fixed-size byte blobs over ``torch.distributed`` (NCCL on GPUs,
-    gloo in the CPU tests)."""
+    """All-gather over ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests): small byte blobs
+    (partial commitments) and device-resident slabs (coset evaluations, quotient slices)."""
 
     def __init__(self, device=None):
         import torch
@@ -33,6 +33,15 @@ class Communicator:
         self.dist.all_gather_into_tensor(out, t)
         raw = out.cpu().numpy().tobytes()
         return [raw[i * len(blob):(i + 1) * len(blob)] for i in range(self.world)]
+
+
+    def all_gather_device(self, out, mine, stage):
+        """``out`` (world equal chunks, device tensor) <- every rank's ``mine`` (which may be a view of
+        ``out``; it is staged through ``stage`` so the collective never aliases its input)."""
+        st = stage[:mine.numel()]
+        st.copy_(mine)
+        self.dist.all_gather_into_tensor(out, st)
+        self.torch.cuda.synchronize()
 
 
 class LocalCommunicator:

@@ -201,6 +201,10 @@ typedef struct zkp_quotient_args {
                                      polynomial identically zero, widget skipped (contributes 0) */
 } zkp_quotient_args;
 int zkp_quotient_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* args, zkp_buf* out, size_t out_off);
+/* Only the evaluations [first, first + count) of the same vector (out[i] for those i): one rank's
+ * slice when the 8n points are split over GPUs; inputs are full-length on every rank. */
+int zkp_quotient_range_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* args, size_t first, size_t count,
+                           zkp_buf* out, size_t out_off);
 
 /* Coefficients::evaluate for up to 16 polynomials at one point (linearization_poly.rs:52-73). */
 int zkp_poly_eval_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, unsigned count, const uint64_t point[4],

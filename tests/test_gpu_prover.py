@@ -261,7 +261,10 @@ def test_negative_cases_of_the_reference_suites(ctx, name):
     honest circuit errs on an unsatisfying witness of the same shape; a wrong public input makes the
     verifier reject."""
     if name == "logic":
-        good, bad = circuits.logic_curve_circuit(), circuits.logic_curve_circuit(bad=True)
+        good, bad = circuits.logic_curve_circuit(), circuits.logic_curve_circuit()
+        # same gates, wrong product quad in the first logic row (tests/logic.rs negative case)
+        row = next(c for c in bad.constraints if c.q_logic)
+        bad.witness[row.w_o] = (bad.witness[row.w_o] + 1) % R_MOD
     elif name == "boolean":
         good, bad = circuits.boolean_select_circuit(bit=1), circuits.boolean_select_circuit(bit=2)
     elif name == "decomposition_bit":
