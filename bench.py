@@ -421,14 +421,17 @@ def main():
                                        (msm_pts // args.steps)}
             extra = {"prove_ms": ms_step, "e2e_prove_ms": e2e_ms / args.steps, "kernel_groups": shares}
         elif args.workload == "msm":
-            achieved = MSM_IMAD_PER_POINT * n / (dom_avg_ms * 1e-3) / 1e12
+            # the roofline is per GPU: a sharded job's kernel on this rank sums n / world points
+            n_local = n // world if shard else n
+            achieved = MSM_IMAD_PER_POINT * n_local / (dom_avg_ms * 1e-3) / 1e12
             roofline = {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": imad_pk,
                         "unit": "T IMAD/s", "frac": achieved / imad_pk, "traffic": None, "peak_source": imad_src,
                         "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_avg_ms / ms_step,
                         "algorithmic": "48000 mul-adds per point (SURVEY 8d)"}
         else:
-            achieved = NTT_BYTES_PER_ELEM * n / (dom_avg_ms * 1e-3) / 1e9
-            imad = NTT_IMAD_PER_ELEM_PER_STAGE * n * args.logn / (dom_avg_ms * 1e-3) / 1e12
+            n_local = n // world if shard else n   # per-GPU roofline: this rank transforms n / world elements
+            achieved = NTT_BYTES_PER_ELEM * n_local / (dom_avg_ms * 1e-3) / 1e9
+            imad = NTT_IMAD_PER_ELEM_PER_STAGE * n_local * args.logn / (dom_avg_ms * 1e-3) / 1e12
             roofline = {"bound": "hbm", "kernel": "ntt_pass_kernel (all passes)", "achieved": achieved,
                         "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
                         "peak_source": hbm_src, "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_avg_ms / ms_step,

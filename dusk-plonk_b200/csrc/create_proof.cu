@@ -1,0 +1,667 @@
+// Native round driver: Prover::create_proof (src/prover.rs:67-474) behind one C-ABI call.
+//
+// The reference's prover is compiled host code that calls the NTT / commit primitives between
+// Fiat-Shamir transcript operations.  This file is that host side above the kernels: the five
+// rounds in the reference's order, the Merlin transcript (STROBE-128 over Keccak-f[1600]; labels
+// src/prover.rs:99-105,139-199,203-226,268-295,321-405,435-450), the scalar side of the
+// linearisation (src/prover/linearization_poly.rs:75-105,136-225) and the proof wire format
+// (src/prover/proof.rs:36-66).  Polynomials stay in HBM for the whole proof; per proof the host
+// sees 11 affine points and 17 field elements, and sends 8 challenges.
+//
+// Streams: the 8n-coset transforms of a, b, c, d, PI (and later z) depend on nothing the
+// transcript still has to produce, so they run on a second stream under the wire / z
+// commitments (whose bucket-reduction tail leaves most SMs idle); event dependencies only, no
+// host synchronisation beyond the reads the transcript needs.
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+struct zkp_prover {
+    zkp_ctx* ctx = nullptr;
+    zkp_ctx* side = nullptr;          // second stream on the same device
+    const zkp_srs* srs = nullptr;
+    zkp_proving_key key;
+    size_t n = 0, S = 0;
+    unsigned k = 0;
+    zkp_buf *W = nullptr, *Z = nullptr, *P7 = nullptr, *E7 = nullptr, *T = nullptr, *R = nullptr, *AGG = nullptr,
+            *WZ = nullptr, *SAGG = nullptr, *WZW = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+};
+
+namespace zkp {
+namespace drv {
+
+typedef unsigned __int128 u128;
+
+// ------------------------------------------------------------------ host Montgomery fields
+// 64-bit-limb CIOS over the same constants as the device arithmetic (arith.cuh parameter tables).
+template <class P>
+struct HostField {
+    static constexpr int N = P::N / 2;
+    struct el {
+        uint64_t l[N];
+        bool is_zero() const { uint64_t x = 0; for (int i = 0; i < N; i++) x |= l[i]; return x == 0; }
+    };
+    struct Consts {
+        uint64_t p[N], one[N], r2[N], inv;
+        Consts() {
+            for (int i = 0; i < N; i++) {
+                p[i] = (uint64_t)P::p(2 * i) | ((uint64_t)P::p(2 * i + 1) << 32);
+                one[i] = (uint64_t)P::one(2 * i) | ((uint64_t)P::one(2 * i + 1) << 32);
+                r2[i] = (uint64_t)P::r2(2 * i) | ((uint64_t)P::r2(2 * i + 1) << 32);
+            }
+            uint64_t x = 1;  // Newton: x <- x (2 - p0 x) doubles the correct low bits
+            for (int i = 0; i < 7; i++) x *= 2 - p[0] * x;
+            inv = 0 - x;
+        }
+    };
+    static const Consts& C() { static const Consts c; return c; }
+
+    static el zero() { el r; memset(r.l, 0, sizeof r.l); return r; }
+    static el one() { el r; memcpy(r.l, C().one, sizeof r.l); return r; }
+    static bool geq_p(const uint64_t* a) {
+        const uint64_t* p = C().p;
+        for (int i = N - 1; i >= 0; i--) { if (a[i] > p[i]) return true; if (a[i] < p[i]) return false; }
+        return true;
+    }
+    static void sub_p(uint64_t* a) {
+        const uint64_t* p = C().p;
+        uint64_t br = 0;
+        for (int i = 0; i < N; i++) { u128 d = (u128)a[i] - p[i] - br; a[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
+    }
+    // a may be any value below 2^(64 N) (not necessarily reduced); b < p
+    static el mul(const el& a, const el& b) {
+        const Consts& c = C();
+        uint64_t t[N + 2];
+        memset(t, 0, sizeof t);
+        for (int i = 0; i < N; i++) {
+            uint64_t cy = 0;
+            for (int j = 0; j < N; j++) { u128 s = (u128)a.l[j] * b.l[i] + t[j] + cy; t[j] = (uint64_t)s; cy = (uint64_t)(s >> 64); }
+            u128 s = (u128)t[N] + cy; t[N] = (uint64_t)s; t[N + 1] = (uint64_t)(s >> 64);
+            const uint64_t m = t[0] * c.inv;
+            s = (u128)m * c.p[0] + t[0]; cy = (uint64_t)(s >> 64);
+            for (int j = 1; j < N; j++) { s = (u128)m * c.p[j] + t[j] + cy; t[j - 1] = (uint64_t)s; cy = (uint64_t)(s >> 64); }
+            s = (u128)t[N] + cy; t[N - 1] = (uint64_t)s; t[N] = t[N + 1] + (uint64_t)(s >> 64);
+        }
+        if (t[N] || geq_p(t)) sub_p(t);
+        el r; memcpy(r.l, t, sizeof r.l); return r;
+    }
+    static el sqr(const el& a) { return mul(a, a); }
+    static el add(const el& a, const el& b) {
+        uint64_t t[N]; uint64_t cy = 0;
+        for (int i = 0; i < N; i++) { u128 s = (u128)a.l[i] + b.l[i] + cy; t[i] = (uint64_t)s; cy = (uint64_t)(s >> 64); }
+        if (cy || geq_p(t)) sub_p(t);
+        el r; memcpy(r.l, t, sizeof r.l); return r;
+    }
+    static el neg(const el& a) {
+        if (a.is_zero()) return a;
+        const uint64_t* p = C().p;
+        el r; uint64_t br = 0;
+        for (int i = 0; i < N; i++) { u128 d = (u128)p[i] - a.l[i] - br; r.l[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
+        return r;
+    }
+    static el sub(const el& a, const el& b) { return add(a, neg(b)); }
+    static el dbl(const el& a) { return add(a, a); }
+    static el to_mont(const el& raw) { el r2; memcpy(r2.l, C().r2, sizeof r2.l); return mul(raw, r2); }
+    static el from_mont(const el& a) { el o = zero(); o.l[0] = 1; return mul(a, o); }
+    static el from_u64(uint64_t v) { el r = zero(); r.l[0] = v; return to_mont(r); }
+    static el pow(el base, uint64_t e) {
+        el acc = one();
+        while (e) { if (e & 1) acc = mul(acc, base); base = sqr(base); e >>= 1; }
+        return acc;
+    }
+    static el inv(const el& a) {  // a^(p-2); 0 -> 0
+        uint64_t e[N]; memcpy(e, C().p, sizeof e);
+        e[0] -= 2;  // p is odd and > 2: no borrow
+        el acc = one();
+        for (int i = 64 * N - 1; i >= 0; i--) {
+            acc = sqr(acc);
+            if ((e[i / 64] >> (i % 64)) & 1) acc = mul(acc, a);
+        }
+        return acc;
+    }
+};
+
+typedef HostField<FrParams> F;
+typedef HostField<FqParams> Q;
+typedef F::el fr;
+
+static inline fr fr_load(const uint64_t* p) { fr r; memcpy(r.l, p, 32); return r; }
+static inline void fr_store(uint64_t* p, const fr& a) { memcpy(p, a.l, 32); }
+
+// 32-byte little-endian canonical encoding (TranscriptProtocol::append_scalar, proof wire format)
+static void fr_bytes(const fr& mont, uint8_t out[32]) {
+    const fr c = F::from_mont(mont);
+    for (int i = 0; i < 4; i++)
+        for (int b = 0; b < 8; b++) out[8 * i + b] = (uint8_t)(c.l[i] >> (8 * b));
+}
+
+// 64 little-endian bytes reduced mod r, returned in Montgomery form (challenge_scalar):
+// v = lo + 2^256 hi; mul(x, R^2) maps any 256-bit x to x R mod r, and R^2 is also the
+// Montgomery form of 2^256
+static fr fr_from_wide(const uint8_t b[64]) {
+    fr lo = F::zero(), hi = F::zero();
+    for (int i = 0; i < 32; i++) {
+        lo.l[i / 8] |= (uint64_t)b[i] << (8 * (i % 8));
+        hi.l[i / 8] |= (uint64_t)b[32 + i] << (8 * (i % 8));
+    }
+    fr r2; memcpy(r2.l, F::C().r2, 32);
+    return F::add(F::mul(lo, r2), F::mul(F::mul(hi, r2), r2));
+}
+
+// 48-byte compressed G1 (big-endian x; bit 7 compressed, bit 6 infinity, bit 5 = y is the larger root)
+static void g1_compress(const uint64_t xy[12], uint8_t out[48]) {
+    uint64_t any = 0;
+    for (int i = 0; i < 12; i++) any |= xy[i];
+    memset(out, 0, 48);
+    if (!any) { out[0] = 0xC0; return; }
+    Q::el x, y;
+    memcpy(x.l, xy, 48); memcpy(y.l, xy + 6, 48);
+    const Q::el xc = Q::from_mont(x), yc = Q::from_mont(y);
+    for (int i = 0; i < 6; i++)
+        for (int b = 0; b < 8; b++) out[47 - (8 * i + b)] = (uint8_t)(xc.l[i] >> (8 * b));
+    out[0] |= 0x80;
+    // y > p - y  (canonical integers)
+    const uint64_t* p = Q::C().p;
+    uint64_t ny[6]; uint64_t br = 0;
+    for (int i = 0; i < 6; i++) { u128 d = (u128)p[i] - yc.l[i] - br; ny[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
+    bool larger = false;
+    for (int i = 5; i >= 0; i--) {
+        if (yc.l[i] > ny[i]) { larger = true; break; }
+        if (yc.l[i] < ny[i]) break;
+    }
+    if (larger) out[0] |= 0x20;
+}
+
+// ------------------------------------------------------------------ Merlin transcript
+// STROBE-128/1600 restricted to the operations Merlin uses (meta-AD, AD, PRF).
+struct Transcript {
+    static constexpr int RATE = 166;
+    uint8_t st[200];
+    uint8_t pos, pos_begin, cur_flags;
+
+    void load(const uint8_t in[203]) { memcpy(st, in, 200); pos = in[200]; pos_begin = in[201]; cur_flags = in[202]; }
+    void save(uint8_t out[203]) const { memcpy(out, st, 200); out[200] = pos; out[201] = pos_begin; out[202] = cur_flags; }
+    void run_f() {
+        st[pos] ^= pos_begin;
+        st[pos + 1] ^= 0x04;
+        st[RATE + 1] ^= 0x80;
+        uint64_t w[25];
+        memcpy(w, st, 200);
+        zkp_keccak_f1600(w);
+        memcpy(st, w, 200);
+        pos = 0; pos_begin = 0;
+    }
+    void absorb(const uint8_t* d, size_t n) {
+        for (size_t i = 0; i < n; i++) { st[pos++] ^= d[i]; if (pos == RATE) run_f(); }
+    }
+    void squeeze(uint8_t* d, size_t n) {
+        for (size_t i = 0; i < n; i++) { d[i] = st[pos]; st[pos++] = 0; if (pos == RATE) run_f(); }
+    }
+    void begin_op(uint8_t flags, bool more) {
+        if (more) return;
+        const uint8_t old = pos_begin;
+        pos_begin = pos + 1;
+        cur_flags = flags;
+        const uint8_t hdr[2] = {old, flags};
+        absorb(hdr, 2);
+        if ((flags & (4 | 32)) && pos != 0) run_f();
+    }
+    void meta_ad(const void* d, size_t n, bool more) { begin_op(16 | 2, more); absorb((const uint8_t*)d, n); }
+    void ad(const void* d, size_t n) { begin_op(2, false); absorb((const uint8_t*)d, n); }
+    void append_message(const char* label, const uint8_t* msg, uint32_t n) {
+        meta_ad(label, strlen(label), false);
+        const uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+        meta_ad(len, 4, true);
+        ad(msg, n);
+    }
+    void challenge_bytes(const char* label, uint8_t* out, uint32_t n) {
+        meta_ad(label, strlen(label), false);
+        const uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+        meta_ad(len, 4, true);
+        begin_op(1 | 2 | 4, false);
+        squeeze(out, n);
+    }
+    // TranscriptProtocol (dusk encodings)
+    void append_scalar(const char* label, const fr& mont) { uint8_t b[32]; fr_bytes(mont, b); append_message(label, b, 32); }
+    void append_commitment(const char* label, const uint64_t xy[12]) { uint8_t b[48]; g1_compress(xy, b); append_message(label, b, 48); }
+    fr challenge_scalar(const char* label) { uint8_t b[64]; challenge_bytes(label, b, 64); return fr_from_wide(b); }
+};
+
+// ------------------------------------------------------------------ linearisation scalars
+// widget.linearize / permutation.linearize on the opened evaluations (Montgomery form throughout).
+struct Lin {
+    static fr c(uint64_t v) { return F::from_u64(v); }
+    static fr m(const fr& a, const fr& b) { return F::mul(a, b); }
+    static fr a(const fr& x, const fr& y) { return F::add(x, y); }
+    static fr s(const fr& x, const fr& y) { return F::sub(x, y); }
+    static fr delta(const fr& f) {
+        const fr one = F::one();
+        const fr f1 = s(f, one), f2 = s(f1, one), f3 = s(f2, one);
+        return m(m(m(f, f1), f2), f3);
+    }
+    static fr x4(const fr& v) { return F::dbl(F::dbl(v)); }
+    static fr edwards_d() {  // JubJub d = -(10240 / 10241)
+        static const fr d = F::neg(m(c(10240), F::inv(c(10241))));
+        return d;
+    }
+    static fr range_term(const fr& sep, const fr& A, const fr& B, const fr& C, const fr& D, const fr& Dn) {
+        const fr k = m(sep, sep), k2 = m(k, k), k3 = m(k2, k);
+        fr r = delta(s(C, x4(D)));
+        r = a(r, m(delta(s(B, x4(C))), k));
+        r = a(r, m(delta(s(A, x4(B))), k2));
+        r = a(r, m(delta(s(Dn, x4(A))), k3));
+        return m(r, sep);
+    }
+    static fr logic_term(const fr& sep, const fr& wa, const fr& an, const fr& wb, const fr& bn, const fr& wc,
+                         const fr& wd, const fr& dn, const fr& qc) {
+        const fr k = m(sep, sep), k2 = m(k, k), k3 = m(k2, k), k4 = m(k3, k);
+        const fr A = s(an, x4(wa)), B = s(bn, x4(wb)), D = s(dn, x4(wd));
+        const fr AB = a(A, B);
+        // f = c (c (4c - 18(A+B) + 81) + 18(A^2 + B^2) - 81(A+B) + 83)
+        fr inner = a(s(x4(wc), m(c(18), AB)), c(81));
+        inner = m(wc, inner);
+        inner = a(inner, m(c(18), a(m(A, A), m(B, B))));
+        inner = s(inner, m(c(81), AB));
+        inner = a(inner, c(83));
+        const fr f = m(wc, inner);
+        const fr e = s(m(c(3), a(AB, D)), F::dbl(f));
+        const fr bb = m(qc, s(m(c(9), D), m(c(3), AB)));
+        fr r = m(s(wc, m(A, B)), k3);
+        r = a(r, delta(A));
+        r = a(r, m(delta(B), k));
+        r = a(r, m(delta(D), k2));
+        r = a(r, m(a(bb, e), k4));
+        return m(r, sep);
+    }
+    static fr fixed_base_term(const fr& sep, const fr& wa, const fr& an, const fr& wb, const fr& bn, const fr& wc,
+                              const fr& wd, const fr& dn, const fr& ql, const fr& qr, const fr& qc) {
+        const fr one = F::one();
+        const fr k = m(sep, sep), k2 = m(k, k), k3 = m(k2, k);
+        const fr bit = s(dn, F::dbl(wd));
+        const fr y_alpha = a(m(m(bit, bit), s(qr, one)), one);
+        const fr x_alpha = m(bit, ql);
+        const fr t = m(m(m(wc, wa), wb), edwards_d());
+        const fr x_acc = m(s(a(an, m(an, t)), a(m(wa, y_alpha), m(wb, x_alpha))), k2);
+        const fr y_acc = m(s(s(bn, m(bn, t)), a(m(wb, y_alpha), m(wa, x_alpha))), k3);
+        fr r = m(m(bit, s(bit, one)), a(bit, one));
+        r = a(r, x_acc);
+        r = a(r, y_acc);
+        r = a(r, m(s(m(bit, qc), wc), k));
+        return m(r, sep);
+    }
+    static fr var_base_term(const fr& sep, const fr& wa, const fr& an, const fr& wb, const fr& bn, const fr& wc,
+                            const fr& wd, const fr& dn) {
+        const fr k = m(sep, sep);
+        const fr y1x2 = m(wb, wc), y1y2 = m(wb, wd), x1x2 = m(wa, wc);
+        const fr t = m(m(edwards_d(), dn), y1x2);
+        const fr x3c = m(s(a(dn, y1x2), a(an, m(an, t))), k);
+        const fr y3c = m(s(a(y1y2, x1x2), s(bn, m(bn, t))), m(k, k));
+        return m(a(a(s(m(wa, wd), dn), x3c), y3c), sep);
+    }
+};
+
+// r(X) = sum_j sc[j] * poly_j(X) over q_m q_l q_r q_o q_4 q_c q_range q_logic q_fixed q_var z s_sigma_4.
+// ch = alpha beta gamma range logic fixed var z_challenge; e = the first 15 entries of `Evaluations`.
+static void linearization_scalars(uint64_t n, const fr ch[8], const fr e[15], fr sc[12]) {
+    const fr &alpha = ch[0], &beta = ch[1], &gamma = ch[2], &zc = ch[7];
+    const fr &a = e[0], &b = e[1], &c = e[2], &d = e[3], &an = e[4], &bn = e[5], &dn = e[6], &s1 = e[7], &s2 = e[8],
+             &s3 = e[9], &qarith = e[10], &qc = e[11], &ql = e[12], &qr = e[13], &pe = e[14];
+    sc[0] = F::mul(F::mul(a, b), qarith);
+    sc[1] = F::mul(a, qarith);
+    sc[2] = F::mul(b, qarith);
+    sc[3] = F::mul(c, qarith);
+    sc[4] = F::mul(d, qarith);
+    sc[5] = qarith;
+    sc[6] = Lin::range_term(ch[3], a, b, c, d, dn);
+    sc[7] = Lin::logic_term(ch[4], a, an, b, bn, c, d, dn, qc);
+    sc[8] = Lin::fixed_base_term(ch[5], a, an, b, bn, c, d, dn, ql, qr, qc);
+    sc[9] = Lin::var_base_term(ch[6], a, an, b, bn, c, d, dn);
+    // permutation part (pinned by the verifier identity, src/prover/proof.rs:386-440)
+    const fr one = F::one();
+    const fr zh = F::sub(F::pow(zc, n), one);
+    const fr l1 = F::mul(zh, F::inv(F::mul(F::from_u64(n), F::sub(zc, one))));
+    const fr bz = F::mul(beta, zc);
+    fr x = F::add(F::add(a, bz), gamma);
+    x = F::mul(x, F::add(F::add(b, F::mul(bz, F::from_u64(7))), gamma));
+    x = F::mul(x, F::add(F::add(c, F::mul(bz, F::from_u64(13))), gamma));
+    x = F::mul(x, F::add(F::add(d, F::mul(bz, F::from_u64(17))), gamma));
+    x = F::mul(x, alpha);
+    fr y = F::add(F::add(a, F::mul(beta, s1)), gamma);
+    y = F::mul(y, F::add(F::add(b, F::mul(beta, s2)), gamma));
+    y = F::mul(y, F::add(F::add(c, F::mul(beta, s3)), gamma));
+    y = F::mul(F::mul(F::mul(y, beta), pe), alpha);
+    sc[10] = F::add(x, F::mul(l1, F::sqr(alpha)));
+    sc[11] = F::neg(y);
+}
+
+#define TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+static inline zkp_poly_ref ref(const zkp_buf* b, size_t off, size_t len) { zkp_poly_ref r; r.buf = b; r.off = off; r.len = len; return r; }
+
+// key.poly / key.eval8 indices
+enum { Q_M = 0, Q_L, Q_R, Q_O, Q_C, Q_D, Q_ARITH, Q_RANGE, Q_LOGIC, Q_FIXED, Q_VAR, S1, S2, S3, S4 };
+
+static int commit_group(zkp_prover* pr, const zkp_poly_ref* polys, unsigned count, uint64_t* out_xy) {
+    const fr_t* ptrs[8];
+    size_t lens[8];
+    int ovf[8];
+    for (unsigned i = 0; i < count; i++) { ptrs[i] = polys[i].buf->d + polys[i].off; lens[i] = polys[i].len; }
+    TRY(msm_run_batch(pr->ctx, pr->srs, ptrs, lens, count, reinterpret_cast<g1_affine*>(out_xy), ovf));
+    for (unsigned i = 0; i < count; i++) if (ovf[i]) return ZKP_ERR_DEGREE;  // commit(..)? in the reference
+    return ZKP_OK;
+}
+
+static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_t* wires_host, const zkp_buf* wires_dev,
+                 const uint64_t* pi_host, const zkp_buf* pi_dev, const uint64_t* blinders, uint64_t* comms,
+                 uint64_t* evals, uint8_t* proof_bytes, uint8_t* transcript_out) {
+    zkp_ctx* ctx = pr->ctx;
+    zkp_ctx* side = pr->side;
+    const zkp_proving_key& key = pr->key;
+    const size_t n = pr->n, S = pr->S, n8 = 8 * n;
+    const unsigned k = pr->k, k8 = k + 3;
+    TRY(set_device(ctx));
+    Transcript tr;
+    tr.load(transcript_in);
+
+    // round 1: wires -> iNTT -> blind -> commit (src/prover.rs:107-158)
+    const zkp_buf* W = wires_dev;
+    if (!W) {
+        ZKP_CUDA(ctx, cudaMemcpyAsync(pr->W->d, wires_host, 4 * n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+        W = pr->W;
+    }
+    TRY(ntt_run(ctx, W->d, n, n, pr->P7->d, S, k, true, false, 4));
+    for (unsigned j = 0; j < 4; j++) TRY(zkp_poly_blind_dev(ctx, pr->P7, j * S, n, blinders + 8 * j, 2));
+    if (pi_dev) {
+        TRY(ntt_run(ctx, pi_dev->d, 0, n, pr->P7->d + 4 * S, 0, k, true, false, 1));
+    } else {
+        ZKP_CUDA(ctx, cudaMemcpyAsync(pr->P7->d + 4 * S, pi_host, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
+        TRY(ntt_run(ctx, pr->P7->d + 4 * S, 0, n, pr->P7->d + 4 * S, 0, k, true, false, 1));
+    }
+    // a, b, c, d, PI on the 8n coset: second stream, under the wire commitments
+    // (reference order: src/prover.rs:229, quotient_poly.rs:54-58,145 -- same values, earlier)
+    ZKP_CUDA(ctx, cudaEventRecord(pr->ev_main, ctx->stream));
+    ZKP_CUDA(ctx, cudaStreamWaitEvent(side->stream, pr->ev_main, 0));
+    TRY(ntt_run(side, pr->P7->d, S, n + 3, pr->E7->d, n8, k8, false, true, 5));
+    zkp_poly_ref wp[4];
+    for (unsigned j = 0; j < 4; j++) wp[j] = ref(pr->P7, j * S, n + 2);
+    TRY(commit_group(pr, wp, 4, comms));
+    static const char* const wl[4] = {"a_w", "b_w", "c_w", "d_w"};
+    for (unsigned j = 0; j < 4; j++) tr.append_commitment(wl[j], comms + 12 * j);
+
+    // round 2: permutation accumulator (src/prover.rs:160-199)
+    const fr beta = tr.challenge_scalar("beta");
+    tr.append_scalar("beta", beta);
+    const fr gamma = tr.challenge_scalar("gamma");
+    zkp_poly_ref wr[4];
+    for (unsigned j = 0; j < 4; j++) wr[j] = ref(W, j * n, n);
+    TRY(zkp_perm_z_dev(ctx, n, wr, key.sigma_evals, key.roots, beta.l, gamma.l, pr->Z, 0));
+    const zkp_poly_ref zp = ref(pr->P7, 5 * S, n + 3);
+    TRY(ntt_run(ctx, pr->Z->d, 0, n, pr->P7->d + 5 * S, 0, k, true, false, 1));
+    TRY(zkp_poly_blind_dev(ctx, pr->P7, 5 * S, n, blinders + 32, 3));
+    // z on the 8n coset needs no further challenge either: side stream, under the z commitment
+    ZKP_CUDA(ctx, cudaEventRecord(pr->ev_main, ctx->stream));
+    ZKP_CUDA(ctx, cudaStreamWaitEvent(side->stream, pr->ev_main, 0));
+    TRY(ntt_run(side, pr->P7->d + 5 * S, 0, n + 3, pr->E7->d + 5 * n8, 0, k8, false, true, 1));
+    ZKP_CUDA(ctx, cudaEventRecord(pr->ev_side, side->stream));
+    TRY(commit_group(pr, &zp, 1, comms + 12 * 4));
+    tr.append_commitment("z", comms + 12 * 4);
+
+    // round 3: quotient on the 8n coset (src/prover.rs:201-287, quotient_poly.rs)
+    fr ch[7];
+    ch[0] = tr.challenge_scalar("alpha");
+    ch[1] = beta;
+    ch[2] = gamma;
+    ch[3] = tr.challenge_scalar("range separation challenge");
+    ch[4] = tr.challenge_scalar("logic separation challenge");
+    ch[5] = tr.challenge_scalar("fixed base separation challenge");
+    ch[6] = tr.challenge_scalar("variable base separation challenge");
+    const fr alpha = ch[0];
+    const fr alpha2 = F::sqr(alpha);
+    // L1 * alpha^2: idft of (alpha^2, 0, ..) has every coefficient alpha^2 / n (quotient_poly.rs:264-272)
+    const fr n_inv = F::inv(F::from_u64((uint64_t)n));
+    const fr l1c = F::mul(alpha2, n_inv);
+    TRY(zkp_buf_fill(ctx, pr->P7, 6 * S, n, l1c.l));
+    TRY(ntt_run(ctx, pr->P7->d + 6 * S, 0, n, pr->E7->d + 6 * n8, 0, k8, false, true, 1));
+    ZKP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pr->ev_side, 0));
+    zkp_quotient_args qa;
+    memset(&qa, 0, sizeof qa);
+    for (unsigned j = 0; j < 4; j++) { qa.wires[j] = ref(pr->E7, j * n8, n8); qa.sigma[j] = key.eval8[S1 + j]; }
+    qa.pi = ref(pr->E7, 4 * n8, n8);
+    qa.z = ref(pr->E7, 5 * n8, n8);
+    qa.l1 = ref(pr->E7, 6 * n8, n8);
+    for (unsigned j = 0; j < 11; j++) qa.sel[j] = key.eval8[j];
+    qa.linear = key.linear8;
+    for (unsigned j = 0; j < 7; j++) memcpy(qa.challenges[j], ch[j].l, 32);
+    memcpy(qa.zh_inv, key.zh_inv, sizeof qa.zh_inv);
+    qa.widget_mask = key.widget_mask;
+    TRY(zkp_quotient_dev(ctx, k8, &qa, pr->T, 0));
+    TRY(ntt_run(ctx, pr->T->d, 0, n8, pr->T->d, 0, k8, true, true, 1));  // coset_idft -> t coefficients
+    const zkp_poly_ref tq[4] = {ref(pr->T, 0, n), ref(pr->T, n, n), ref(pr->T, 2 * n, n), ref(pr->T, 3 * n, 5 * n)};
+    TRY(commit_group(pr, tq, 4, comms + 12 * 5));
+    static const char* const tl[4] = {"t_low", "t_mid", "t_high", "t_4"};
+    for (unsigned j = 0; j < 4; j++) tr.append_commitment(tl[j], comms + 12 * (5 + j));
+
+    // rounds 4/5: evaluations, linearisation, openings (src/prover.rs:289-452)
+    const fr zc = tr.challenge_scalar("z_challenge");
+    const fr zw = F::mul(zc, fr_load(key.generator));
+    zkp_poly_ref at_z[12];
+    at_z[0] = ref(pr->T, 0, n8);
+    for (unsigned j = 0; j < 4; j++) at_z[1 + j] = wp[j];
+    static const int atz_key[7] = {S1, S2, S3, Q_ARITH, Q_C, Q_L, Q_R};
+    for (unsigned j = 0; j < 7; j++) at_z[5 + j] = key.poly[atz_key[j]];
+    uint64_t e1[12 * 4], e2[4 * 4];
+    TRY(zkp_poly_eval_dev(ctx, at_z, 12, zc.l, e1));
+    const zkp_poly_ref at_zw[4] = {wp[0], wp[1], wp[3], zp};
+    TRY(zkp_poly_eval_dev(ctx, at_zw, 4, zw.l, e2));
+    const fr t_eval = fr_load(e1);
+    const fr a = fr_load(e1 + 4), b = fr_load(e1 + 8), c = fr_load(e1 + 12), d = fr_load(e1 + 16);
+    const fr s1 = fr_load(e1 + 20), s2 = fr_load(e1 + 24), s3 = fr_load(e1 + 28);
+    const fr qarith = fr_load(e1 + 32), qc = fr_load(e1 + 36), ql = fr_load(e1 + 40), qr = fr_load(e1 + 44);
+    const fr an = fr_load(e2), bn = fr_load(e2 + 4), dn = fr_load(e2 + 8), pe = fr_load(e2 + 12);
+
+    // r(X) = sum scalar * poly(X)
+    fr sc[12];
+    zkp_poly_ref lr[12];
+    static const int lin_key[10] = {Q_M, Q_L, Q_R, Q_O, Q_D, Q_C, Q_RANGE, Q_LOGIC, Q_FIXED, Q_VAR};
+    for (unsigned j = 0; j < 10; j++) lr[j] = key.poly[lin_key[j]];
+    lr[10] = zp;
+    lr[11] = key.poly[S4];
+    {
+        fr ch8[8];
+        for (unsigned j = 0; j < 7; j++) ch8[j] = ch[j];
+        ch8[7] = zc;
+        const fr e15[15] = {a, b, c, d, an, bn, dn, s1, s2, s3, qarith, qc, ql, qr, pe};
+        linearization_scalars((uint64_t)n, ch8, e15, sc);
+    }
+    uint64_t scl[16 * 4];
+    for (unsigned j = 0; j < 12; j++) fr_store(scl + 4 * j, sc[j]);
+    TRY(zkp_poly_lincomb_dev(ctx, lr, scl, 12, pr->R, 0, n + 3));
+    const zkp_poly_ref rr = ref(pr->R, 0, n + 3);
+    uint64_t e3[4];
+    TRY(zkp_poly_eval_dev(ctx, &rr, 1, zc.l, e3));
+    const fr r_eval = fr_load(e3);
+
+    // evaluations in `Evaluations` order (prover.py EVAL_NAMES)
+    const fr ev[16] = {a, b, c, d, an, bn, dn, s1, s2, s3, qarith, qc, ql, qr, pe, r_eval};
+    static const char* const el[15] = {"a_eval", "b_eval", "c_eval", "d_eval", "a_next_eval", "b_next_eval",
+                                       "d_next_eval", "s_sigma_1_eval", "s_sigma_2_eval", "s_sigma_3_eval",
+                                       "q_arith_eval", "q_c_eval", "q_l_eval", "q_r_eval", "perm_eval"};
+    for (unsigned j = 0; j < 15; j++) tr.append_scalar(el[j], ev[j]);
+    tr.append_scalar("t_eval", t_eval);
+    tr.append_scalar("r_eval", r_eval);
+
+    // W_z: (t_low + z^n t_mid + z^2n t_high + z^3n t_4) + v r + v^2 a + .., divided by (X - z)
+    {
+        const fr z_n = F::pow(zc, (uint64_t)n);
+        const fr v1 = tr.challenge_scalar("v_challenge");
+        zkp_poly_ref ar[12] = {tq[0], tq[1], tq[2], tq[3], rr, wp[0], wp[1], wp[2], wp[3],
+                               key.poly[S1], key.poly[S2], key.poly[S3]};
+        fr as[12];
+        as[0] = F::one();
+        as[1] = z_n;
+        as[2] = F::sqr(z_n);
+        as[3] = F::mul(as[2], z_n);
+        as[4] = v1;
+        for (unsigned j = 5; j < 12; j++) as[j] = F::mul(as[j - 1], v1);
+        for (unsigned j = 0; j < 12; j++) fr_store(scl + 4 * j, as[j]);
+        TRY(zkp_poly_lincomb_dev(ctx, ar, scl, 12, pr->AGG, 0, 5 * n));
+        TRY(zkp_poly_div_linear_dev(ctx, ref(pr->AGG, 0, 5 * n), zc.l, pr->WZ, 0));
+        // the second v_challenge follows the first with nothing appended in between
+        // (src/prover.rs:435-450): both witnesses are committed as one batch of two
+        const fr v2 = tr.challenge_scalar("v_challenge");
+        const zkp_poly_ref br[4] = {zp, wp[0], wp[1], wp[3]};
+        fr bs[4];
+        bs[0] = F::one();
+        for (unsigned j = 1; j < 4; j++) bs[j] = F::mul(bs[j - 1], v2);
+        for (unsigned j = 0; j < 4; j++) fr_store(scl + 4 * j, bs[j]);
+        TRY(zkp_poly_lincomb_dev(ctx, br, scl, 4, pr->SAGG, 0, n + 3));
+        TRY(zkp_poly_div_linear_dev(ctx, ref(pr->SAGG, 0, n + 3), zw.l, pr->WZW, 0));
+        const zkp_poly_ref wc[2] = {ref(pr->WZ, 0, 5 * n - 1), ref(pr->WZW, 0, n + 2)};
+        TRY(commit_group(pr, wc, 2, comms + 12 * 9));
+    }
+
+    for (unsigned j = 0; j < 16; j++) fr_store(evals + 4 * j, ev[j]);
+    if (proof_bytes) {
+        // 11 compressed G1 then the 16 evaluations in the field order of `Evaluations`
+        // (src/prover/linearization_poly.rs:113-130): a b c d a' b' d' q_arith q_c q_l q_r s1 s2 s3 r perm
+        for (unsigned j = 0; j < 11; j++) g1_compress(comms + 12 * j, proof_bytes + 48 * j);
+        static const int wire_order[16] = {0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 7, 8, 9, 15, 14};
+        for (unsigned j = 0; j < 16; j++) fr_bytes(ev[wire_order[j]], proof_bytes + 48 * 11 + 32 * j);
+    }
+    if (transcript_out) tr.save(transcript_out);
+    return ZKP_OK;
+}
+
+}  // namespace drv
+}  // namespace zkp
+
+using namespace zkp;
+
+extern "C" {
+
+int zkp_prover_destroy(zkp_prover* pr) {
+    if (!pr) return ZKP_OK;
+    zkp_ctx* ctx = pr->ctx;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (pr->side) cudaStreamSynchronize(pr->side->stream);
+    zkp_buf** bufs[] = {&pr->W, &pr->Z, &pr->P7, &pr->E7, &pr->T, &pr->R, &pr->AGG, &pr->WZ, &pr->SAGG, &pr->WZW};
+    for (zkp_buf** b : bufs) if (*b) { zkp_buf_free(ctx, *b); *b = nullptr; }
+    if (pr->ev_main) cudaEventDestroy(pr->ev_main);
+    if (pr->ev_side) cudaEventDestroy(pr->ev_side);
+    if (pr->side) zkp_ctx_destroy(pr->side);
+    delete pr;
+    return ZKP_OK;
+}
+
+int zkp_prover_create(zkp_ctx* ctx, const zkp_srs* srs, const zkp_proving_key* key, zkp_prover** out) {
+    if (!ctx || !srs || !key || !out || key->k < 1 || key->k > 25 || !key->roots) return ZKP_ERR_INVALID;
+    const size_t n = (size_t)1 << key->k, n8 = 8 * n;
+    for (int j = 0; j < 15; j++) {
+        const zkp_poly_ref &p = key->poly[j], &e = key->eval8[j];
+        if (!p.buf || p.off + p.len > p.buf->n || p.len < n) return ZKP_ERR_INVALID;
+        if (!e.buf || e.off + e.len > e.buf->n || e.len < n8) return ZKP_ERR_INVALID;
+    }
+    for (int j = 0; j < 4; j++) {
+        const zkp_poly_ref& s = key->sigma_evals[j];
+        if (!s.buf || s.off + s.len > s.buf->n || s.len < n) return ZKP_ERR_INVALID;
+    }
+    if (!key->linear8.buf || key->linear8.off + key->linear8.len > key->linear8.buf->n || key->linear8.len < n8 ||
+        key->roots->n < n)
+        return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    zkp_prover* pr = new (std::nothrow) zkp_prover();
+    if (!pr) return ZKP_ERR_NOMEM;
+    pr->ctx = ctx;
+    pr->srs = srs;
+    pr->key = *key;
+    pr->n = n;
+    pr->k = key->k;
+    pr->S = n + 8;  // the seven polynomials bound for the 8n coset sit side by side
+    struct { zkp_buf** b; size_t len; } want[] = {
+        {&pr->W, 4 * n}, {&pr->Z, n}, {&pr->P7, 7 * pr->S}, {&pr->E7, 7 * n8}, {&pr->T, n8}, {&pr->R, n + 3},
+        {&pr->AGG, 5 * n}, {&pr->WZ, 5 * n}, {&pr->SAGG, n + 3}, {&pr->WZW, n + 3}};
+    for (auto& w : want)
+        if ((rc = zkp_buf_alloc(ctx, w.len, w.b))) { zkp_prover_destroy(pr); return rc; }
+    if ((rc = zkp_buf_zero(ctx, pr->P7, 0, 7 * pr->S)) || (rc = zkp_ctx_create(ctx->device, &pr->side))) {
+        zkp_prover_destroy(pr);
+        return rc;
+    }
+    if (cudaEventCreateWithFlags(&pr->ev_main, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pr->ev_side, cudaEventDisableTiming) != cudaSuccess) {
+        zkp_prover_destroy(pr);
+        return ZKP_ERR_CUDA;
+    }
+    if ((rc = zkp_ctx_sync(ctx))) { zkp_prover_destroy(pr); return rc; }
+    *out = pr;
+    return ZKP_OK;
+}
+
+int zkp_prover_prove(zkp_prover* pr, const uint8_t transcript[203], const uint64_t* wires_host,
+                     const zkp_buf* wires_dev, const uint64_t* pi_host, const zkp_buf* pi_dev,
+                     const uint64_t blinders[44], uint64_t commitments[132], uint64_t evaluations[64],
+                     uint8_t proof_bytes[1040], uint8_t transcript_out[203]) {
+    if (!pr || !transcript || !blinders || !commitments || !evaluations) return ZKP_ERR_INVALID;
+    if ((!wires_host && !wires_dev) || (!pi_host && !pi_dev)) return ZKP_ERR_INVALID;
+    if ((wires_dev && wires_dev->n < 4 * pr->n) || (pi_dev && pi_dev->n < pr->n)) return ZKP_ERR_INVALID;
+    const int rc = drv::prove(pr, transcript, wires_host, wires_dev, pi_host, pi_dev, blinders, commitments,
+                              evaluations, proof_bytes, transcript_out);
+    if (rc) {
+        // leave both streams idle so the next proof never races a half-finished one
+        cudaStreamSynchronize(pr->side->stream);
+        cudaStreamSynchronize(pr->ctx->stream);
+    }
+    return rc;
+}
+
+/* Merlin transcript operations on a serialized state (host code): what TranscriptProtocol needs
+ * outside a proof (seeding with the verification key, public inputs) without leaving native code. */
+int zkp_transcript_append(uint8_t state[203], const char* label, const uint8_t* msg, uint32_t len) {
+    if (!state || !label || (!msg && len)) return ZKP_ERR_INVALID;
+    drv::Transcript t;
+    t.load(state);
+    t.append_message(label, msg, len);
+    t.save(state);
+    return ZKP_OK;
+}
+
+int zkp_transcript_challenge(uint8_t state[203], const char* label, uint8_t* out, uint32_t len) {
+    if (!state || !label || (!out && len)) return ZKP_ERR_INVALID;
+    drv::Transcript t;
+    t.load(state);
+    t.challenge_bytes(label, out, len);
+    t.save(state);
+    return ZKP_OK;
+}
+
+/* The scalar side of the linearisation alone (host code; unit-tested on the CPU against widgets.py):
+ * challenges = alpha beta gamma range logic fixed var z (8 x 4, Montgomery), evals in `Evaluations`
+ * order (first 15 used), out = the 12 scalars of q_m q_l q_r q_o q_4 q_c q_range q_logic q_fixed q_var z s_sigma_4. */
+int zkp_linearization_scalars(unsigned k, const uint64_t challenges[32], const uint64_t evals[60], uint64_t out[48]) {
+    if (!challenges || !evals || !out || k > 28) return ZKP_ERR_INVALID;
+    using drv::fr; using drv::fr_load; using drv::fr_store;
+    fr ch[8], e[15], sc[12];
+    for (int j = 0; j < 8; j++) ch[j] = fr_load(challenges + 4 * j);
+    for (int j = 0; j < 15; j++) e[j] = fr_load(evals + 4 * j);
+    drv::linearization_scalars((uint64_t)1 << k, ch, e, sc);
+    for (int j = 0; j < 12; j++) fr_store(out + 4 * j, sc[j]);
+    return ZKP_OK;
+}
+
+/* Encodings the transcript and the proof wire format use (host code). */
+int zkp_g1_compress(const uint64_t xy[12], uint8_t out[48]) {
+    if (!xy || !out) return ZKP_ERR_INVALID;
+    drv::g1_compress(xy, out);
+    return ZKP_OK;
+}
+
+int zkp_fr_from_wide(const uint8_t bytes[64], uint64_t out_mont[4]) {
+    if (!bytes || !out_mont) return ZKP_ERR_INVALID;
+    drv::fr_store(out_mont, drv::fr_from_wide(bytes));
+    return ZKP_OK;
+}
+
+}  // extern "C"

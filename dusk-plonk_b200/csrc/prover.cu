@@ -641,7 +641,8 @@ int zkp_quotient_range_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* q
     a.bk2 = a.beta * from_u64<FrParams>(13);
     a.bk3 = a.beta * from_u64<FrParams>(17);
     // JubJub d = -(10240 / 10241)
-    a.edwards_d = neg(from_u64<FrParams>(10240) * inverse(from_u64<FrParams>(10241)));
+    static const fr_t edwards_d = neg(from_u64<FrParams>(10240) * inverse(from_u64<FrParams>(10241)));  // once
+    a.edwards_d = edwards_d;
     for (int j = 0; j < 8; j++) a.zh_inv[j] = fr_from_host(q->zh_inv[j]);
     a.mask = q->widget_mask;
     a.n8 = n8;

@@ -100,6 +100,26 @@ SIGNATURES.update({
     "zkp_poly_div_linear_dev": (_int, [_vp, PolyRef, _vp, _vp, _sz]),
 })
 
+
+
+class ProvingKeyDesc(ctypes.Structure):
+    """``zkp_proving_key``."""
+    _fields_ = [("k", _uint), ("poly", PolyRef * 15), ("eval8", PolyRef * 15), ("linear8", PolyRef),
+                ("sigma_evals", PolyRef * 4), ("roots", _vp), ("zh_inv", (ctypes.c_uint64 * 4) * 8),
+                ("generator", ctypes.c_uint64 * 4), ("widget_mask", ctypes.c_uint32)]
+
+
+SIGNATURES.update({
+    "zkp_prover_create": (_int, [_vp, _vp, ctypes.POINTER(ProvingKeyDesc), ctypes.POINTER(_vp)]),
+    "zkp_prover_destroy": (_int, [_vp]),
+    "zkp_prover_prove": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "zkp_transcript_append": (_int, [_vp, ctypes.c_char_p, _vp, ctypes.c_uint32]),
+    "zkp_transcript_challenge": (_int, [_vp, ctypes.c_char_p, _vp, ctypes.c_uint32]),
+    "zkp_linearization_scalars": (_int, [_uint, _vp, _vp, _vp]),
+    "zkp_g1_compress": (_int, [_vp, _vp]),
+    "zkp_fr_from_wide": (_int, [_vp, _vp]),
+})
+
 _lib = None
 
 
@@ -491,5 +511,44 @@ class Srs:
     def __del__(self):
         try:
             self.free()
+        except Exception:
+            pass
+
+
+class NativeProver:
+    """``zkp_prover``: the round driver of ``create_proof`` in native code (csrc/create_proof.cu)."""
+
+    def __init__(self, ctx, srs, desc, keepalive):
+        self.ctx = ctx
+        self._keep = (srs, desc, keepalive)   # the key's buffers and the SRS must outlive the handle
+        h = _vp()
+        ctx.check(ctx.lib.zkp_prover_create(ctx.h, srs.h, ctypes.byref(desc), ctypes.byref(h)))
+        self.h = h
+        self._comms = np.zeros((11, 12), dtype=np.uint64)
+        self._evals = np.zeros((16, 4), dtype=np.uint64)
+        self._bytes = np.zeros(1040, dtype=np.uint8)
+
+    def prove(self, transcript_state, wires_host, wires_dev, pi_host, pi_dev, blinders_mont):
+        """-> (rc, commitments (11, 12), evaluations (16, 4), proof bytes).  Exactly one of
+        wires_host / wires_dev and of pi_host / pi_dev is given."""
+        st = np.frombuffer(bytes(transcript_state), dtype=np.uint8)
+        assert st.shape[0] == 203
+        bl = as_fr_array(blinders_mont)
+        assert bl.shape[0] == 11
+        rc = self.ctx.lib.zkp_prover_prove(
+            self.h, _ptr(st),
+            _ptr(wires_host) if wires_host is not None else None, wires_dev.h if wires_dev is not None else None,
+            _ptr(pi_host) if pi_host is not None else None, pi_dev.h if pi_dev is not None else None,
+            _ptr(bl), _ptr(self._comms), _ptr(self._evals), _ptr(self._bytes), None)
+        return rc, self._comms, self._evals, self._bytes
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.zkp_prover_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass

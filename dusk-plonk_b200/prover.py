@@ -11,6 +11,7 @@ from .field import R_MOD, K1, K2, K3, fr_from_mont, fr_to_mont, fr_to_mont1, g1_
 from .ffi import QuotientArgs, BufferView as _View
 from .composer import SELECTORS, SynthesizedCircuit, Plonk
 from .widgets import linearization_scalars
+from .plonk_params import PlonkParams
 
 _r = R_MOD
 EVAL_NAMES = ("a_eval", "b_eval", "c_eval", "d_eval", "a_next_eval", "b_next_eval", "d_next_eval",
@@ -69,6 +70,10 @@ class Prover:
         self.size = prover_key.n
         self.pi_indexes = list(pi_indexes)
         self._ws = None
+        self._native = None
+        # the sharded proof (NCCL collectives between rounds) and traced proofs run the same rounds
+        # from Python; everything else goes through the native driver
+        self.native = True
 
     # ---------------------------------------------------------------- workspace
     def _workspace(self):
@@ -121,10 +126,61 @@ class Prover:
         if getattr(self, "_side", None) is not None:
             self._side.close()
             self._side = None
+        if self._native is not None:
+            self._native.close()
+            self._native = None
         self._ws = None
 
     def _commit(self, buf, off=0, n=None):
         return self.keypair.commit(_View(buf, off, n)).affine()
+
+    # ---------------------------------------------------------------- native round driver
+    def _native_prover(self):
+        """``zkp_prover`` over this key (csrc/create_proof.cu): rounds, transcript and the
+        linearisation scalars in native code, one call per proof."""
+        if self._native is None:
+            from .ffi import NativeProver, ProvingKeyDesc
+            from .key import SIGMAS
+            pk, ref = self.prover_key, self.ctx.ref
+            d = ProvingKeyDesc()
+            d.k = pk.k
+            n, n8 = pk.n, 8 * pk.n
+            for i, nm in enumerate(SELECTORS + SIGMAS):
+                d.poly[i] = ref(pk.poly[nm], 0, n)
+                d.eval8[i] = ref(pk.eval8[nm], 0, n8)
+            d.linear8 = ref(pk.eval8["linear"], 0, n8)
+            for j in range(4):
+                d.sigma_evals[j] = ref(pk.sigma_evals[j], 0, n)
+            d.roots = pk.roots.h
+            gen = fr_to_mont1(self.verifier_key["generator"])
+            for j in range(8):
+                for l in range(4):
+                    d.zh_inv[j][l] = int(pk.zh_inv[j, l])
+            for l in range(4):
+                d.generator[l] = int(gen[l])
+            d.widget_mask = pk.widget_mask
+            self._native = NativeProver(self.ctx, self.keypair.srs, d, (pk, self.keypair))
+        return self._native
+
+    def _create_proof_native(self, tr, wa, bl):
+        from .ffi import ZKP_ERR_DEGREE, ZkpError
+        from .plonk_params import Error
+        st = bytes(tr.strobe.state) + bytes([tr.strobe.pos, tr.strobe.pos_begin, tr.strobe.cur_flags])
+        n = self.size
+        wires_host = None if wa.wires_dev is not None else np.ascontiguousarray(wa.wires_mont).reshape(4 * n, 4)
+        pi_host = None if wa.pi_dev is not None else np.ascontiguousarray(wa.dense_pi_mont)
+        rc, comms, evals, raw = self._native_prover().prove(st, wires_host, wa.wires_dev, pi_host, wa.pi_dev, bl)
+        if rc == ZKP_ERR_DEGREE:
+            raise Error("polynomial degree exceeds the SRS")
+        if rc:
+            self.ctx.check(rc)
+            raise ZkpError(rc)
+        proof = Proof()
+        for i, c in enumerate(COMM_NAMES):
+            setattr(proof, c, g1_from_mont(comms[i]))
+        proof.evaluations = dict(zip(EVAL_NAMES, fr_from_mont(evals)))
+        proof.wire_bytes = bytes(raw)   # as serialised by the native driver (== to_bytes())
+        return proof, list(wa.pi_values)
 
     # ---------------------------------------------------------------- create_proof
     def create_proof(self, blinders, circuit, trace=None):
@@ -144,6 +200,8 @@ class Prover:
         for pi in wa.pi_values:
             tr.append_scalar(b"pi", pi)
         bl = fr_to_mont(blinders)
+        if self.native and trace is None and type(self.keypair) is PlonkParams:
+            return self._create_proof_native(tr, wa, bl)
         proof = Proof()
 
         # round 1: wires -> iNTT -> blind -> commit (src/prover.rs:107-158)

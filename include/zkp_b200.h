@@ -218,6 +218,54 @@ int zkp_poly_lincomb_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, const uint64_t
 int zkp_poly_div_linear_dev(zkp_ctx* ctx, zkp_poly_ref in, const uint64_t point[4], zkp_buf* out,
                             size_t out_off);
 
+/* ---- Prover::create_proof as one call (src/prover.rs:67-474) --------------------------- */
+/* ProvingKey (fields src/key.rs:247-302) as device-resident vectors.  Index order of poly / eval8:
+ * q_m q_l q_r q_o q_c q_4 q_arith q_range q_logic q_fixed_group_add q_variable_group_add
+ * s_sigma_1 s_sigma_2 s_sigma_3 s_sigma_4.  poly[i]: n coefficients; eval8[i]: 8n coset evaluations. */
+typedef struct zkp_proving_key {
+    unsigned k;                    /* n = 2^k gates (padded) */
+    zkp_poly_ref poly[15];
+    zkp_poly_ref eval8[15];
+    zkp_poly_ref linear8;          /* the polynomial X on the 8n coset */
+    zkp_poly_ref sigma_evals[4];   /* sigma_j over the n-domain (round 2 reads them directly) */
+    const zkp_buf* roots;          /* Fft::elements of the n-domain */
+    uint64_t zh_inv[8][4];         /* 1 / Z_H on the coset (period 8) */
+    uint64_t generator[4];         /* w of the n-domain (verifier_key.generator), Montgomery */
+    uint32_t widget_mask;          /* as in zkp_quotient_args */
+} zkp_proving_key;
+
+typedef struct zkp_prover zkp_prover;   /* `Prover`: key + workspace + second stream */
+
+/* The key's buffers and the SRS must outlive the prover.  Allocates the proof workspace
+ * (about 70 n Fr) once; proofs on one prover are serialised by the caller. */
+int zkp_prover_create(zkp_ctx* ctx, const zkp_srs* srs, const zkp_proving_key* key, zkp_prover** out);
+int zkp_prover_destroy(zkp_prover* prover);
+/* One proof.  transcript: the Merlin state after Transcript::base and the public-input appends
+ * (src/prover.rs:54-55,99-105), serialised as 200 Keccak state bytes + pos, pos_begin, cur_flags.
+ * Witness: the four wire columns over the n-domain, 4n x 4 uint64 Montgomery (a | b | o | d), from
+ * host memory (pinned for full link rate) or already on the device; public inputs likewise as a
+ * dense n-vector.  blinders: the 11 scalars `blind` draws, in draw order (src/prover.rs:126-129,193).
+ * Out: the 11 commitments (a b c d z t_low t_mid t_high t_4 w_z w_zw; 12 uint64 each, affine
+ * Montgomery, zeros = identity), the 16 evaluations in `Evaluations` order (Montgomery), and, if
+ * non-null, the 1040-byte wire format (src/prover/proof.rs:36-66) and the transcript state after
+ * the proof.  Returns ZKP_ERR_DEGREE where the reference returns Err (unsatisfied circuit). */
+int zkp_prover_prove(zkp_prover* prover, const uint8_t transcript[203], const uint64_t* wires_host,
+                     const zkp_buf* wires_dev, const uint64_t* pi_host, const zkp_buf* pi_dev,
+                     const uint64_t blinders[44], uint64_t commitments[132], uint64_t evaluations[64],
+                     uint8_t proof_bytes[1040], uint8_t transcript_out[203]);
+
+/* Host-side pieces of the driver, exported so they are testable without a GPU:
+ * Merlin append_message / challenge_bytes on a serialised state, the scalar side of the
+ * linearisation (challenges = alpha beta gamma range logic fixed var z; evals in `Evaluations`
+ * order; out = scalars of q_m q_l q_r q_o q_4 q_c q_range q_logic q_fixed q_var z s_sigma_4),
+ * compressed G1 and the 64-byte wide reduction of challenge_scalar. */
+int zkp_transcript_append(uint8_t state[203], const char* label, const uint8_t* msg, uint32_t len);
+int zkp_transcript_challenge(uint8_t state[203], const char* label, uint8_t* out, uint32_t len);
+int zkp_linearization_scalars(unsigned k, const uint64_t challenges[32], const uint64_t evals[60],
+                              uint64_t out[48]);
+int zkp_g1_compress(const uint64_t xy[12], uint8_t out[48]);
+int zkp_fr_from_wide(const uint8_t bytes[64], uint64_t out_mont[4]);
+
 #ifdef __cplusplus
 }
 #endif

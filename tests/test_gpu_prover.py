@@ -291,3 +291,30 @@ def test_negative_cases_of_the_reference_suites(ctx, name):
         prover.create_proof(bl, badc)
     with pytest.raises(oplonk.ProverError):
         oplonk.create_proof(opk, badc, commit, otr, bl)
+
+
+@pytest.mark.parametrize("name", ["range", "readme", "logic"])
+def test_native_round_driver_equals_python_driven_rounds(ctx, name):
+    """csrc/create_proof.cu (rounds + transcript + linearisation scalars in native code, one C-ABI call)
+    against the same rounds driven call by call from Python -- which the tests above pin to the oracle:
+    identical proofs, identical 1040-byte wire format, from host-resident and device-resident witnesses."""
+    comp = {"range": lambda: circuits.range_circuit(424242), "readme": circuits.readme_circuit,
+            "logic": circuits.logic_curve_circuit}[name]()
+    circ, tau, prover, commit, opk, ovk, otr, bl = both_sides(ctx, comp)
+    assert prover.native
+    nproof, npi = prover.create_proof(bl, circ)
+    assert nproof.wire_bytes == nproof.to_bytes()          # native serialisation == host mirror's
+    prover.native = False
+    pproof, ppi = prover.create_proof(bl, circ)
+    prover.native = True
+    assert nproof == pproof and npi == ppi
+    oproof, opi = oplonk.create_proof(opk, circ, commit, otr, bl)
+    for c in oplonk.Proof.COMM_NAMES:
+        assert getattr(nproof, c) == getattr(oproof, c), c
+    assert nproof.evaluations == oproof.evaluations
+    # witness already in HBM, and a second proof on the same workspace
+    wa = z.WitnessAssignment.from_circuit(circ, circ.n).to_device(ctx)
+    dproof, _ = prover.create_proof(bl, wa)
+    assert dproof == nproof and dproof.wire_bytes == nproof.wire_bytes
+    assert z.Proof.from_bytes(nproof.wire_bytes) == nproof
+    assert oplonk.verify(ovk, circ.n, nproof, circ.pi_indexes, npi, otr, oplonk.trapdoor_kzg_check(tau))
