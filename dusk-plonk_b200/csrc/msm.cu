@@ -27,6 +27,7 @@
 // Addition in G1 is commutative and the result is normalised to affine, so the output is
 // bit-identical to any correct CPU evaluation regardless of accumulation order.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -58,6 +59,7 @@ struct MsmScratch {
     int acc_variant = 3;
     bool acc_variant_forced = false;
     int acc_blocks_per_sm2 = 0;   // occupancy of the 2-blocks/SM build used for small jobs
+    bool reduce_coop = true;      // four-warp cooperative bucket reduction (ZKP_MSM_REDUCE=legacy: one warp per sum)
 };
 
 static constexpr uint32_t DIGIT_ZERO = 0xffffffffu;
@@ -234,7 +236,9 @@ __global__ void msm_scatter_kernel(const __grid_constant__ MsmBatch batch, const
 // MB = resident blocks per SM the register allocation is bounded for (2: 172 registers, 4: 128
 // registers with ~70 bytes of spill): more warps hide the dependent IMAD chains (ncu: `wait`
 // stalls dominate at 2 blocks / SM).
-template <int MB>
+// PF: software-pipelined loads -- the index and the table point of entry j + 1 are requested before the
+// mixed addition of entry j starts, so the random 96-byte gather is hidden behind ~10 multiplications.
+template <int MB, bool PF = false>
 __global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const g1_affine* table, const uint32_t* sorted,
                                                             const uint32_t* offsets, const uint32_t* counts,
                                                             const uint32_t* meta, uint32_t B, uint32_t L,
@@ -260,7 +264,23 @@ __global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const g1_affine
     uint32_t seg = start;
     bool first = true;
     g1_xyzz acc = g1_xyzz::inf();
+    uint32_t e_next = 0;
+    g1_affine q_next;
+    if (PF) {
+        e_next = sorted[start];
+        q_next = msm_ld_affine(table + (e_next & 0x7fffffffu));
+    }
     for (uint32_t j = start; j < end; j++) {
+        uint32_t e;
+        g1_affine q;
+        if (PF) {
+            e = e_next;
+            q = q_next;
+            if (j + 1 < end) {
+                e_next = sorted[j + 1];
+                q_next = msm_ld_affine(table + (e_next & 0x7fffffffu));
+            }
+        }
         if (j >= bend) {  // the bucket ended inside this chunk
             if (seg == bbeg) buckets[bk] = acc;          // ... and began inside it too: complete
             else slots[2 * t] = acc;                     // continuation from the previous chunk
@@ -270,8 +290,10 @@ __global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const g1_affine
             seg = j;
             acc = g1_xyzz::inf();
         }
-        const uint32_t e = sorted[j];
-        g1_affine q = msm_ld_affine(table + (e & 0x7fffffffu));
+        if (!PF) {
+            e = sorted[j];
+            q = msm_ld_affine(table + (e & 0x7fffffffu));
+        }
         if (e & 0x80000000u) q.y = neg(q.y);
         xyzz_madd(acc, q);
     }
@@ -409,6 +431,258 @@ __global__ void __launch_bounds__(32) msm_final_sum_kernel(const g1_xyzz* planes
     if (lane == 0) out[blockIdx.x] = v;
 }
 
+// ---- the same reduction with cooperative point arithmetic --------------------------------------
+// The reduction is a dependency chain (~30 point additions + c doublings deep) on a mostly idle GPU,
+// and one point addition is 14 dependent Fq multiplications when a single thread runs it.  Here a
+// block of four warps -- one per SM sub-partition -- adds 32 pairs of points at a time: warp w takes
+// the w-th multiplication of each dependency level (add: 4 levels instead of 14 multiplications,
+// double: 3 instead of 9), operands and intermediates live in shared memory in limb-major order
+// (conflict-free), one barrier per level.  Exceptional lanes (an operand at infinity, equal or
+// opposite points) are flagged and redone by warp 0 with the generic formulas, so results are exact.
+enum { AX, AY, AZZ, AZZZ, BX, BY, BZZ, BZZZ, TU1, TU2, TS1, TS2, TP, TPP, TR, TRR, TZZ, TZZZ, TPPP, TQ, TT, TV, NSLOT };
+struct CoopSm {
+    uint32_t s[NSLOT][12][32];
+    uint32_t flag[32];
+};
+
+__device__ __forceinline__ fq_t cs_ld(const CoopSm& sm, int slot, unsigned l) {
+    fq_t r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = sm.s[slot][i][l];
+    return r;
+}
+__device__ __forceinline__ void cs_st(CoopSm& sm, int slot, unsigned l, const fq_t& v) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) sm.s[slot][i][l] = v.l[i];
+}
+__device__ __forceinline__ g1_xyzz cs_ld_point(const CoopSm& sm, int base, unsigned l) {
+    g1_xyzz r;
+    r.x = cs_ld(sm, base, l); r.y = cs_ld(sm, base + 1, l); r.zz = cs_ld(sm, base + 2, l); r.zzz = cs_ld(sm, base + 3, l);
+    return r;
+}
+__device__ __forceinline__ void cs_st_point(CoopSm& sm, int base, unsigned l, const g1_xyzz& v) {
+    cs_st(sm, base, l, v.x); cs_st(sm, base + 1, l, v.y); cs_st(sm, base + 2, l, v.zz); cs_st(sm, base + 3, l, v.zzz);
+}
+// warp w fetches coordinate w of lane l's point (nullptr = infinity) into slot base + w
+__device__ __forceinline__ void cs_fetch(CoopSm& sm, int base, unsigned w, unsigned l, const g1_xyzz* p) {
+    if (p) {
+        const uint4* q = reinterpret_cast<const uint4*>(p) + 3 * w;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const uint4 v = q[i];
+            sm.s[base + w][4 * i][l] = v.x; sm.s[base + w][4 * i + 1][l] = v.y;
+            sm.s[base + w][4 * i + 2][l] = v.z; sm.s[base + w][4 * i + 3][l] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 12; i++) sm.s[base + w][i][l] = 0;
+    }
+}
+__device__ __forceinline__ void cs_emit(const CoopSm& sm, int base, unsigned w, unsigned l, g1_xyzz* p) {
+    uint4* q = reinterpret_cast<uint4*>(p) + 3 * w;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        q[i] = make_uint4(sm.s[base + w][4 * i][l], sm.s[base + w][4 * i + 1][l], sm.s[base + w][4 * i + 2][l],
+                          sm.s[base + w][4 * i + 3][l]);
+}
+
+// exceptional lanes only (rare): kept out of line so the common path stays within its register budget
+__device__ __noinline__ void coop_add_slow(CoopSm& sm, unsigned l) {
+    g1_xyzz a = cs_ld_point(sm, AX, l);
+    const g1_xyzz b = cs_ld_point(sm, BX, l);
+    xyzz_add(a, b);
+    cs_st_point(sm, AX, l, a);
+}
+__device__ __noinline__ void coop_dbl_slow(CoopSm& sm, unsigned l) {
+    g1_xyzz a = cs_ld_point(sm, AX, l);
+    xyzz_dbl(a);
+    cs_st_point(sm, AX, l, a);
+}
+
+// A[l] <- A[l] + B[l] for lanes l < nact.  Called by all 128 threads; ends with a barrier.
+__device__ __noinline__ void coop_add(CoopSm& sm, unsigned nact) {
+    const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const bool on = l < nact;
+    if (on) {
+        if (w == 0) {
+            const fq_t azz = cs_ld(sm, AZZ, l), bzz = cs_ld(sm, BZZ, l);
+            sm.flag[l] = (azz.is_zero() ? 1u : 0u) | (bzz.is_zero() ? 2u : 0u);
+            cs_st(sm, TU1, l, cs_ld(sm, AX, l) * bzz);
+        } else if (w == 1) {
+            cs_st(sm, TU2, l, cs_ld(sm, BX, l) * cs_ld(sm, AZZ, l));
+        } else if (w == 2) {
+            cs_st(sm, TS1, l, cs_ld(sm, AY, l) * cs_ld(sm, BZZZ, l));
+        } else {
+            cs_st(sm, TS2, l, cs_ld(sm, BY, l) * cs_ld(sm, AZZZ, l));
+        }
+    }
+    __syncthreads();
+    if (on) {
+        if (w == 0) {
+            const fq_t P = cs_ld(sm, TU2, l) - cs_ld(sm, TU1, l);
+            if (P.is_zero()) sm.flag[l] |= 4u;
+            cs_st(sm, TP, l, P);
+            cs_st(sm, TPP, l, sqr(P));
+        } else if (w == 1) {
+            const fq_t R = cs_ld(sm, TS2, l) - cs_ld(sm, TS1, l);
+            cs_st(sm, TR, l, R);
+            cs_st(sm, TRR, l, sqr(R));
+        } else if (w == 2) {
+            cs_st(sm, TZZ, l, cs_ld(sm, AZZ, l) * cs_ld(sm, BZZ, l));
+        } else {
+            cs_st(sm, TZZZ, l, cs_ld(sm, AZZZ, l) * cs_ld(sm, BZZZ, l));
+        }
+    }
+    __syncthreads();
+    const bool fast = on && sm.flag[l] == 0;
+    if (fast) {
+        if (w == 0) cs_st(sm, TPPP, l, cs_ld(sm, TP, l) * cs_ld(sm, TPP, l));
+        else if (w == 1) cs_st(sm, TQ, l, cs_ld(sm, TU1, l) * cs_ld(sm, TPP, l));
+        else if (w == 2) cs_st(sm, AZZ, l, cs_ld(sm, TZZ, l) * cs_ld(sm, TPP, l));
+    }
+    __syncthreads();
+    if (fast) {
+        if (w == 0) {
+            const fq_t Q = cs_ld(sm, TQ, l);
+            const fq_t X3 = cs_ld(sm, TRR, l) - cs_ld(sm, TPPP, l) - dbl(Q);
+            cs_st(sm, TT, l, cs_ld(sm, TR, l) * (Q - X3));
+            cs_st(sm, AX, l, X3);
+        } else if (w == 1) {
+            cs_st(sm, TV, l, cs_ld(sm, TS1, l) * cs_ld(sm, TPPP, l));
+        } else if (w == 2) {
+            cs_st(sm, AZZZ, l, cs_ld(sm, TZZZ, l) * cs_ld(sm, TPPP, l));
+        }
+    }
+    __syncthreads();
+    if (w == 0 && on) {
+        if (fast) {
+            cs_st(sm, AY, l, cs_ld(sm, TT, l) - cs_ld(sm, TV, l));
+        } else {  // infinity / doubling / cancellation: generic formulas on the untouched operands
+            coop_add_slow(sm, l);
+        }
+    }
+    __syncthreads();
+}
+
+// A[l] <- 2 A[l] for lanes l < nact.
+__device__ __noinline__ void coop_dbl(CoopSm& sm, unsigned nact) {
+    const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const bool on = l < nact;
+    if (on) {
+        if (w == 0) {
+            const fq_t y = cs_ld(sm, AY, l);
+            sm.flag[l] = (cs_ld(sm, AZZ, l).is_zero() ? 1u : 0u) | (y.is_zero() ? 2u : 0u);
+            const fq_t U = dbl(y);
+            cs_st(sm, TU1, l, U);
+            cs_st(sm, TPP, l, sqr(U));             // V
+        } else if (w == 1) {
+            const fq_t X2 = sqr(cs_ld(sm, AX, l));
+            cs_st(sm, TR, l, dbl(X2) + X2);        // M
+        }
+    }
+    __syncthreads();
+    const bool fast = on && sm.flag[l] == 0;
+    if (fast) {
+        if (w == 0) cs_st(sm, TPPP, l, cs_ld(sm, TU1, l) * cs_ld(sm, TPP, l));        // W
+        else if (w == 1) cs_st(sm, TQ, l, cs_ld(sm, AX, l) * cs_ld(sm, TPP, l));      // S
+        else if (w == 2) cs_st(sm, TRR, l, sqr(cs_ld(sm, TR, l)));                    // M^2
+        else cs_st(sm, AZZ, l, cs_ld(sm, TPP, l) * cs_ld(sm, AZZ, l));
+    }
+    __syncthreads();
+    if (fast) {
+        if (w == 0) {
+            const fq_t S = cs_ld(sm, TQ, l);
+            const fq_t X3 = cs_ld(sm, TRR, l) - dbl(S);
+            cs_st(sm, TT, l, cs_ld(sm, TR, l) * (S - X3));
+            cs_st(sm, AX, l, X3);
+        } else if (w == 1) {
+            cs_st(sm, TV, l, cs_ld(sm, TPPP, l) * cs_ld(sm, AY, l));
+        } else if (w == 2) {
+            cs_st(sm, AZZZ, l, cs_ld(sm, TPPP, l) * cs_ld(sm, AZZZ, l));
+        }
+    }
+    __syncthreads();
+    if (w == 0 && on) {
+        if (fast) {
+            cs_st(sm, AY, l, cs_ld(sm, TT, l) - cs_ld(sm, TV, l));
+        } else {
+            coop_dbl_slow(sm, l);
+        }
+    }
+    __syncthreads();
+}
+
+// A[0] <- sum of item(0 .. len): lane l adds up items l, l + 32, .. (all lanes busy), then a tree over
+// the lanes.  item(i) returns the point's address or nullptr for infinity.
+template <class F>
+__device__ __forceinline__ void coop_block_sum(CoopSm& sm, uint32_t len, F item) {
+    const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    cs_fetch(sm, AX, w, l, l < len ? item(l) : nullptr);
+    __syncthreads();
+    for (uint32_t i0 = 32; i0 < len; i0 += 32) {
+        cs_fetch(sm, BX, w, l, i0 + l < len ? item(i0 + l) : nullptr);
+        __syncthreads();
+        coop_add(sm, 32);
+    }
+    unsigned s = 16;
+    while (s >= len && s > 0) s >>= 1;   // lanes >= len hold infinity: skip the empty levels
+    for (; s > 0; s >>= 1) {
+        if (l < s) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) sm.s[BX + w][i][l] = sm.s[AX + w][i][l + s];
+        }
+        __syncthreads();
+        coop_add(sm, s);
+    }
+}
+
+// grid (nrows + ncols, nb), 128 threads: rc[pb][x] = row sum (x < nrows) or column sum of the weight grid
+__global__ void __launch_bounds__(128, 4) msm_rowcol_coop_kernel(const g1_xyzz* buckets, uint32_t B, unsigned h,
+                                                              uint32_t nrows, uint32_t ncols, g1_xyzz* rc) {
+    __shared__ CoopSm sm;
+    const unsigned pb = blockIdx.y;
+    const uint32_t x = blockIdx.x;
+    buckets += (size_t)pb * B;
+    const bool is_row = x < nrows;
+    const uint32_t len = is_row ? ncols : nrows;
+    coop_block_sum(sm, len, [&](uint32_t i) -> const g1_xyzz* {
+        const uint32_t wgt = is_row ? (x << h) + i : (i << h) + (x - nrows);
+        return (wgt >= 1 && wgt <= B) ? buckets + (wgt - 1) : nullptr;
+    });
+    if ((threadIdx.x & 31) == 0) cs_emit(sm, AX, threadIdx.x >> 5, 0, rc + (size_t)pb * (nrows + ncols) + x);
+}
+
+// grid (planes_r + planes_c, nb), 128 threads: block j sums the rows (columns) whose index has bit j set
+// and applies the plane's factor 2^(h + j) (2^j) by doublings.
+__global__ void __launch_bounds__(128, 4) msm_planes_coop_kernel(const g1_xyzz* rc, unsigned h, uint32_t nrows,
+                                                              uint32_t ncols, unsigned planes_r, g1_xyzz* planes) {
+    __shared__ CoopSm sm;
+    const unsigned pb = blockIdx.y;
+    rc += (size_t)pb * (nrows + ncols);
+    const bool is_row = blockIdx.x < planes_r;
+    const unsigned j = is_row ? blockIdx.x : blockIdx.x - planes_r;
+    const g1_xyzz* arr = is_row ? rc : rc + nrows;
+    const uint32_t len = is_row ? nrows : ncols;
+    // indices below len with bit j set, enumerated densely: m -> x
+    const uint32_t period = 2u << j, rem = len & (period - 1);
+    const uint32_t cnt = ((len >> (j + 1)) << j) + (rem > (1u << j) ? rem - (1u << j) : 0u);
+    coop_block_sum(sm, cnt, [&](uint32_t m) -> const g1_xyzz* {
+        const uint32_t xi = ((m >> j) << (j + 1)) | (1u << j) | (m & ((1u << j) - 1));
+        return arr + xi;
+    });
+    const unsigned dbl_n = is_row ? h + j : j;
+    for (unsigned i = 0; i < dbl_n; i++) coop_dbl(sm, 1);
+    if ((threadIdx.x & 31) == 0) cs_emit(sm, AX, threadIdx.x >> 5, 0, planes + (size_t)pb * 32 + blockIdx.x);
+}
+
+// one block per polynomial: sum of its <= 32 weighted plane sums
+__global__ void __launch_bounds__(128, 4) msm_final_coop_kernel(const g1_xyzz* planes, unsigned nplanes, g1_xyzz* out) {
+    __shared__ CoopSm sm;
+    planes += (size_t)blockIdx.x * 32;
+    coop_block_sum(sm, nplanes, [&](uint32_t m) -> const g1_xyzz* { return planes + m; });
+    if ((threadIdx.x & 31) == 0) cs_emit(sm, AX, threadIdx.x >> 5, 0, out + blockIdx.x);
+}
+
 // T[w][i] = 2^c * T[w-1][i]: one thread per point walks the windows (load-time only).
 __global__ void __launch_bounds__(128) srs_table_window_kernel(g1_affine* table, size_t n, unsigned c, unsigned W) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -532,17 +806,29 @@ static inline fq inv(const fq& a) {  // a^(p-2)
 }
 }  // namespace hostfq
 
-// x = X / ZZ, y = Y / ZZZ with 1/ZZ = (ZZ / ZZZ)^2
-static g1_affine host_xyzz_to_affine(const g1_xyzz& a) {
-    g1_affine r = g1_affine::inf();
-    if (a.is_inf()) return r;
-    hostfq::fq X, Y, ZZ, ZZZ;
-    memcpy(X.l, a.x.l, 48); memcpy(Y.l, a.y.l, 48); memcpy(ZZ.l, a.zz.l, 48); memcpy(ZZZ.l, a.zzz.l, 48);
-    const hostfq::fq t = hostfq::inv(ZZZ);
-    const hostfq::fq zi = hostfq::mul(ZZ, t);
-    const hostfq::fq x = hostfq::mul(X, hostfq::mul(zi, zi)), y = hostfq::mul(Y, t);
-    memcpy(r.x.l, x.l, 48); memcpy(r.y.l, y.l, 48);
-    return r;
+// x = X / ZZ, y = Y / ZZZ with 1/ZZ = (ZZ / ZZZ)^2.  The count <= MSM_MAX_BATCH points of one commit
+// group share a single Fermat inversion (Montgomery's trick: prefix products, one inverse, unwind).
+static void host_xyzz_to_affine_batch(const g1_xyzz* a, unsigned count, g1_affine* out) {
+    hostfq::fq zzz[MSM_MAX_BATCH], pre[MSM_MAX_BATCH], acc;
+    memcpy(acc.l, hostfq::ONE, 48);
+    for (unsigned i = 0; i < count; i++) {
+        out[i] = g1_affine::inf();
+        if (a[i].is_inf()) continue;
+        memcpy(zzz[i].l, a[i].zzz.l, 48);
+        pre[i] = acc;                       // product of the finite ZZZ before i
+        acc = hostfq::mul(acc, zzz[i]);
+    }
+    hostfq::fq inv = hostfq::inv(acc);      // 1 / (product of every finite ZZZ)
+    for (unsigned i = count; i-- > 0;) {
+        if (a[i].is_inf()) continue;
+        const hostfq::fq t = hostfq::mul(inv, pre[i]);   // 1 / ZZZ_i
+        inv = hostfq::mul(inv, zzz[i]);
+        hostfq::fq X, Y, ZZ;
+        memcpy(X.l, a[i].x.l, 48); memcpy(Y.l, a[i].y.l, 48); memcpy(ZZ.l, a[i].zz.l, 48);
+        const hostfq::fq zi = hostfq::mul(ZZ, t);
+        const hostfq::fq x = hostfq::mul(X, hostfq::mul(zi, zi)), y = hostfq::mul(Y, t);
+        memcpy(out[i].x.l, x.l, 48); memcpy(out[i].y.l, y.l, 48);
+    }
 }
 
 // Window width for an SRS of n powers, calibrated on B200 (bench/sweep_window.sh): the n * W mixed
@@ -603,8 +889,9 @@ static int msm_scratch(zkp_ctx* ctx, MsmScratch** out) {
             mb = atoi(e);
             ctx->msm->acc_variant_forced = true;
         }
+        if (const char* e = getenv("ZKP_MSM_REDUCE")) ctx->msm->reduce_coop = strcmp(e, "legacy") != 0;
         if (mb < 2) mb = 2;
-        if (mb > 6) mb = 6;
+        if (mb > 7) mb = 7;   // 7 = the 2-blocks/SM build with software-pipelined loads
         ctx->msm->acc_variant = mb;
         int nb = 0;
         switch (mb) {
@@ -612,7 +899,8 @@ static int msm_scratch(zkp_ctx* ctx, MsmScratch** out) {
             case 3: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<3>, 128, 0)); break;
             case 4: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<4>, 128, 0)); break;
             case 5: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<5>, 128, 0)); break;
-            default: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<6>, 128, 0)); break;
+            case 6: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<6>, 128, 0)); break;
+            default: ZKP_CUDA(ctx, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<2, true>, 128, 0))); break;
         }
         ctx->msm->acc_blocks_per_sm = nb > 0 ? nb : 1;
         int nb2 = 0;
@@ -694,7 +982,7 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     // small jobs (about one wave) run best with the unconstrained 2-blocks/SM build, large ones with 3
     const int variant = (s->acc_variant_forced || E * nb >= ((size_t)1 << 23)) ? s->acc_variant : 2;
     const size_t resident =
-        (size_t)ctx->sm_count * (variant == 2 ? s->acc_blocks_per_sm2 : s->acc_blocks_per_sm) * 128;
+        (size_t)ctx->sm_count * ((variant == 2 || variant == 7) ? s->acc_blocks_per_sm2 : s->acc_blocks_per_sm) * 128;
     size_t L = (E * nb + resident - 1) / resident;
     if (L < 8) L = 8;
     if (L > 128) L = 128;
@@ -749,14 +1037,15 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     {
     ProfScope prof(ctx, "msm_accumulate");
     const dim3 agrid((nchunks + 127) / 128, nb);
-#define ZKP_ACC(MB) msm_accumulate_kernel<MB><<<agrid, 128, 0, st>>>( \
+#define ZKP_ACC(...) msm_accumulate_kernel<__VA_ARGS__><<<agrid, 128, 0, st>>>( \
         srs->d, s->sorted, s->offsets, s->counts, s->meta, B, (uint32_t)L, nchunks, E, s->buckets, s->slots)
     switch (variant) {
         case 2: ZKP_ACC(2); break;
         case 3: ZKP_ACC(3); break;
         case 4: ZKP_ACC(4); break;
         case 5: ZKP_ACC(5); break;
-        default: ZKP_ACC(6); break;
+        case 6: ZKP_ACC(6); break;
+        default: ZKP_ACC(2, true); break;
     }
 #undef ZKP_ACC
     ZKP_LAUNCHED(ctx);
@@ -775,12 +1064,21 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
             ZKP_LAUNCHED(ctx);
         }
     }
-    msm_rowcol_kernel<<<dim3(nrows + ncols, nb), 32, 0, st>>>(s->buckets, B, h, nrows, ncols, rowcol);
-    ZKP_LAUNCHED(ctx);
-    msm_weighted_planes_kernel<<<dim3(planes_r + planes_c, nb), 32, 0, st>>>(rowcol, h, nrows, ncols, planes_r, planes);
-    ZKP_LAUNCHED(ctx);
-    msm_final_sum_kernel<<<nb, 32, 0, st>>>(planes, planes_r + planes_c, sums);
-    ZKP_LAUNCHED(ctx);
+    if (s->reduce_coop) {
+        msm_rowcol_coop_kernel<<<dim3(nrows + ncols, nb), 128, 0, st>>>(s->buckets, B, h, nrows, ncols, rowcol);
+        ZKP_LAUNCHED(ctx);
+        msm_planes_coop_kernel<<<dim3(planes_r + planes_c, nb), 128, 0, st>>>(rowcol, h, nrows, ncols, planes_r, planes);
+        ZKP_LAUNCHED(ctx);
+        msm_final_coop_kernel<<<nb, 128, 0, st>>>(planes, planes_r + planes_c, sums);
+        ZKP_LAUNCHED(ctx);
+    } else {
+        msm_rowcol_kernel<<<dim3(nrows + ncols, nb), 32, 0, st>>>(s->buckets, B, h, nrows, ncols, rowcol);
+        ZKP_LAUNCHED(ctx);
+        msm_weighted_planes_kernel<<<dim3(planes_r + planes_c, nb), 32, 0, st>>>(rowcol, h, nrows, ncols, planes_r, planes);
+        ZKP_LAUNCHED(ctx);
+        msm_final_sum_kernel<<<nb, 32, 0, st>>>(planes, planes_r + planes_c, sums);
+        ZKP_LAUNCHED(ctx);
+    }
     }
     // the single inversion of each conversion to affine runs on the host (one Fq Fermat chain
     // would occupy one GPU thread for ~0.6 ms)
@@ -789,10 +1087,8 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     ZKP_CUDA(ctx, cudaMemcpyAsync(hs, sums, nb * sizeof(g1_xyzz), cudaMemcpyDeviceToHost, st));
     ZKP_CUDA(ctx, cudaMemcpyAsync(hm, s->meta, 4 * MSM_MAX_BATCH * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     ZKP_CUDA(ctx, cudaStreamSynchronize(st));
-    for (unsigned b = 0; b < nb; b++) {
-        overflow[b] = hm[4 * b + 2] != 0;
-        out_host[b] = host_xyzz_to_affine(hs[b]);
-    }
+    for (unsigned b = 0; b < nb; b++) overflow[b] = hm[4 * b + 2] != 0;
+    host_xyzz_to_affine_batch(hs, nb, out_host);
     return ZKP_OK;
 }
 
