@@ -236,9 +236,7 @@ __global__ void msm_scatter_kernel(const __grid_constant__ MsmBatch batch, const
 // MB = resident blocks per SM the register allocation is bounded for (2: 172 registers, 4: 128
 // registers with ~70 bytes of spill): more warps hide the dependent IMAD chains (ncu: `wait`
 // stalls dominate at 2 blocks / SM).
-// PF: software-pipelined loads -- the index and the table point of entry j + 1 are requested before the
-// mixed addition of entry j starts, so the random 96-byte gather is hidden behind ~10 multiplications.
-template <int MB, bool PF = false>
+template <int MB>
 __global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const g1_affine* table, const uint32_t* sorted,
                                                             const uint32_t* offsets, const uint32_t* counts,
                                                             const uint32_t* meta, uint32_t B, uint32_t L,
@@ -264,23 +262,7 @@ __global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const g1_affine
     uint32_t seg = start;
     bool first = true;
     g1_xyzz acc = g1_xyzz::inf();
-    uint32_t e_next = 0;
-    g1_affine q_next;
-    if (PF) {
-        e_next = sorted[start];
-        q_next = msm_ld_affine(table + (e_next & 0x7fffffffu));
-    }
     for (uint32_t j = start; j < end; j++) {
-        uint32_t e;
-        g1_affine q;
-        if (PF) {
-            e = e_next;
-            q = q_next;
-            if (j + 1 < end) {
-                e_next = sorted[j + 1];
-                q_next = msm_ld_affine(table + (e_next & 0x7fffffffu));
-            }
-        }
         if (j >= bend) {  // the bucket ended inside this chunk
             if (seg == bbeg) buckets[bk] = acc;          // ... and began inside it too: complete
             else slots[2 * t] = acc;                     // continuation from the previous chunk
@@ -290,10 +272,8 @@ __global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const g1_affine
             seg = j;
             acc = g1_xyzz::inf();
         }
-        if (!PF) {
-            e = sorted[j];
-            q = msm_ld_affine(table + (e & 0x7fffffffu));
-        }
+        const uint32_t e = sorted[j];
+        g1_affine q = msm_ld_affine(table + (e & 0x7fffffffu));
         if (e & 0x80000000u) q.y = neg(q.y);
         xyzz_madd(acc, q);
     }
@@ -499,10 +479,10 @@ __device__ __noinline__ void coop_dbl_slow(CoopSm& sm, unsigned l) {
     cs_st_point(sm, AX, l, a);
 }
 
-// A[l] <- A[l] + B[l] for lanes l < nact.  Called by all 128 threads; ends with a barrier.
-__device__ __noinline__ void coop_add(CoopSm& sm, unsigned nact) {
+// A[l] <- A[l] + B[l] for the lanes whose threads pass on = true (the four warps agree per lane).
+// Called by all 128 threads; ends with a barrier.
+__device__ __noinline__ void coop_add(CoopSm& sm, bool on) {
     const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    const bool on = l < nact;
     if (on) {
         if (w == 0) {
             const fq_t azz = cs_ld(sm, AZZ, l), bzz = cs_ld(sm, BZZ, l);
@@ -564,10 +544,9 @@ __device__ __noinline__ void coop_add(CoopSm& sm, unsigned nact) {
     __syncthreads();
 }
 
-// A[l] <- 2 A[l] for lanes l < nact.
-__device__ __noinline__ void coop_dbl(CoopSm& sm, unsigned nact) {
+// A[l] <- 2 A[l] for the lanes with on = true.
+__device__ __noinline__ void coop_dbl(CoopSm& sm, bool on) {
     const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    const bool on = l < nact;
     if (on) {
         if (w == 0) {
             const fq_t y = cs_ld(sm, AY, l);
@@ -612,44 +591,56 @@ __device__ __noinline__ void coop_dbl(CoopSm& sm, unsigned nact) {
     __syncthreads();
 }
 
-// A[0] <- sum of item(0 .. len): lane l adds up items l, l + 32, .. (all lanes busy), then a tree over
-// the lanes.  item(i) returns the point's address or nullptr for infinity.
-template <class F>
-__device__ __forceinline__ void coop_block_sum(CoopSm& sm, uint32_t len, F item) {
+// The block's 32 lanes are split into groups of `lpo` (a power of two): group o sums item(o, 0 .. len)
+// into A[o * lpo].  Lane p of a group adds up items p, p + lpo, .. (every lane busy, no idle tree
+// levels), then a log2(lpo)-level tree folds the group.  Fewer lanes per output = less idle tree work
+// but a longer dependency chain: the launcher picks lpo from how full the GPU is.
+// item(o, i) returns the point's address or nullptr for infinity; valid(o) = group o has an output.
+template <class F, class V>
+__device__ __forceinline__ void coop_group_sum(CoopSm& sm, unsigned lpo, uint32_t len, V valid, F item) {
     const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    cs_fetch(sm, AX, w, l, l < len ? item(l) : nullptr);
+    const unsigned o = l / lpo, p = l & (lpo - 1);
+    const bool ok = valid(o);
+    cs_fetch(sm, AX, w, l, (ok && p < len) ? item(o, p) : nullptr);
     __syncthreads();
-    for (uint32_t i0 = 32; i0 < len; i0 += 32) {
-        cs_fetch(sm, BX, w, l, i0 + l < len ? item(i0 + l) : nullptr);
+    for (uint32_t i0 = lpo; i0 < len; i0 += lpo) {
+        cs_fetch(sm, BX, w, l, (ok && i0 + p < len) ? item(o, i0 + p) : nullptr);
         __syncthreads();
-        coop_add(sm, 32);
+        coop_add(sm, ok);
     }
-    unsigned s = 16;
+    unsigned s = lpo >> 1;
     while (s >= len && s > 0) s >>= 1;   // lanes >= len hold infinity: skip the empty levels
     for (; s > 0; s >>= 1) {
-        if (l < s) {
+        if (p < s) {
 #pragma unroll
             for (int i = 0; i < 12; i++) sm.s[BX + w][i][l] = sm.s[AX + w][i][l + s];
         }
         __syncthreads();
-        coop_add(sm, s);
+        coop_add(sm, ok && p < s);
     }
 }
 
-// grid (nrows + ncols, nb), 128 threads: rc[pb][x] = row sum (x < nrows) or column sum of the weight grid
+// grid (ceil(nrows / R) + ceil(ncols / R), nb), 128 threads, R = 32 / lpo outputs per block:
+// rc[pb][x] = row sum (x < nrows) or column sum of the weight grid
 __global__ void __launch_bounds__(128, 4) msm_rowcol_coop_kernel(const g1_xyzz* buckets, uint32_t B, unsigned h,
-                                                              uint32_t nrows, uint32_t ncols, g1_xyzz* rc) {
+                                                                 uint32_t nrows, uint32_t ncols, unsigned lpo,
+                                                                 g1_xyzz* rc) {
     __shared__ CoopSm sm;
-    const unsigned pb = blockIdx.y;
-    const uint32_t x = blockIdx.x;
+    const unsigned pb = blockIdx.y, R = 32 / lpo;
+    const uint32_t row_blocks = (nrows + R - 1) / R;
+    const bool is_row = blockIdx.x < row_blocks;
+    const uint32_t x0 = is_row ? blockIdx.x * R : (blockIdx.x - row_blocks) * R;   // first row / column of the block
+    const uint32_t count = is_row ? nrows : ncols, len = is_row ? ncols : nrows;
     buckets += (size_t)pb * B;
-    const bool is_row = x < nrows;
-    const uint32_t len = is_row ? ncols : nrows;
-    coop_block_sum(sm, len, [&](uint32_t i) -> const g1_xyzz* {
-        const uint32_t wgt = is_row ? (x << h) + i : (i << h) + (x - nrows);
-        return (wgt >= 1 && wgt <= B) ? buckets + (wgt - 1) : nullptr;
-    });
-    if ((threadIdx.x & 31) == 0) cs_emit(sm, AX, threadIdx.x >> 5, 0, rc + (size_t)pb * (nrows + ncols) + x);
+    coop_group_sum(sm, lpo, len,
+        [&](unsigned o) { return x0 + o < count; },
+        [&](unsigned o, uint32_t i) -> const g1_xyzz* {
+            const uint32_t wgt = is_row ? ((x0 + o) << h) + i : (i << h) + (x0 + o);
+            return (wgt >= 1 && wgt <= B) ? buckets + (wgt - 1) : nullptr;
+        });
+    const unsigned l = threadIdx.x & 31, o = l / lpo;
+    if ((l & (lpo - 1)) == 0 && x0 + o < count)
+        cs_emit(sm, AX, threadIdx.x >> 5, l, rc + (size_t)pb * (nrows + ncols) + (is_row ? 0 : nrows) + x0 + o);
 }
 
 // grid (planes_r + planes_c, nb), 128 threads: block j sums the rows (columns) whose index has bit j set
@@ -666,12 +657,12 @@ __global__ void __launch_bounds__(128, 4) msm_planes_coop_kernel(const g1_xyzz* 
     // indices below len with bit j set, enumerated densely: m -> x
     const uint32_t period = 2u << j, rem = len & (period - 1);
     const uint32_t cnt = ((len >> (j + 1)) << j) + (rem > (1u << j) ? rem - (1u << j) : 0u);
-    coop_block_sum(sm, cnt, [&](uint32_t m) -> const g1_xyzz* {
+    coop_group_sum(sm, 32, cnt, [](unsigned) { return true; }, [&](unsigned, uint32_t m) -> const g1_xyzz* {
         const uint32_t xi = ((m >> j) << (j + 1)) | (1u << j) | (m & ((1u << j) - 1));
         return arr + xi;
     });
     const unsigned dbl_n = is_row ? h + j : j;
-    for (unsigned i = 0; i < dbl_n; i++) coop_dbl(sm, 1);
+    for (unsigned i = 0; i < dbl_n; i++) coop_dbl(sm, (threadIdx.x & 31) == 0);
     if ((threadIdx.x & 31) == 0) cs_emit(sm, AX, threadIdx.x >> 5, 0, planes + (size_t)pb * 32 + blockIdx.x);
 }
 
@@ -679,7 +670,8 @@ __global__ void __launch_bounds__(128, 4) msm_planes_coop_kernel(const g1_xyzz* 
 __global__ void __launch_bounds__(128, 4) msm_final_coop_kernel(const g1_xyzz* planes, unsigned nplanes, g1_xyzz* out) {
     __shared__ CoopSm sm;
     planes += (size_t)blockIdx.x * 32;
-    coop_block_sum(sm, nplanes, [&](uint32_t m) -> const g1_xyzz* { return planes + m; });
+    coop_group_sum(sm, 32, nplanes, [](unsigned) { return true; },
+                   [&](unsigned, uint32_t m) -> const g1_xyzz* { return planes + m; });
     if ((threadIdx.x & 31) == 0) cs_emit(sm, AX, threadIdx.x >> 5, 0, out + blockIdx.x);
 }
 
@@ -891,7 +883,7 @@ static int msm_scratch(zkp_ctx* ctx, MsmScratch** out) {
         }
         if (const char* e = getenv("ZKP_MSM_REDUCE")) ctx->msm->reduce_coop = strcmp(e, "legacy") != 0;
         if (mb < 2) mb = 2;
-        if (mb > 7) mb = 7;   // 7 = the 2-blocks/SM build with software-pipelined loads
+        if (mb > 6) mb = 6;
         ctx->msm->acc_variant = mb;
         int nb = 0;
         switch (mb) {
@@ -899,8 +891,7 @@ static int msm_scratch(zkp_ctx* ctx, MsmScratch** out) {
             case 3: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<3>, 128, 0)); break;
             case 4: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<4>, 128, 0)); break;
             case 5: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<5>, 128, 0)); break;
-            case 6: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<6>, 128, 0)); break;
-            default: ZKP_CUDA(ctx, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<2, true>, 128, 0))); break;
+            default: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<6>, 128, 0)); break;
         }
         ctx->msm->acc_blocks_per_sm = nb > 0 ? nb : 1;
         int nb2 = 0;
@@ -982,7 +973,7 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     // small jobs (about one wave) run best with the unconstrained 2-blocks/SM build, large ones with 3
     const int variant = (s->acc_variant_forced || E * nb >= ((size_t)1 << 23)) ? s->acc_variant : 2;
     const size_t resident =
-        (size_t)ctx->sm_count * ((variant == 2 || variant == 7) ? s->acc_blocks_per_sm2 : s->acc_blocks_per_sm) * 128;
+        (size_t)ctx->sm_count * (variant == 2 ? s->acc_blocks_per_sm2 : s->acc_blocks_per_sm) * 128;
     size_t L = (E * nb + resident - 1) / resident;
     if (L < 8) L = 8;
     if (L > 128) L = 128;
@@ -1044,8 +1035,7 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
         case 3: ZKP_ACC(3); break;
         case 4: ZKP_ACC(4); break;
         case 5: ZKP_ACC(5); break;
-        case 6: ZKP_ACC(6); break;
-        default: ZKP_ACC(2, true); break;
+        default: ZKP_ACC(6); break;
     }
 #undef ZKP_ACC
     ZKP_LAUNCHED(ctx);
@@ -1065,7 +1055,15 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
         }
     }
     if (s->reduce_coop) {
-        msm_rowcol_coop_kernel<<<dim3(nrows + ncols, nb), 128, 0, st>>>(s->buckets, B, h, nrows, ncols, rowcol);
+        // lanes per row / column sum: 32 while the blocks fit in one wave (shortest chain), fewer as the
+        // launch outgrows the GPU (less idle tree work per sum)
+        const size_t slots = (size_t)ctx->sm_count * 4, sums_total = (size_t)(nrows + ncols) * nb;
+        unsigned lpo = 32;
+        while (lpo > 4 && sums_total * lpo > slots * 32) lpo >>= 1;
+        if (const char* e = getenv("ZKP_MSM_ROWCOL_LPO")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) lpo = v; }
+        const unsigned R = 32 / lpo;
+        msm_rowcol_coop_kernel<<<dim3((nrows + R - 1) / R + (ncols + R - 1) / R, nb), 128, 0, st>>>(
+            s->buckets, B, h, nrows, ncols, lpo, rowcol);
         ZKP_LAUNCHED(ctx);
         msm_planes_coop_kernel<<<dim3(planes_r + planes_c, nb), 128, 0, st>>>(rowcol, h, nrows, ncols, planes_r, planes);
         ZKP_LAUNCHED(ctx);
