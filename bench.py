@@ -292,14 +292,20 @@ def main():
             pp = PlonkParams.setup_synthetic(ctx, args.logn, fr_to_mont1(tau))
         prover = z.PlonkKey.compile(pp, circ)
         bl = [rng.fr() for _ in range(11)]
-        wa_host = z.WitnessAssignment.from_circuit(circ, circ.n)
-        wa_host.wires_mont = pinned_copy(wa_host.wires_mont)
-        wa_host.dense_pi_mont = pinned_copy(wa_host.dense_pi_mont)
+        if shard:    # the sharded proof is driven round by round from Python: host-gathered wire columns
+            wa_host = z.WitnessAssignment.from_circuit(circ, circ.n)
+            wa_host.wires_mont = pinned_copy(wa_host.wires_mont)
+            wa_host.dense_pi_mont = pinned_copy(wa_host.dense_pi_mont)
+            h2d_prove = 5 * circ.n * 32 + 19 * 32
+        else:        # witness values in pinned host memory; the wire gather runs on the device
+            wa_host = z.WitnessValues.from_circuit(circ)
+            wa_host.witness_mont = pinned_copy(wa_host.witness_mont)
+            h2d_prove = (wa_host.witness_mont.shape[0] + len(wa_host.pi_values) + 19) * 32
         wa_dev = z.WitnessAssignment.from_circuit(circ, circ.n).to_device(ctx)
         proofs = []
         step = lambda: proofs.append(prover.create_proof(bl, wa_dev)[0])
         e2e_step = lambda: proofs.append(prover.create_proof(bl, wa_host)[0])
-        h2d, d2h = 5 * circ.n * 32 + 19 * 32, 11 * 96 + 17 * 32
+        h2d, d2h = h2d_prove, 11 * 96 + 17 * 32
         dominant = "msm_accumulate"
         metric = "create_proof_throughput"
         n = 1

@@ -28,6 +28,11 @@ struct zkp_prover {
     zkp_buf *W = nullptr, *Z = nullptr, *P7 = nullptr, *E7 = nullptr, *T = nullptr, *R = nullptr, *AGG = nullptr,
             *WZ = nullptr, *SAGG = nullptr, *WZW = nullptr;
     cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+    // circuit wiring for the witness gather on the device (zkp_prover_set_wiring)
+    uint32_t* wire_idx = nullptr;   // [4][m]: witness index of wire j at gate i (src/prover.rs:114-119)
+    uint32_t* pi_idx = nullptr;     // gate positions of the public inputs
+    size_t m = 0, pi_count = 0, wv_cap = 0;
+    zkp::fr_t* wv = nullptr;        // staging for the witness values and public-input values
 };
 
 namespace zkp {
@@ -337,6 +342,32 @@ static void linearization_scalars(uint64_t n, const fr ch[8], const fr e[15], fr
     sc[11] = F::neg(y);
 }
 
+// wires[j][i] = witness[idx[j][i]] for i < m, zero in the padding rows (src/prover.rs:109-119)
+__global__ void gather_wires_kernel(const fr_t* witness, size_t num_w, const uint32_t* idx, size_t m, size_t n,
+                                    fr_t* wires) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 4 * n) return;
+    const size_t j = t / n, i = t - j * n;
+    uint4 a = make_uint4(0, 0, 0, 0), b = a;
+    if (i < m) {
+        const uint32_t k = idx[j * m + i];
+        if (k < num_w) {
+            const uint4* q = reinterpret_cast<const uint4*>(witness + k);
+            a = __ldg(q); b = __ldg(q + 1);
+        }
+    }
+    uint4* o = reinterpret_cast<uint4*>(wires + t);
+    o[0] = a; o[1] = b;
+}
+
+// dense public-input vector (src/lib.rs:206-219): pi[idx[c]] = values[c] on a zeroed n-vector
+__global__ void scatter_pi_kernel(const fr_t* values, const uint32_t* idx, size_t count, size_t n, fr_t* pi) {
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= count) return;
+    const uint32_t i = idx[c];
+    if (i < n) pi[i] = values[c];
+}
+
 #define TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
 static inline zkp_poly_ref ref(const zkp_buf* b, size_t off, size_t len) { zkp_poly_ref r; r.buf = b; r.off = off; r.len = len; return r; }
@@ -376,6 +407,8 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     for (unsigned j = 0; j < 4; j++) TRY(zkp_poly_blind_dev(ctx, pr->P7, j * S, n, blinders + 8 * j, 2));
     if (pi_dev) {
         TRY(ntt_run(ctx, pi_dev->d, 0, n, pr->P7->d + 4 * S, 0, k, true, false, 1));
+    } else if (!pi_host) {   // the dense vector was built in place (zkp_prover_prove_witness)
+        TRY(ntt_run(ctx, pr->P7->d + 4 * S, 0, n, pr->P7->d + 4 * S, 0, k, true, false, 1));
     } else {
         ZKP_CUDA(ctx, cudaMemcpyAsync(pr->P7->d + 4 * S, pi_host, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
         TRY(ntt_run(ctx, pr->P7->d + 4 * S, 0, n, pr->P7->d + 4 * S, 0, k, true, false, 1));
@@ -549,6 +582,9 @@ int zkp_prover_destroy(zkp_prover* pr) {
     if (pr->side) cudaStreamSynchronize(pr->side->stream);
     zkp_buf** bufs[] = {&pr->W, &pr->Z, &pr->P7, &pr->E7, &pr->T, &pr->R, &pr->AGG, &pr->WZ, &pr->SAGG, &pr->WZW};
     for (zkp_buf** b : bufs) if (*b) { zkp_buf_free(ctx, *b); *b = nullptr; }
+    if (pr->wire_idx) cudaFree(pr->wire_idx);
+    if (pr->pi_idx) cudaFree(pr->pi_idx);
+    if (pr->wv) cudaFree(pr->wv);
     if (pr->ev_main) cudaEventDestroy(pr->ev_main);
     if (pr->ev_side) cudaEventDestroy(pr->ev_side);
     if (pr->side) zkp_ctx_destroy(pr->side);
@@ -613,6 +649,68 @@ int zkp_prover_prove(zkp_prover* pr, const uint8_t transcript[203], const uint64
         // leave both streams idle so the next proof never races a half-finished one
         cudaStreamSynchronize(pr->side->stream);
         cudaStreamSynchronize(pr->ctx->stream);
+    }
+    return rc;
+}
+
+int zkp_prover_set_wiring(zkp_prover* pr, const uint32_t* wire_idx, size_t m, const uint32_t* pi_idx,
+                          size_t pi_count) {
+    if (!pr || (!wire_idx && m) || m > pr->n || (!pi_idx && pi_count) || pi_count > pr->n) return ZKP_ERR_INVALID;
+    zkp_ctx* ctx = pr->ctx;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (pr->wire_idx) cudaFree(pr->wire_idx);
+    if (pr->pi_idx) cudaFree(pr->pi_idx);
+    pr->wire_idx = pr->pi_idx = nullptr;
+    pr->m = pr->pi_count = 0;
+    if (m) {
+        ZKP_CUDA(ctx, cudaMalloc(&pr->wire_idx, 4 * m * sizeof(uint32_t)));
+        ZKP_CUDA(ctx, cudaMemcpy(pr->wire_idx, wire_idx, 4 * m * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    if (pi_count) {
+        ZKP_CUDA(ctx, cudaMalloc(&pr->pi_idx, pi_count * sizeof(uint32_t)));
+        ZKP_CUDA(ctx, cudaMemcpy(pr->pi_idx, pi_idx, pi_count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    pr->m = m;
+    pr->pi_count = pi_count;
+    return ZKP_OK;
+}
+
+int zkp_prover_prove_witness(zkp_prover* pr, const uint8_t transcript[203], const uint64_t* witness, size_t num_w,
+                             const uint64_t* pi_values, const uint64_t blinders[44], uint64_t commitments[132],
+                             uint64_t evaluations[64], uint8_t proof_bytes[1040], uint8_t transcript_out[203]) {
+    if (!pr || !transcript || !blinders || !commitments || !evaluations || (!witness && num_w) ||
+        (!pi_values && pr->pi_count) || (pr->m && !pr->wire_idx))
+        return ZKP_ERR_INVALID;
+    zkp_ctx* ctx = pr->ctx;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    const size_t n = pr->n, need = num_w + pr->pi_count + 1;
+    if (pr->wv_cap < need) {
+        ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (pr->wv) cudaFree(pr->wv);
+        pr->wv = nullptr; pr->wv_cap = 0;
+        ZKP_CUDA(ctx, cudaMalloc(&pr->wv, need * sizeof(fr_t)));
+        pr->wv_cap = need;
+    }
+    cudaStream_t st = ctx->stream;
+    if (num_w) ZKP_CUDA(ctx, cudaMemcpyAsync(pr->wv, witness, num_w * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+    drv::gather_wires_kernel<<<(unsigned)((4 * n + 255) / 256), 256, 0, st>>>(pr->wv, num_w, pr->wire_idx, pr->m, n, pr->W->d);
+    ZKP_LAUNCHED(ctx);
+    fr_t* pi = pr->P7->d + 4 * pr->S;
+    ZKP_CUDA(ctx, cudaMemsetAsync(pi, 0, n * sizeof(fr_t), st));
+    if (pr->pi_count) {
+        fr_t* pv = pr->wv + num_w;
+        ZKP_CUDA(ctx, cudaMemcpyAsync(pv, pi_values, pr->pi_count * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        drv::scatter_pi_kernel<<<(unsigned)((pr->pi_count + 255) / 256), 256, 0, st>>>(pv, pr->pi_idx, pr->pi_count, n, pi);
+        ZKP_LAUNCHED(ctx);
+    }
+    rc = drv::prove(pr, transcript, nullptr, pr->W, nullptr, nullptr, blinders, commitments, evaluations, proof_bytes,
+                    transcript_out);
+    if (rc) {
+        cudaStreamSynchronize(pr->side->stream);
+        cudaStreamSynchronize(ctx->stream);
     }
     return rc;
 }

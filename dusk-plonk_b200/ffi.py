@@ -113,6 +113,8 @@ SIGNATURES.update({
     "zkp_prover_create": (_int, [_vp, _vp, ctypes.POINTER(ProvingKeyDesc), ctypes.POINTER(_vp)]),
     "zkp_prover_destroy": (_int, [_vp]),
     "zkp_prover_prove": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "zkp_prover_set_wiring": (_int, [_vp, _vp, _sz, _vp, _sz]),
+    "zkp_prover_prove_witness": (_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp]),
     "zkp_transcript_append": (_int, [_vp, ctypes.c_char_p, _vp, ctypes.c_uint32]),
     "zkp_transcript_challenge": (_int, [_vp, ctypes.c_char_p, _vp, ctypes.c_uint32]),
     "zkp_linearization_scalars": (_int, [_uint, _vp, _vp, _vp]),
@@ -539,6 +541,26 @@ class NativeProver:
             self.h, _ptr(st),
             _ptr(wires_host) if wires_host is not None else None, wires_dev.h if wires_dev is not None else None,
             _ptr(pi_host) if pi_host is not None else None, pi_dev.h if pi_dev is not None else None,
+            _ptr(bl), _ptr(self._comms), _ptr(self._evals), _ptr(self._bytes), None)
+        return rc, self._comms, self._evals, self._bytes
+
+    def set_wiring(self, wire_idx, pi_idx):
+        """wire_idx: (4, m) witness indices per gate; pi_idx: gate positions of the public inputs."""
+        w = np.ascontiguousarray(wire_idx, dtype=np.uint32)
+        p = np.ascontiguousarray(pi_idx, dtype=np.uint32)
+        assert w.ndim == 2 and w.shape[0] == 4
+        self.ctx.check(self.ctx.lib.zkp_prover_set_wiring(self.h, _ptr(w), w.shape[1], _ptr(p) if p.size else None,
+                                                          p.size))
+
+    def prove_witness(self, transcript_state, witness_mont, pi_values_mont, blinders_mont):
+        """As ``prove`` with the wire gather done on the device from the witness values."""
+        st = np.frombuffer(bytes(transcript_state), dtype=np.uint8)
+        assert st.shape[0] == 203
+        bl = as_fr_array(blinders_mont)
+        wv = as_fr_array(witness_mont)
+        pv = as_fr_array(pi_values_mont) if len(pi_values_mont) else None
+        rc = self.ctx.lib.zkp_prover_prove_witness(
+            self.h, _ptr(st), _ptr(wv), wv.shape[0], _ptr(pv) if pv is not None else None,
             _ptr(bl), _ptr(self._comms), _ptr(self._evals), _ptr(self._bytes), None)
         return rc, self._comms, self._evals, self._bytes
 

@@ -71,6 +71,7 @@ class Prover:
         self.pi_indexes = list(pi_indexes)
         self._ws = None
         self._native = None
+        self._wiring_of = None
         # the sharded proof (NCCL collectives between rounds) and traced proofs run the same rounds
         # from Python; everything else goes through the native driver
         self.native = True
@@ -167,9 +168,16 @@ class Prover:
         from .plonk_params import Error
         st = bytes(tr.strobe.state) + bytes([tr.strobe.pos, tr.strobe.pos_begin, tr.strobe.cur_flags])
         n = self.size
-        wires_host = None if wa.wires_dev is not None else np.ascontiguousarray(wa.wires_mont).reshape(4 * n, 4)
-        pi_host = None if wa.pi_dev is not None else np.ascontiguousarray(wa.dense_pi_mont)
-        rc, comms, evals, raw = self._native_prover().prove(st, wires_host, wa.wires_dev, pi_host, wa.pi_dev, bl)
+        np_ = self._native_prover()
+        if isinstance(wa, WitnessValues):
+            if self._wiring_of is not wa.wires:           # same circuit shape as the last proof: already set
+                np_.set_wiring(wa.wires, wa.pi_indexes)
+                self._wiring_of = wa.wires
+            rc, comms, evals, raw = np_.prove_witness(st, wa.witness_mont, wa.pi_values_mont, bl)
+        else:
+            wires_host = None if wa.wires_dev is not None else np.ascontiguousarray(wa.wires_mont).reshape(4 * n, 4)
+            pi_host = None if wa.pi_dev is not None else np.ascontiguousarray(wa.dense_pi_mont)
+            rc, comms, evals, raw = np_.prove(st, wires_host, wa.wires_dev, pi_host, wa.pi_dev, bl)
         if rc == ZKP_ERR_DEGREE:
             raise Error("polynomial degree exceeds the SRS")
         if rc:
@@ -195,12 +203,20 @@ class Prover:
         T = trace if trace is not None else None
         if isinstance(circuit, Plonk):
             circuit = SynthesizedCircuit.from_composer(circuit)
-        wa = circuit if isinstance(circuit, WitnessAssignment) else WitnessAssignment.from_circuit(circuit, n)
+        use_native = self.native and trace is None and type(self.keypair) is PlonkParams
+        if isinstance(circuit, (WitnessAssignment, WitnessValues)):
+            wa = circuit
+        elif use_native:
+            wa = WitnessValues.from_circuit(circuit)      # the wire gather happens on the device
+        else:
+            wa = WitnessAssignment.from_circuit(circuit, n)
+        if isinstance(wa, WitnessValues) and not use_native:
+            wa = wa.gathered(n)
         tr = self.transcript.clone()
         for pi in wa.pi_values:
             tr.append_scalar(b"pi", pi)
         bl = fr_to_mont(blinders)
-        if self.native and trace is None and type(self.keypair) is PlonkParams:
+        if use_native:
             return self._create_proof_native(tr, wa, bl)
         proof = Proof()
 
@@ -383,3 +399,32 @@ class WitnessAssignment:
         if len(circ.pi_indexes):
             dense[np.asarray(circ.pi_indexes, dtype=np.int64)] = fr_to_mont(circ.pi_values)
         return cls(wires, dense, circ.pi_values)
+
+
+class WitnessValues:
+    """A proof's inputs before the wire gather: the witness values, the (4, m) wire -> witness table
+    of the synthesized circuit and the public inputs.  ``create_proof`` ships the values and gathers
+    the four wire columns on the device (src/prover.rs:109-119), so the host never builds them."""
+
+    def __init__(self, witness_mont, wires, pi_indexes, pi_values):
+        self.witness_mont = witness_mont                     # (num_witness, 4) uint64 Montgomery
+        self.wires = wires                                   # (4, m) uint32
+        self.pi_indexes = np.asarray(pi_indexes, dtype=np.uint32)
+        self.pi_values = list(pi_values)
+        self.pi_values_mont = fr_to_mont(self.pi_values) if len(self.pi_values) else np.zeros((0, 4), dtype=np.uint64)
+
+    @classmethod
+    def from_circuit(cls, circ):
+        return cls(fr_to_mont(circ.witness), np.ascontiguousarray(circ.wires, dtype=np.uint32), circ.pi_indexes,
+                   circ.pi_values)
+
+    def gathered(self, n):
+        """The host-side gather (what ``WitnessAssignment.from_circuit`` builds)."""
+        wires = np.zeros((4, n, 4), dtype=np.uint64)
+        idx = self.wires.astype(np.int64)
+        for j in range(4):
+            wires[j, :idx.shape[1]] = self.witness_mont[idx[j]]
+        dense = np.zeros((n, 4), dtype=np.uint64)
+        if len(self.pi_values):
+            dense[self.pi_indexes.astype(np.int64)] = self.pi_values_mont
+        return WitnessAssignment(wires, dense, self.pi_values)

@@ -10,6 +10,6 @@ from .poly_commit import Fft, Coefficients, PointsValue, Commitment  # noqa: E40
 from .plonk_params import PlonkParams, Error  # noqa: E402,F401
 from .composer import Plonk, Constraint, SynthesizedCircuit  # noqa: E402,F401
 from .key import PlonkKey  # noqa: E402,F401
-from .prover import Prover, Proof, WitnessAssignment  # noqa: E402,F401
+from .prover import Prover, Proof, WitnessAssignment, WitnessValues  # noqa: E402,F401
 from .transcript import Transcript  # noqa: E402,F401
 from . import sharding  # noqa: E402,F401

@@ -254,6 +254,17 @@ int zkp_prover_prove(zkp_prover* prover, const uint8_t transcript[203], const ui
                      const uint64_t blinders[44], uint64_t commitments[132], uint64_t evaluations[64],
                      uint8_t proof_bytes[1040], uint8_t transcript_out[203]);
 
+/* The same with the witness gather on the device (src/prover.rs:109-119, src/lib.rs:206-219): the
+ * circuit's wiring is set once -- wire_idx[j * m + i] = witness index of wire j (a, b, o, d) at gate
+ * i < m, pi_idx[c] = gate of public input c -- and each proof ships only the witness values
+ * (num_w x 4 uint64 Montgomery) and the public-input values in the form the dense vector holds them. */
+int zkp_prover_set_wiring(zkp_prover* prover, const uint32_t* wire_idx, size_t m, const uint32_t* pi_idx,
+                          size_t pi_count);
+int zkp_prover_prove_witness(zkp_prover* prover, const uint8_t transcript[203], const uint64_t* witness,
+                             size_t num_w, const uint64_t* pi_values, const uint64_t blinders[44],
+                             uint64_t commitments[132], uint64_t evaluations[64], uint8_t proof_bytes[1040],
+                             uint8_t transcript_out[203]);
+
 /* Host-side pieces of the driver, exported so they are testable without a GPU:
  * Merlin append_message / challenge_bytes on a serialised state, the scalar side of the
  * linearisation (challenges = alpha beta gamma range logic fixed var z; evals in `Evaluations`

@@ -312,9 +312,13 @@ def test_native_round_driver_equals_python_driven_rounds(ctx, name):
     for c in oplonk.Proof.COMM_NAMES:
         assert getattr(nproof, c) == getattr(oproof, c), c
     assert nproof.evaluations == oproof.evaluations
-    # witness already in HBM, and a second proof on the same workspace
+    # the three witness forms: values + device gather (above), gathered on the host, already in HBM
+    hproof, _ = prover.create_proof(bl, z.WitnessAssignment.from_circuit(circ, circ.n))
+    assert hproof == nproof and hproof.wire_bytes == nproof.wire_bytes
     wa = z.WitnessAssignment.from_circuit(circ, circ.n).to_device(ctx)
     dproof, _ = prover.create_proof(bl, wa)
     assert dproof == nproof and dproof.wire_bytes == nproof.wire_bytes
+    vproof, _ = prover.create_proof(bl, z.WitnessValues.from_circuit(circ))
+    assert vproof == nproof
     assert z.Proof.from_bytes(nproof.wire_bytes) == nproof
     assert oplonk.verify(ovk, circ.n, nproof, circ.pi_indexes, npi, otr, oplonk.trapdoor_kzg_check(tau))
