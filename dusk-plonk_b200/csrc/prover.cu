@@ -126,11 +126,16 @@ __global__ void prod_chunk_kernel(const fr_t* in, size_t n, fr_t* chunk) {
     pst(chunk + t, p);
 }
 
-// single block: chunk[t] <- product of the chunks before (after, if reverse) t
-__global__ void __launch_bounds__(1024) prod_carry_kernel(fr_t* chunk, size_t nc, int reverse) {
+// one block per scan: block 0 turns fwd[t] into the product of the chunks before t, block 1 turns
+// rev[t] into the product of the chunks after t (the numerator and denominator scans of the
+// permutation accumulator are independent: one launch, two SMs)
+__global__ void __launch_bounds__(1024) prod_carry_kernel(fr_t* fwd, fr_t* rev, size_t nc) {
     __shared__ fr_t sm[1024];
     const unsigned T = blockDim.x, tid = threadIdx.x;
+    const int reverse = blockIdx.x;
+    fr_t* chunk = reverse ? rev : fwd;
     const size_t per = (nc + T - 1) / T;
+    const unsigned active = (unsigned)((nc + per - 1) / per);   // threads that own chunks
     // logical index j runs in scan direction
     auto at = [&](size_t j) { return reverse ? nc - 1 - j : j; };
     const size_t lo = (size_t)tid * per, hi = lo + per < nc ? lo + per : nc;
@@ -138,7 +143,7 @@ __global__ void __launch_bounds__(1024) prod_carry_kernel(fr_t* chunk, size_t nc
     for (size_t j = lo; j < hi; j++) p = p * pld(chunk + at(j));
     sm[tid] = p;
     __syncthreads();
-    for (unsigned s = 1; s < T; s <<= 1) {
+    for (unsigned s = 1; s < active; s <<= 1) {   // threads beyond `active` hold one: no level needed for them
         fr_t v = sm[tid];
         if (tid >= s) v = sm[tid - s] * v;
         __syncthreads();
@@ -425,6 +430,7 @@ __global__ void __launch_bounds__(512) div_carry_kernel(fr_t* chunk, size_t nc_a
     const size_t nc = nc_all - base < tile ? nc_all - base : tile;
     chunk += base;
     const size_t per = (nc + T - 1) / T;
+    const unsigned active = (unsigned)((nc + per - 1) / per);   // threads that own chunks
     // reversed logical order: j = 0 is the top chunk
     const size_t lo = (size_t)tid * per, hi = lo + per < nc ? lo + per : nc;
     // local value of this thread's span relative to the span's lowest chunk, and X^(span length)
@@ -434,7 +440,7 @@ __global__ void __launch_bounds__(512) div_carry_kernel(fr_t* chunk, size_t nc_a
     xp[tid] = xl;
     __syncthreads();
     // inclusive scan over threads of the affine maps carry -> carry * xl + s
-    for (unsigned st = 1; st < T; st <<= 1) {
+    for (unsigned st = 1; st < active; st <<= 1) {   // idle threads hold the identity map
         fr_t v = sm[tid], w = xp[tid];
         if (tid >= st) { v = sm[tid - st] * w + v; w = xp[tid - st] * w; }
         __syncthreads();
@@ -586,9 +592,8 @@ int zkp_perm_z_dev(zkp_ctx* ctx, size_t n, const zkp_poly_ref wires[4], const zk
     ZKP_LAUNCHED(ctx);
     prod_chunk_kernel<<<cb, 128, 0, st>>>(den, n, c2);
     ZKP_LAUNCHED(ctx);
-    prod_carry_kernel<<<1, 1024, 0, st>>>(c1, nc, 0);
-    ZKP_LAUNCHED(ctx);
-    prod_carry_kernel<<<1, 1024, 0, st>>>(c2, nc, 1);
+    // few warps per scheduler keep each thread's multiplication chain at its latency, not the pipe's
+    prod_carry_kernel<<<2, nc <= 16384 ? 256 : 1024, 0, st>>>(c1, c2, nc);
     ZKP_LAUNCHED(ctx);
     prod_apply_kernel<<<cb, 128, 0, st>>>(num, n, c1, 0, P);
     ZKP_LAUNCHED(ctx);
@@ -731,16 +736,16 @@ int zkp_poly_div_linear_dev(zkp_ctx* ctx, zkp_poly_ref in, const uint64_t point[
     div_chunk_kernel<<<blocks_for(nc, 128), 128, 0, st>>>(c, n, pt, s);
     ZKP_LAUNCHED(ctx);
     if (nc <= DV_TILE) {
-        div_carry_kernel<<<1, 512, 0, st>>>(s, nc, nc, X, nullptr);
+        div_carry_kernel<<<1, 256, 0, st>>>(s, nc, nc, X, nullptr);
         ZKP_LAUNCHED(ctx);
         div_apply_kernel<<<blocks_for(nc, 128), 128, 0, st>>>(c, n, pt, s, nullptr, nc, X, out->d + out_off);
         ZKP_LAUNCHED(ctx);
     } else {
         const size_t ntiles = (nc + DV_TILE - 1) / DV_TILE;
         fr_t* tv = s + nc;
-        div_carry_kernel<<<(unsigned)ntiles, 512, 0, st>>>(s, nc, DV_TILE, X, tv);
+        div_carry_kernel<<<(unsigned)ntiles, 256, 0, st>>>(s, nc, DV_TILE, X, tv);
         ZKP_LAUNCHED(ctx);
-        div_carry_kernel<<<1, 512, 0, st>>>(tv, ntiles, ntiles, pow_u64(X, DV_TILE), nullptr);
+        div_carry_kernel<<<1, ntiles <= 256 ? 32 : 256, 0, st>>>(tv, ntiles, ntiles, pow_u64(X, DV_TILE), nullptr);
         ZKP_LAUNCHED(ctx);
         div_apply_kernel<<<blocks_for(nc, 128), 128, 0, st>>>(c, n, pt, s, tv, nc, X, out->d + out_off);
         ZKP_LAUNCHED(ctx);
