@@ -28,6 +28,7 @@ struct zkp_prover {
     zkp_buf *W = nullptr, *Z = nullptr, *P7 = nullptr, *E7 = nullptr, *T = nullptr, *R = nullptr, *AGG = nullptr,
             *WZ = nullptr, *SAGG = nullptr, *WZW = nullptr;
     cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+    uint64_t n_inv[4] = {0, 0, 0, 0};   // 1 / n, Montgomery (host constant of the L1 polynomial)
     // circuit wiring for the witness gather on the device (zkp_prover_set_wiring)
     uint32_t* wire_idx = nullptr;   // [4][m]: witness index of wire j at gate i (src/prover.rs:114-119)
     uint32_t* pi_idx = nullptr;     // gate positions of the public inputs
@@ -454,7 +455,7 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     const fr alpha = ch[0];
     const fr alpha2 = F::sqr(alpha);
     // L1 * alpha^2: idft of (alpha^2, 0, ..) has every coefficient alpha^2 / n (quotient_poly.rs:264-272)
-    const fr n_inv = F::inv(F::from_u64((uint64_t)n));
+    const fr n_inv = fr_load(pr->n_inv);
     const fr l1c = F::mul(alpha2, n_inv);
     TRY(zkp_buf_fill(ctx, pr->P7, 6 * S, n, l1c.l));
     TRY(ntt_run(ctx, pr->P7->d + 6 * S, 0, n, pr->E7->d + 6 * n8, 0, k8, false, true, 1));
@@ -617,6 +618,7 @@ int zkp_prover_create(zkp_ctx* ctx, const zkp_srs* srs, const zkp_proving_key* k
     pr->n = n;
     pr->k = key->k;
     pr->S = n + 8;  // the seven polynomials bound for the 8n coset sit side by side
+    drv::fr_store(pr->n_inv, drv::F::inv(drv::F::from_u64((uint64_t)n)));
     struct { zkp_buf** b; size_t len; } want[] = {
         {&pr->W, 4 * n}, {&pr->Z, n}, {&pr->P7, 7 * pr->S}, {&pr->E7, 7 * n8}, {&pr->T, n8}, {&pr->R, n + 3},
         {&pr->AGG, 5 * n}, {&pr->WZ, 5 * n}, {&pr->SAGG, n + 3}, {&pr->WZW, n + 3}};

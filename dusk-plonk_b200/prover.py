@@ -28,6 +28,25 @@ class Proof:
     def __init__(self):
         self.evaluations = {}
 
+    @classmethod
+    def from_limbs(cls, comms, evals, wire_bytes=None):
+        """Proof over the native driver's output (11 x 12 / 16 x 4 uint64 Montgomery limbs); the
+        conversion to canonical integers happens on first access, not on the proving path."""
+        p = object.__new__(cls)
+        p.__dict__["_limbs"] = (np.array(comms, dtype=np.uint64), np.array(evals, dtype=np.uint64))
+        if wire_bytes is not None:
+            p.__dict__["wire_bytes"] = bytes(wire_bytes)
+        return p
+
+    def __getattr__(self, name):
+        limbs = self.__dict__.pop("_limbs", None)
+        if limbs is None:
+            raise AttributeError(name)
+        for i, c in enumerate(COMM_NAMES):
+            self.__dict__[c] = g1_from_mont(limbs[0][i])
+        self.__dict__["evaluations"] = dict(zip(EVAL_NAMES, fr_from_mont(limbs[1])))
+        return getattr(self, name)
+
     def __eq__(self, o):
         return all(getattr(self, c) == getattr(o, c) for c in COMM_NAMES) and \
             dict(self.evaluations) == dict(o.evaluations)
@@ -183,12 +202,8 @@ class Prover:
         if rc:
             self.ctx.check(rc)
             raise ZkpError(rc)
-        proof = Proof()
-        for i, c in enumerate(COMM_NAMES):
-            setattr(proof, c, g1_from_mont(comms[i]))
-        proof.evaluations = dict(zip(EVAL_NAMES, fr_from_mont(evals)))
-        proof.wire_bytes = bytes(raw)   # as serialised by the native driver (== to_bytes())
-        return proof, list(wa.pi_values)
+        # wire_bytes: as serialised by the native driver (== to_bytes())
+        return Proof.from_limbs(comms, evals, raw), list(wa.pi_values)
 
     # ---------------------------------------------------------------- create_proof
     def create_proof(self, blinders, circuit, trace=None):
