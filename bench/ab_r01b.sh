@@ -1,3 +1,6 @@
+# HISTORICAL (round 1): A/B of the cooperative bucket reduction (ZKP_MSM_REDUCE=legacy) and of software-pipelined
+# loads in the accumulate kernel (ZKP_MSM_BLOCKS_PER_SM=7).  Both knobs were removed after the measurement;
+# results: profiles/r01/ab_*.json.
 set -x
 timeout 300 python -m pytest tests/test_gpu_msm.py tests/test_gpu_prover.py -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/pytest_coop_v1.log
 run() { name=$1; shift; timeout 200 "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err; python - gpurun_out/$name.json <<'P'

@@ -1,3 +1,5 @@
+# HISTORICAL (round 1): sweep of the lanes per row/column sum (ZKP_MSM_ROWCOL_LPO, knob removed afterwards;
+# the launcher now picks it from the launch size).  Results: profiles/r01/ab2_*.json.
 set -x
 timeout 300 python -m pytest tests/test_gpu_msm.py tests/test_gpu_prover.py -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/pytest_coop_v2.log
 run() { name=$1; shift; timeout 200 "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err; python - gpurun_out/$name.json <<'P'

@@ -59,7 +59,6 @@ struct MsmScratch {
     int acc_variant = 3;
     bool acc_variant_forced = false;
     int acc_blocks_per_sm2 = 0;   // occupancy of the 2-blocks/SM build used for small jobs
-    bool reduce_coop = true;      // four-warp cooperative bucket reduction (ZKP_MSM_REDUCE=legacy: one warp per sum)
 };
 
 static constexpr uint32_t DIGIT_ZERO = 0xffffffffu;
@@ -233,9 +232,9 @@ __global__ void msm_scatter_kernel(const __grid_constant__ MsmBatch batch, const
 // distribution.  A bucket that lies inside one chunk is written directly; a bucket cut by a chunk
 // boundary leaves partial sums in the chunk's head slot (first segment of the chunk) or tail slot
 // (last segment), which msm_merge_kernel adds up.
-// MB = resident blocks per SM the register allocation is bounded for (2: 172 registers, 4: 128
-// registers with ~70 bytes of spill): more warps hide the dependent IMAD chains (ncu: `wait`
-// stalls dominate at 2 blocks / SM).
+// MB = resident blocks per SM the register allocation is bounded for (2: 174 registers, 3: 168).  Small,
+// one-wave jobs run best with 2, large ones with 3; 4 .. 6 (128 .. 80 registers, spills) were measured
+// slower.
 template <int MB>
 __global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const g1_affine* table, const uint32_t* sorted,
                                                             const uint32_t* offsets, const uint32_t* counts,
@@ -338,80 +337,7 @@ __global__ void __launch_bounds__(128) msm_merge_giant_kernel(const uint32_t* of
 // with R[hi] / C[lo] the row / column sums of the (hi, lo) grid -- 2 B additions in total, all
 // rows and columns in parallel -- and the two short weighted sums done by bit planes
 // (sum_x x A[x] = sum_j 2^j * sum_{x: bit j} A[x]), the 2^j factors applied in parallel.
-// One warp per row / column: lanes stride, then a shared-memory tree over the 32 lanes.
-__device__ __forceinline__ g1_xyzz warp_point_sum(g1_xyzz v, g1_xyzz* w, unsigned lane) {
-    w[lane] = v;
-    __syncwarp();
-    for (unsigned s = 16; s > 0; s >>= 1) {
-        if (lane < s) {
-            g1_xyzz o = w[lane + s];
-            xyzz_add(v, o);
-            w[lane] = v;
-        }
-        __syncwarp();
-    }
-    return v;
-}
-
-// grid (nrows + ncols, nb), 32 threads.  rc[pb][0 .. nrows) = R, rc[pb][nrows .. nrows+ncols) = C.
-// 16 resident one-warp blocks per SM (128 registers): all rows + columns of a 4-polynomial batch in one wave
-__global__ void __launch_bounds__(32, 16) msm_rowcol_kernel(const g1_xyzz* buckets, uint32_t B, unsigned h, uint32_t nrows,
-                                                       uint32_t ncols, g1_xyzz* rc) {
-    __shared__ g1_xyzz w[32];
-    const unsigned lane = threadIdx.x, pb = blockIdx.y;
-    const uint32_t x = blockIdx.x;
-    buckets += (size_t)pb * B;
-    g1_xyzz v = g1_xyzz::inf();
-    if (x < nrows) {           // row hi = x: weights hi * 2^h + lo
-        for (uint32_t lo = lane; lo < ncols; lo += 32) {
-            const uint32_t wgt = (x << h) + lo;
-            if (wgt >= 1 && wgt <= B) xyzz_add(v, buckets[wgt - 1]);
-        }
-    } else {                   // column lo = x - nrows
-        const uint32_t lo = x - nrows;
-        for (uint32_t hi = lane; hi < nrows; hi += 32) {
-            const uint32_t wgt = (hi << h) + lo;
-            if (wgt >= 1 && wgt <= B) xyzz_add(v, buckets[wgt - 1]);
-        }
-    }
-    v = warp_point_sum(v, w, lane);
-    if (lane == 0) rc[(size_t)pb * (nrows + ncols) + x] = v;
-}
-
-// grid (planes_r + planes_c, nb), 32 threads: block j < planes_r handles bit j of the row index and
-// applies 2^(h + j); the others handle bit j - planes_r of the column index and apply 2^(j - planes_r).
-__global__ void __launch_bounds__(32) msm_weighted_planes_kernel(const g1_xyzz* rc, unsigned h, uint32_t nrows,
-                                                                uint32_t ncols, unsigned planes_r, g1_xyzz* planes) {
-    __shared__ g1_xyzz w[32];
-    const unsigned lane = threadIdx.x, pb = blockIdx.y, nplanes = gridDim.x;
-    rc += (size_t)pb * (nrows + ncols);
-    const bool is_row = blockIdx.x < planes_r;
-    const unsigned j = is_row ? blockIdx.x : blockIdx.x - planes_r;
-    const g1_xyzz* arr = is_row ? rc : rc + nrows;
-    const uint32_t len = is_row ? nrows : ncols;
-    g1_xyzz v = g1_xyzz::inf();
-    for (uint32_t x = lane; x < len; x += 32)
-        if ((x >> j) & 1u) xyzz_add(v, arr[x]);
-    v = warp_point_sum(v, w, lane);
-    if (lane == 0) {
-        const unsigned dbl_n = is_row ? h + j : j;
-        for (unsigned i = 0; i < dbl_n; i++) xyzz_dbl(v);
-        planes[(size_t)pb * 32 + blockIdx.x] = v;
-    }
-    (void)nplanes;
-}
-
-// one warp per polynomial: tree over the <= 32 weighted plane sums
-__global__ void __launch_bounds__(32) msm_final_sum_kernel(const g1_xyzz* planes, unsigned nplanes, g1_xyzz* out) {
-    __shared__ g1_xyzz w[32];
-    const unsigned lane = threadIdx.x;
-    planes += (size_t)blockIdx.x * 32;
-    g1_xyzz v = lane < nplanes ? planes[lane] : g1_xyzz::inf();
-    v = warp_point_sum(v, w, lane);
-    if (lane == 0) out[blockIdx.x] = v;
-}
-
-// ---- the same reduction with cooperative point arithmetic --------------------------------------
+// ---- cooperative point arithmetic ----------------------------------------------------------------
 // The reduction is a dependency chain (~30 point additions + c doublings deep) on a mostly idle GPU,
 // and one point addition is 14 dependent Fq multiplications when a single thread runs it.  Here a
 // block of four warps -- one per SM sub-partition -- adds 32 pairs of points at a time: warp w takes
@@ -876,23 +802,16 @@ static int msm_scratch(zkp_ctx* ctx, MsmScratch** out) {
         ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->top, sizeof(long long)));
         ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->meta, 4 * MSM_MAX_BATCH * sizeof(uint32_t)));
         ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->tile_sums, 1024 * MSM_MAX_BATCH * sizeof(uint32_t)));
-        int mb = 3;  // measured best on B200 (2^22: 22.3 / 21.8 / 23.1 / 23.7 / 24.4 ms for 2..6)
-        if (const char* e = getenv("ZKP_MSM_BLOCKS_PER_SM")) {  // tuning knob: 2..6, applies to every job size
+        int mb = 3;  // measured best on B200 (2^22: 22.3 / 21.8 / 23.1 / 23.7 / 24.4 ms for 2..6 blocks per SM)
+        if (const char* e = getenv("ZKP_MSM_BLOCKS_PER_SM")) {  // tuning knob: 2 or 3, applies to every job size
             mb = atoi(e);
             ctx->msm->acc_variant_forced = true;
         }
-        if (const char* e = getenv("ZKP_MSM_REDUCE")) ctx->msm->reduce_coop = strcmp(e, "legacy") != 0;
-        if (mb < 2) mb = 2;
-        if (mb > 6) mb = 6;
+        mb = mb <= 2 ? 2 : 3;
         ctx->msm->acc_variant = mb;
         int nb = 0;
-        switch (mb) {
-            case 2: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<2>, 128, 0)); break;
-            case 3: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<3>, 128, 0)); break;
-            case 4: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<4>, 128, 0)); break;
-            case 5: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<5>, 128, 0)); break;
-            default: ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<6>, 128, 0)); break;
-        }
+        if (mb == 2) ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<2>, 128, 0));
+        else ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<3>, 128, 0));
         ctx->msm->acc_blocks_per_sm = nb > 0 ? nb : 1;
         int nb2 = 0;
         ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, msm_accumulate_kernel<2>, 128, 0));
@@ -1030,13 +949,8 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     const dim3 agrid((nchunks + 127) / 128, nb);
 #define ZKP_ACC(...) msm_accumulate_kernel<__VA_ARGS__><<<agrid, 128, 0, st>>>( \
         srs->d, s->sorted, s->offsets, s->counts, s->meta, B, (uint32_t)L, nchunks, E, s->buckets, s->slots)
-    switch (variant) {
-        case 2: ZKP_ACC(2); break;
-        case 3: ZKP_ACC(3); break;
-        case 4: ZKP_ACC(4); break;
-        case 5: ZKP_ACC(5); break;
-        default: ZKP_ACC(6); break;
-    }
+    if (variant == 2) ZKP_ACC(2);
+    else ZKP_ACC(3);
 #undef ZKP_ACC
     ZKP_LAUNCHED(ctx);
     }
@@ -1054,13 +968,12 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
             ZKP_LAUNCHED(ctx);
         }
     }
-    if (s->reduce_coop) {
+    {
         // lanes per row / column sum: 32 while the blocks fit in one wave (shortest chain), fewer as the
         // launch outgrows the GPU (less idle tree work per sum)
         const size_t slots = (size_t)ctx->sm_count * 4, sums_total = (size_t)(nrows + ncols) * nb;
         unsigned lpo = 32;
         while (lpo > 4 && sums_total * lpo > slots * 32) lpo >>= 1;
-        if (const char* e = getenv("ZKP_MSM_ROWCOL_LPO")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) lpo = v; }
         const unsigned R = 32 / lpo;
         msm_rowcol_coop_kernel<<<dim3((nrows + R - 1) / R + (ncols + R - 1) / R, nb), 128, 0, st>>>(
             s->buckets, B, h, nrows, ncols, lpo, rowcol);
@@ -1068,13 +981,6 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
         msm_planes_coop_kernel<<<dim3(planes_r + planes_c, nb), 128, 0, st>>>(rowcol, h, nrows, ncols, planes_r, planes);
         ZKP_LAUNCHED(ctx);
         msm_final_coop_kernel<<<nb, 128, 0, st>>>(planes, planes_r + planes_c, sums);
-        ZKP_LAUNCHED(ctx);
-    } else {
-        msm_rowcol_kernel<<<dim3(nrows + ncols, nb), 32, 0, st>>>(s->buckets, B, h, nrows, ncols, rowcol);
-        ZKP_LAUNCHED(ctx);
-        msm_weighted_planes_kernel<<<dim3(planes_r + planes_c, nb), 32, 0, st>>>(rowcol, h, nrows, ncols, planes_r, planes);
-        ZKP_LAUNCHED(ctx);
-        msm_final_sum_kernel<<<nb, 32, 0, st>>>(planes, planes_r + planes_c, sums);
         ZKP_LAUNCHED(ctx);
     }
     }
