@@ -320,8 +320,11 @@ __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ Q
 
 // ------------------------------------------------------------------ batched evaluation
 static constexpr unsigned EV_MAX = 16;   // polynomials per launch
-static constexpr unsigned EV_L = 8;      // coefficients per thread
+static constexpr unsigned EV_L = 32;     // coefficients per thread (the serial Horner part runs with every lane
+                                         // busy; the tree that follows does not, so it is kept a small share)
 static constexpr unsigned EV_T = 256;    // threads per block
+static constexpr unsigned EV_BLOCK_LOG = 13;  // log2(EV_T * EV_L): a block's chunk is weighed by X^(2^13 * block)
+static_assert((1u << EV_BLOCK_LOG) == EV_T * EV_L, "block chunk");
 
 struct EvalArgs {
     const fr_t* p[EV_MAX];
@@ -337,16 +340,26 @@ __global__ void __launch_bounds__(EV_T) eval_block_kernel(const __grid_constant_
     const unsigned y = blockIdx.y, tid = threadIdx.x;
     const fr_t* p = a.p[y];
     const size_t len = a.len[y];
-    const size_t lo = ((size_t)blockIdx.x * EV_T + tid) * EV_L;
+    // thread t takes coefficients base + t + j EV_T (consecutive threads read consecutive elements:
+    // coalesced), Horner in X^EV_T; the tree then weighs thread t by X^t
+    static_assert(EV_T == 256, "X^EV_T is pw[8]");
+    const size_t base = (size_t)blockIdx.x * EV_T * EV_L;
+    if (base >= len) {   // block beyond this (shorter) polynomial: nothing to add, skip the tree
+        if (tid == 0) pst(a.partial + (size_t)y * a.nblocks + blockIdx.x, fr_t::zero());
+        return;
+    }
     fr_t s = fr_t::zero();
-    if (lo < len) {
-        const size_t hi = lo + EV_L < len ? lo + EV_L : len;
-        s = pld(p + hi - 1);
-        for (size_t i = hi - 1; i-- > lo;) s = s * a.pw[0] + pld(p + i);
+    {
+#pragma unroll 4
+        for (int j = EV_L - 1; j >= 0; j--) {
+            const size_t i = base + (size_t)j * EV_T + tid;
+            const fr_t c = i < len ? pld(p + i) : fr_t::zero();
+            s = j == (int)EV_L - 1 ? c : s * a.pw[8] + c;
+        }
     }
     sm[tid] = s;
     __syncthreads();
-    unsigned lvl = 3;  // log2(EV_L)
+    unsigned lvl = 0;
     for (unsigned st = 1; st < EV_T; st <<= 1, lvl++) {
         if ((tid & (2 * st - 1)) == 0) sm[tid] = sm[tid] + a.pw[lvl] * sm[tid + st];
         __syncthreads();
@@ -368,11 +381,11 @@ __global__ void __launch_bounds__(EV_T) eval_final_kernel(const __grid_constant_
     if (lo < a.nblocks) {
         const size_t hi = lo + per < a.nblocks ? lo + per : a.nblocks;
         s = pld(part + hi - 1);
-        for (size_t i = hi - 1; i-- > lo;) s = s * a.pw[11] + pld(part + i);
+        for (size_t i = hi - 1; i-- > lo;) s = s * a.pw[EV_BLOCK_LOG] + pld(part + i);
     }
     sm[tid] = s;
     __syncthreads();
-    unsigned lvl = 11 + per_log;
+    unsigned lvl = EV_BLOCK_LOG + per_log;
     for (unsigned st = 1; st < EV_T; st <<= 1, lvl++) {
         if ((tid & (2 * st - 1)) == 0) sm[tid] = sm[tid] + a.pw[lvl < 28 ? lvl : 27] * sm[tid + st];
         __syncthreads();
@@ -679,7 +692,7 @@ int zkp_poly_eval_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, unsigned count, c
     const size_t per_block = (size_t)EV_T * EV_L;
     a.nblocks = (unsigned)((maxlen + per_block - 1) / per_block);
     if (a.nblocks == 0) a.nblocks = 1;
-    if ((size_t)a.nblocks > ((size_t)1 << 16)) return ZKP_ERR_INVALID;  // 2^27 coefficients
+    if ((size_t)a.nblocks > ((size_t)1 << 15)) return ZKP_ERR_INVALID;  // 2^28 coefficients: X^(2^27) is the last table entry
     fr_t* s;
     if ((rc = scratch(ctx, (size_t)count * a.nblocks + count, &s))) return rc;
     a.partial = s;
