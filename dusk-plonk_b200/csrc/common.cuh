@@ -56,6 +56,12 @@ struct zkp_ctx {
     struct ProfSpan { std::string name; cudaEvent_t a, b; };
     std::vector<ProfSpan> prof_spans;
     std::vector<cudaEvent_t> prof_pool;
+    // One-shot hook the MSM calls right after it has launched its accumulate kernel: the round driver
+    // uses it to queue transcript-independent work on a second stream behind an event recorded at that
+    // point, so that it runs under the latency-bound bucket reduction instead of competing with the
+    // accumulation for the SMs.
+    void (*after_accumulate)(void*) = nullptr;
+    void* after_accumulate_arg = nullptr;
 };
 
 namespace zkp {

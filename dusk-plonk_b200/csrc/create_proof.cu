@@ -376,6 +376,46 @@ static inline zkp_poly_ref ref(const zkp_buf* b, size_t off, size_t len) { zkp_p
 // key.poly / key.eval8 indices
 enum { Q_M = 0, Q_L, Q_R, Q_O, Q_C, Q_D, Q_ARITH, Q_RANGE, Q_LOGIC, Q_FIXED, Q_VAR, S1, S2, S3, S4 };
 
+// Transcript-independent coset transforms, queued on the second stream from inside the commit (see
+// zkp_ctx::after_accumulate): they start when the commit's accumulate kernel has finished and run under
+// its bucket reduction.
+struct SideJob {
+    zkp_prover* pr;
+    const fr_t* in;
+    size_t in_stride, len_in;
+    fr_t* out;
+    unsigned batch;
+    int rc;
+};
+
+static void run_side_job(void* arg) {
+    SideJob* j = static_cast<SideJob*>(arg);
+    zkp_prover* pr = j->pr;
+    zkp_ctx *ctx = pr->ctx, *side = pr->side;
+    const size_t n8 = 8 * pr->n;
+    j->rc = ZKP_ERR_CUDA;
+    if (cudaEventRecord(pr->ev_main, ctx->stream) != cudaSuccess) return;
+    if (cudaStreamWaitEvent(side->stream, pr->ev_main, 0) != cudaSuccess) return;
+    j->rc = ntt_run(side, j->in, j->in_stride, j->len_in, j->out, n8, pr->k + 3, false, true, j->batch);
+    if (j->rc == ZKP_OK && cudaEventRecord(pr->ev_side, side->stream) != cudaSuccess) j->rc = ZKP_ERR_CUDA;
+}
+
+// commit with a side job attached: if the MSM never reached its accumulate kernel (all-zero input),
+// the job is queued right after
+static int commit_group(zkp_prover* pr, const zkp_poly_ref* polys, unsigned count, uint64_t* out_xy);
+static int commit_group_with(zkp_prover* pr, const zkp_poly_ref* polys, unsigned count, uint64_t* out_xy, SideJob* job) {
+    pr->ctx->after_accumulate = run_side_job;
+    pr->ctx->after_accumulate_arg = job;
+    job->rc = ZKP_OK;
+    const int rc = commit_group(pr, polys, count, out_xy);
+    if (pr->ctx->after_accumulate) {   // not consumed
+        pr->ctx->after_accumulate = nullptr;
+        run_side_job(job);
+    }
+    if (rc) return rc;
+    return job->rc;
+}
+
 static int commit_group(zkp_prover* pr, const zkp_poly_ref* polys, unsigned count, uint64_t* out_xy) {
     const fr_t* ptrs[8];
     size_t lens[8];
@@ -414,14 +454,12 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
         ZKP_CUDA(ctx, cudaMemcpyAsync(pr->P7->d + 4 * S, pi_host, n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
         TRY(ntt_run(ctx, pr->P7->d + 4 * S, 0, n, pr->P7->d + 4 * S, 0, k, true, false, 1));
     }
-    // a, b, c, d, PI on the 8n coset: second stream, under the wire commitments
+    // a, b, c, d, PI on the 8n coset: second stream, under the bucket reduction of the wire commitments
     // (reference order: src/prover.rs:229, quotient_poly.rs:54-58,145 -- same values, earlier)
-    ZKP_CUDA(ctx, cudaEventRecord(pr->ev_main, ctx->stream));
-    ZKP_CUDA(ctx, cudaStreamWaitEvent(side->stream, pr->ev_main, 0));
-    TRY(ntt_run(side, pr->P7->d, S, n + 3, pr->E7->d, n8, k8, false, true, 5));
     zkp_poly_ref wp[4];
     for (unsigned j = 0; j < 4; j++) wp[j] = ref(pr->P7, j * S, n + 2);
-    TRY(commit_group(pr, wp, 4, comms));
+    SideJob wires8 = {pr, pr->P7->d, S, n + 3, pr->E7->d, 5, ZKP_OK};
+    TRY(commit_group_with(pr, wp, 4, comms, &wires8));
     static const char* const wl[4] = {"a_w", "b_w", "c_w", "d_w"};
     for (unsigned j = 0; j < 4; j++) tr.append_commitment(wl[j], comms + 12 * j);
 
@@ -435,12 +473,9 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     const zkp_poly_ref zp = ref(pr->P7, 5 * S, n + 3);
     TRY(ntt_run(ctx, pr->Z->d, 0, n, pr->P7->d + 5 * S, 0, k, true, false, 1));
     TRY(zkp_poly_blind_dev(ctx, pr->P7, 5 * S, n, blinders + 32, 3));
-    // z on the 8n coset needs no further challenge either: side stream, under the z commitment
-    ZKP_CUDA(ctx, cudaEventRecord(pr->ev_main, ctx->stream));
-    ZKP_CUDA(ctx, cudaStreamWaitEvent(side->stream, pr->ev_main, 0));
-    TRY(ntt_run(side, pr->P7->d + 5 * S, 0, n + 3, pr->E7->d + 5 * n8, 0, k8, false, true, 1));
-    ZKP_CUDA(ctx, cudaEventRecord(pr->ev_side, side->stream));
-    TRY(commit_group(pr, &zp, 1, comms + 12 * 4));
+    // z on the 8n coset needs no further challenge either: second stream, under the z commitment's reduction
+    SideJob z8 = {pr, pr->P7->d + 5 * S, 0, n + 3, pr->E7->d + 5 * n8, 1, ZKP_OK};
+    TRY(commit_group_with(pr, &zp, 1, comms + 12 * 4, &z8));
     tr.append_commitment("z", comms + 12 * 4);
 
     // round 3: quotient on the 8n coset (src/prover.rs:201-287, quotient_poly.rs)

@@ -954,6 +954,11 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
 #undef ZKP_ACC
     ZKP_LAUNCHED(ctx);
     }
+    if (ctx->after_accumulate) {
+        void (*hook)(void*) = ctx->after_accumulate;
+        ctx->after_accumulate = nullptr;
+        hook(ctx->after_accumulate_arg);
+    }
     {
     ProfScope prof(ctx, "msm_reduce");
     msm_merge_kernel<<<dim3((B + 127) / 128, nb), 128, 0, st>>>(s->offsets, s->counts, B, (uint32_t)L, nchunks, s->slots,
