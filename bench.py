@@ -251,7 +251,7 @@ def main():
         return
 
     import dusk_plonk_b200 as z
-    from oracle.rng import random_fr_raw_limbs  # synthetic input generator only (SplitMix64)
+    from dusk_plonk_b200.synthetic import random_fr_raw_limbs   # the product's own input generator
 
     dist = None
     if world > 1:
@@ -282,7 +282,7 @@ def main():
         from dusk_plonk_b200.composer import synthetic_circuit
         from dusk_plonk_b200.field import fr_to_mont1
         from dusk_plonk_b200.plonk_params import PlonkParams
-        from oracle.rng import SplitMix64   # seeded input generator only
+        from dusk_plonk_b200.synthetic import SplitMix64
         circ = synthetic_circuit(args.logn)
         rng = SplitMix64(8349)
         tau = rng.fr()
