@@ -516,22 +516,37 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     // rounds 4/5: evaluations, linearisation, openings (src/prover.rs:289-452)
     const fr zc = tr.challenge_scalar("z_challenge");
     const fr zw = F::mul(zc, fr_load(key.generator));
-    zkp_poly_ref at_z[12];
-    at_z[0] = ref(pr->T, 0, n8);
-    for (unsigned j = 0; j < 4; j++) at_z[1 + j] = wp[j];
-    static const int atz_key[7] = {S1, S2, S3, Q_ARITH, Q_C, Q_L, Q_R};
-    for (unsigned j = 0; j < 7; j++) at_z[5 + j] = key.poly[atz_key[j]];
-    uint64_t e1[12 * 4], e2[4 * 4];
-    TRY(zkp_poly_eval_dev(ctx, at_z, 12, zc.l, e1));
-    const zkp_poly_ref at_zw[4] = {wp[0], wp[1], wp[3], zp};
-    TRY(zkp_poly_eval_dev(ctx, at_zw, 4, zw.l, e2));
-    const fr t_eval = fr_load(e1);
-    const fr a = fr_load(e1 + 4), b = fr_load(e1 + 8), c = fr_load(e1 + 12), d = fr_load(e1 + 16);
-    const fr s1 = fr_load(e1 + 20), s2 = fr_load(e1 + 24), s3 = fr_load(e1 + 28);
-    const fr qarith = fr_load(e1 + 32), qc = fr_load(e1 + 36), ql = fr_load(e1 + 40), qr = fr_load(e1 + 44);
-    const fr an = fr_load(e2), bn = fr_load(e2 + 4), dn = fr_load(e2 + 8), pe = fr_load(e2 + 12);
+    // Every opening of the proof in ONE batched launch and one read-back: the 12 evaluations at z, the 4
+    // at z w, and the nine linearisation polynomials not among them at z -- r(X) = sum_j sc_j p_j(X) is
+    // linear in the p_j, so r(z) = sum_j sc_j p_j(z) needs no evaluation of r itself
+    // (linearization_poly.rs:52-73,107-110: same field element).
+    enum { E_T = 0, E_A, E_B, E_C, E_D, E_S1, E_S2, E_S3, E_QARITH, E_QC, E_QL, E_QR,       // at z
+           E_QM, E_QO, E_QD, E_QRANGE, E_QLOGIC, E_QFIXED, E_QVAR, E_Z, E_S4,               // at z (for r)
+           E_AN, E_BN, E_DN, E_PERM, E_COUNT };                                             // at z w
+    zkp_poly_ref ep[E_COUNT];
+    uint8_t which[E_COUNT];
+    memset(which, 0, sizeof which);
+    ep[E_T] = ref(pr->T, 0, n8);
+    for (unsigned j = 0; j < 4; j++) ep[E_A + j] = wp[j];
+    ep[E_S1] = key.poly[S1]; ep[E_S2] = key.poly[S2]; ep[E_S3] = key.poly[S3];
+    ep[E_QARITH] = key.poly[Q_ARITH]; ep[E_QC] = key.poly[Q_C]; ep[E_QL] = key.poly[Q_L]; ep[E_QR] = key.poly[Q_R];
+    ep[E_QM] = key.poly[Q_M]; ep[E_QO] = key.poly[Q_O]; ep[E_QD] = key.poly[Q_D];
+    ep[E_QRANGE] = key.poly[Q_RANGE]; ep[E_QLOGIC] = key.poly[Q_LOGIC]; ep[E_QFIXED] = key.poly[Q_FIXED];
+    ep[E_QVAR] = key.poly[Q_VAR]; ep[E_Z] = zp; ep[E_S4] = key.poly[S4];
+    ep[E_AN] = wp[0]; ep[E_BN] = wp[1]; ep[E_DN] = wp[3]; ep[E_PERM] = zp;
+    for (unsigned j = E_AN; j < E_COUNT; j++) which[j] = 1;
+    uint64_t pts[8], ev_raw[E_COUNT * 4];
+    memcpy(pts, zc.l, 32);
+    memcpy(pts + 4, zw.l, 32);
+    TRY(zkp_poly_eval2_dev(ctx, ep, which, E_COUNT, pts, ev_raw));
+    auto E = [&](int i) { return fr_load(ev_raw + 4 * i); };
+    const fr t_eval = E(E_T);
+    const fr a = E(E_A), b = E(E_B), c = E(E_C), d = E(E_D);
+    const fr s1 = E(E_S1), s2 = E(E_S2), s3 = E(E_S3);
+    const fr qarith = E(E_QARITH), qc = E(E_QC), ql = E(E_QL), qr = E(E_QR);
+    const fr an = E(E_AN), bn = E(E_BN), dn = E(E_DN), pe = E(E_PERM);
 
-    // r(X) = sum scalar * poly(X)
+    // r(X) = sum scalar * poly(X): the polynomial itself is still needed for the opening witness
     fr sc[12];
     zkp_poly_ref lr[12];
     static const int lin_key[10] = {Q_M, Q_L, Q_R, Q_O, Q_D, Q_C, Q_RANGE, Q_LOGIC, Q_FIXED, Q_VAR};
@@ -549,9 +564,11 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     for (unsigned j = 0; j < 12; j++) fr_store(scl + 4 * j, sc[j]);
     TRY(zkp_poly_lincomb_dev(ctx, lr, scl, 12, pr->R, 0, n + 3));
     const zkp_poly_ref rr = ref(pr->R, 0, n + 3);
-    uint64_t e3[4];
-    TRY(zkp_poly_eval_dev(ctx, &rr, 1, zc.l, e3));
-    const fr r_eval = fr_load(e3);
+    fr r_eval = F::zero();
+    {
+        static const int lin_eval[12] = {E_QM, E_QL, E_QR, E_QO, E_QD, E_QC, E_QRANGE, E_QLOGIC, E_QFIXED, E_QVAR, E_Z, E_S4};
+        for (unsigned j = 0; j < 12; j++) r_eval = F::add(r_eval, F::mul(sc[j], E(lin_eval[j])));
+    }
 
     // evaluations in `Evaluations` order (prover.py EVAL_NAMES)
     const fr ev[16] = {a, b, c, d, an, bn, dn, s1, s2, s3, qarith, qc, ql, qr, pe, r_eval};

@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ Q
 }
 
 // ------------------------------------------------------------------ batched evaluation
-static constexpr unsigned EV_MAX = 16;   // polynomials per launch
+static constexpr unsigned EV_MAX = 32;   // polynomials per launch
 static constexpr unsigned EV_L = 32;     // coefficients per thread (the serial Horner part runs with every lane
                                          // busy; the tree that follows does not, so it is kept a small share)
 static constexpr unsigned EV_T = 256;    // threads per block
@@ -329,7 +329,8 @@ static_assert((1u << EV_BLOCK_LOG) == EV_T * EV_L, "block chunk");
 struct EvalArgs {
     const fr_t* p[EV_MAX];
     uint64_t len[EV_MAX];
-    fr_t pw[28];  // point^(2^j)
+    fr_t pw[2][28];        // point_k^(2^j) for the (up to) two evaluation points of a launch
+    uint8_t which[EV_MAX]; // point of polynomial y
     unsigned nblocks;
     fr_t* partial;  // [count][nblocks]
 };
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(EV_T) eval_block_kernel(const __grid_constant_
     const unsigned y = blockIdx.y, tid = threadIdx.x;
     const fr_t* p = a.p[y];
     const size_t len = a.len[y];
+    const fr_t* pw = a.pw[a.which[y]];
     // thread t takes coefficients base + t + j EV_T (consecutive threads read consecutive elements:
     // coalesced), Horner in X^EV_T; the tree then weighs thread t by X^t
     static_assert(EV_T == 256, "X^EV_T is pw[8]");
@@ -354,14 +356,14 @@ __global__ void __launch_bounds__(EV_T) eval_block_kernel(const __grid_constant_
         for (int j = EV_L - 1; j >= 0; j--) {
             const size_t i = base + (size_t)j * EV_T + tid;
             const fr_t c = i < len ? pld(p + i) : fr_t::zero();
-            s = j == (int)EV_L - 1 ? c : s * a.pw[8] + c;
+            s = j == (int)EV_L - 1 ? c : s * pw[8] + c;
         }
     }
     sm[tid] = s;
     __syncthreads();
     unsigned lvl = 0;
     for (unsigned st = 1; st < EV_T; st <<= 1, lvl++) {
-        if ((tid & (2 * st - 1)) == 0) sm[tid] = sm[tid] + a.pw[lvl] * sm[tid + st];
+        if ((tid & (2 * st - 1)) == 0) sm[tid] = sm[tid] + pw[lvl] * sm[tid + st];
         __syncthreads();
     }
     if (tid == 0) pst(a.partial + (size_t)y * a.nblocks + blockIdx.x, sm[0]);
@@ -372,6 +374,7 @@ __global__ void __launch_bounds__(EV_T) eval_final_kernel(const __grid_constant_
     __shared__ fr_t sm[EV_T];
     const unsigned y = blockIdx.x, tid = threadIdx.x;
     const fr_t* part = a.partial + (size_t)y * a.nblocks;
+    const fr_t* pw = a.pw[a.which[y]];
     // thread t owns blocks [t*per, (t+1)*per): per is a power of two so X^per is in the table
     unsigned per_log = 0;
     while (((size_t)EV_T << per_log) < a.nblocks) per_log++;
@@ -381,13 +384,13 @@ __global__ void __launch_bounds__(EV_T) eval_final_kernel(const __grid_constant_
     if (lo < a.nblocks) {
         const size_t hi = lo + per < a.nblocks ? lo + per : a.nblocks;
         s = pld(part + hi - 1);
-        for (size_t i = hi - 1; i-- > lo;) s = s * a.pw[EV_BLOCK_LOG] + pld(part + i);
+        for (size_t i = hi - 1; i-- > lo;) s = s * pw[EV_BLOCK_LOG] + pld(part + i);
     }
     sm[tid] = s;
     __syncthreads();
     unsigned lvl = EV_BLOCK_LOG + per_log;
     for (unsigned st = 1; st < EV_T; st <<= 1, lvl++) {
-        if ((tid & (2 * st - 1)) == 0) sm[tid] = sm[tid] + a.pw[lvl < 28 ? lvl : 27] * sm[tid + st];
+        if ((tid & (2 * st - 1)) == 0) sm[tid] = sm[tid] + pw[lvl < 28 ? lvl : 27] * sm[tid + st];
         __syncthreads();
     }
     if (tid == 0) pst(out + y, sm[0]);
@@ -674,21 +677,34 @@ int zkp_quotient_range_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* q
     return ZKP_OK;
 }
 
-int zkp_poly_eval_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, unsigned count, const uint64_t point[4],
-                      uint64_t* out) {
-    if (!ctx || !polys || !point || !out || count == 0 || count > EV_MAX) return ZKP_ERR_INVALID;
+int zkp_poly_eval2_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, const uint8_t* which, unsigned count,
+                       const uint64_t points[8], uint64_t* out) {
+    if (!ctx || !polys || !points || !out || count == 0 || count > EV_MAX) return ZKP_ERR_INVALID;
     size_t maxlen = 0;
     for (unsigned i = 0; i < count; i++) {
-        if (!CHECK_REF(polys[i])) return ZKP_ERR_INVALID;
+        if (!CHECK_REF(polys[i]) || (which && which[i] > 1)) return ZKP_ERR_INVALID;
         if (polys[i].len > maxlen) maxlen = polys[i].len;
     }
     int rc;
     if ((rc = set_device(ctx))) return rc;
     EvalArgs a;
     memset(&a, 0, sizeof a);
-    for (unsigned i = 0; i < count; i++) { a.p[i] = polys[i].buf->d + polys[i].off; a.len[i] = polys[i].len; }
-    a.pw[0] = fr_from_host(point);
-    for (int j = 1; j < 28; j++) a.pw[j] = sqr(a.pw[j - 1]);
+    bool second = false;
+    for (unsigned i = 0; i < count; i++) {
+        a.p[i] = polys[i].buf->d + polys[i].off;
+        a.len[i] = polys[i].len;
+        a.which[i] = which ? which[i] : 0;
+        second = second || a.which[i];
+    }
+    for (int k = 0; k < (second ? 2 : 1); k++) {
+        // 64-bit-limb host arithmetic for the 27 squarings (the device header's host emulation is 10x slower)
+        hostfr::fr v;
+        memcpy(v.l, points + 4 * k, 32);
+        for (int j = 0; j < 28; j++) {
+            memcpy(a.pw[k][j].l, v.l, 32);
+            v = hostfr::mul(v, v);
+        }
+    }
     const size_t per_block = (size_t)EV_T * EV_L;
     a.nblocks = (unsigned)((maxlen + per_block - 1) / per_block);
     if (a.nblocks == 0) a.nblocks = 1;
@@ -707,6 +723,13 @@ int zkp_poly_eval_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, unsigned count, c
     ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(out, h, count * sizeof(fr_t));
     return ZKP_OK;
+}
+
+int zkp_poly_eval_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, unsigned count, const uint64_t point[4],
+                      uint64_t* out) {
+    if (!point) return ZKP_ERR_INVALID;
+    uint64_t pts[8] = {point[0], point[1], point[2], point[3], 0, 0, 0, 0};
+    return zkp_poly_eval2_dev(ctx, polys, nullptr, count, pts, out);
 }
 
 int zkp_poly_lincomb_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, const uint64_t* scalars, unsigned count,

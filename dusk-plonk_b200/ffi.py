@@ -96,6 +96,7 @@ SIGNATURES.update({
     "zkp_quotient_dev": (_int, [_vp, _uint, ctypes.POINTER(QuotientArgs), _vp, _sz]),
     "zkp_quotient_range_dev": (_int, [_vp, _uint, ctypes.POINTER(QuotientArgs), _sz, _sz, _vp, _sz]),
     "zkp_poly_eval_dev": (_int, [_vp, ctypes.POINTER(PolyRef), _uint, _vp, _vp]),
+    "zkp_poly_eval2_dev": (_int, [_vp, ctypes.POINTER(PolyRef), _vp, _uint, _vp, _vp]),
     "zkp_poly_lincomb_dev": (_int, [_vp, ctypes.POINTER(PolyRef), _vp, _uint, _vp, _sz, _sz]),
     "zkp_poly_div_linear_dev": (_int, [_vp, PolyRef, _vp, _vp, _sz]),
 })
@@ -371,6 +372,15 @@ class Context:
         pt = np.ascontiguousarray(point, dtype=np.uint64).reshape(4)
         out = np.zeros((len(refs), 4), dtype=np.uint64)
         self.check(self.lib.zkp_poly_eval_dev(self.h, arr, len(refs), _ptr(pt), _ptr(out)))
+        return out
+
+    def poly_eval2(self, refs, which, points):
+        """Polynomial i at points[which[i]] (two points, one launch)."""
+        arr = (PolyRef * len(refs))(*refs)
+        w = np.ascontiguousarray(which, dtype=np.uint8)
+        pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(8)
+        out = np.zeros((len(refs), 4), dtype=np.uint64)
+        self.check(self.lib.zkp_poly_eval2_dev(self.h, arr, _ptr(w), len(refs), _ptr(pts), _ptr(out)))
         return out
 
     def poly_lincomb(self, refs, scalars, out, out_off, out_len):

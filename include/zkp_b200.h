@@ -206,9 +206,14 @@ int zkp_quotient_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* args, z
 int zkp_quotient_range_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* args, size_t first, size_t count,
                            zkp_buf* out, size_t out_off);
 
-/* Coefficients::evaluate for up to 16 polynomials at one point (linearization_poly.rs:52-73). */
+/* Coefficients::evaluate for up to 32 polynomials at one point (linearization_poly.rs:52-73). */
 int zkp_poly_eval_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, unsigned count, const uint64_t point[4],
                       uint64_t* out /* count x 4 */);
+/* The same for up to 32 polynomials at up to two points in one launch and one read-back: polynomial i
+ * is evaluated at points[which[i]] (which = NULL: all at points[0]).  The round driver opens every
+ * polynomial of a proof -- at z and at z w -- with one call. */
+int zkp_poly_eval2_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, const uint8_t* which, unsigned count,
+                       const uint64_t points[8], uint64_t* out /* count x 4 */);
 /* out[i] = sum_k scalars[k] * polys[k][i], i < out_len (polys zero beyond their len; count <= 16):
  * widget.linearize sums, t_low + z^n t_mid + .., sum_i v^i p_i. */
 int zkp_poly_lincomb_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, const uint64_t* scalars, unsigned count,

@@ -45,6 +45,17 @@ def test_poly_eval_large_and_offsets(ctx):
     assert got == [poly_eval(p, pt), poly_eval(p[100:5100], pt), p[-1]]
 
 
+def test_poly_eval_two_points_one_launch(ctx):
+    """zkp_poly_eval2_dev: 25 ragged polynomials (the shape of a proof's openings), each at one of two points."""
+    lens = [1 << 15] + [4099] * 4 + [4096] * 16 + [4099, 4098, 1, 8193]
+    polys = [rand_vec(900 + i, l) for i, l in enumerate(lens)]
+    bufs = [ctx.upload(fr_to_mont(p)) for p in polys]
+    z0, z1 = rand_vec(55, 2)
+    which = [0] * 21 + [1] * 4
+    got = fr_from_mont(ctx.poly_eval2([ctx.ref(b) for b in bufs], which, np.stack([fr_to_mont1(z0), fr_to_mont1(z1)])))
+    assert got == [poly_eval(p, z1 if w else z0) for p, w in zip(polys, which)]
+
+
 @pytest.mark.parametrize("n", [2, 3, 16, 17, 33, 1000, 16385, 32768 + 5, 100003])
 def test_div_linear_is_ruffini(ctx, n):
     p = rand_vec(n, n)
