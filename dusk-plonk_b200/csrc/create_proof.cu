@@ -6,12 +6,14 @@
 // src/prover.rs:99-105,139-199,203-226,268-295,321-405,435-450), the scalar side of the
 // linearisation (src/prover/linearization_poly.rs:75-105,136-225) and the proof wire format
 // (src/prover/proof.rs:36-66).  Polynomials stay in HBM for the whole proof; per proof the host
-// sees 11 affine points and 17 field elements, and sends 8 challenges.
+// reads back 11 points and 26 field elements at six synchronisation points (four commit groups, the
+// permutation product, one batched opening of all 25 evaluations) and sends 8 challenges.
 //
 // Streams: the 8n-coset transforms of a, b, c, d, PI (and later z) depend on nothing the
-// transcript still has to produce, so they run on a second stream under the wire / z
-// commitments (whose bucket-reduction tail leaves most SMs idle); event dependencies only, no
-// host synchronisation beyond the reads the transcript needs.
+// transcript still has to produce, so they run on a second stream, queued behind the accumulate
+// kernel of the wire / z commitment (zkp_ctx::after_accumulate): they execute under its
+// latency-bound bucket reduction instead of competing with the accumulation for the integer pipe.
+// Event dependencies only, no host synchronisation beyond the reads the transcript needs.
 #include <string.h>
 
 #include <new>
