@@ -239,6 +239,7 @@ struct QuotArgs {
     uint32_t mask;
     size_t n8;
     size_t first, count;  // evaluate indices [first, first + count) (a rank's slice when sharded)
+    int sliced;           // w / z / pi / l1 hold only [first, first + count + 8): index them relative to first
     fr_t* out;
 };
 
@@ -250,16 +251,19 @@ __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ Q
     const size_t t_ = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t_ >= q.count) return;
     const size_t i = q.first + t_;
-    const size_t in = (i + 8) & (q.n8 - 1);  // "next gate" on the 8n coset (quotient_poly.rs:60-66)
+    // "next gate" on the 8n coset (quotient_poly.rs:60-66).  wi / win index the witness-side vectors
+    // (wires, z, PI, L1): absolute, or relative to the slice (whose 8-element halo holds the wrap-around)
+    const size_t wi = q.sliced ? t_ : i;
+    const size_t win = q.sliced ? t_ + 8 : (i + 8) & (q.n8 - 1);
     const fr_t one = fr_t::one(), two = dbl(one), three = two + one;
-    const fr_t a = pld(q.w[0] + i), b = pld(q.w[1] + i), c = pld(q.w[2] + i), d = pld(q.w[3] + i);
+    const fr_t a = pld(q.w[0] + wi), b = pld(q.w[1] + wi), c = pld(q.w[2] + wi), d = pld(q.w[3] + wi);
     const fr_t qc = pld(q.sel[4] + i);
     // arithmetic widget + PI
     fr_t t = a * b * pld(q.sel[0] + i) + a * pld(q.sel[1] + i) + b * pld(q.sel[2] + i) + c * pld(q.sel[3] + i) +
              d * pld(q.sel[5] + i) + qc;
-    t = t * pld(q.sel[6] + i) + pld(q.pi + i);
+    t = t * pld(q.sel[6] + i) + pld(q.pi + wi);
     if (q.mask) {
-        const fr_t an = pld(q.w[0] + in), bn = pld(q.w[1] + in), dn = pld(q.w[3] + in);
+        const fr_t an = pld(q.w[0] + win), bn = pld(q.w[1] + win), dn = pld(q.w[3] + win);
         if (q.mask & 1u) {  // range
             const fr_t k = sqr(q.rs), k2 = sqr(k), k3 = k2 * k;
             fr_t s = delta4(c - mul_small<4>(d), one, two, three) + delta4(b - mul_small<4>(c), one, two, three) * k +
@@ -306,14 +310,14 @@ __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ Q
     }
     // permutation argument (quotient_poly.rs:245-261)
     {
-        const fr_t z = pld(q.z + i), zn = pld(q.z + in), x = pld(q.linear + i);
+        const fr_t z = pld(q.z + wi), zn = pld(q.z + win), x = pld(q.linear + i);
         const fr_t ag = a + q.gamma, bg = b + q.gamma, cg = c + q.gamma, dg = d + q.gamma;
         // beta K_j x = K_j (beta x) with K = 7, 13, 17 (src/permutation.rs:28-30): additions, not multiplications
         const fr_t bx = q.beta * x;
         fr_t ident = (ag + bx) * (bg + mul_small<7>(bx)) * ((cg + mul_small<13>(bx)) * (dg + mul_small<17>(bx))) * z;
         fr_t copy = (ag + q.beta * pld(q.sigma[0] + i)) * (bg + q.beta * pld(q.sigma[1] + i)) *
                     ((cg + q.beta * pld(q.sigma[2] + i)) * (dg + q.beta * pld(q.sigma[3] + i))) * zn;
-        t = t + (ident - copy) * q.alpha + (z - one) * pld(q.l1 + i);
+        t = t + (ident - copy) * q.alpha + (z - one) * pld(q.l1 + wi);
     }
     pst(q.out + i, t * q.zh_inv[i & 7]);
 }
@@ -644,9 +648,17 @@ int zkp_quotient_range_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* q
         *p = r.buf->d + r.off;
         return true;
     };
+    // witness-side vectors: whole, or (q->sliced) only the rank's slice plus an 8-element halo
+    const bool sliced = q->sliced != 0;
+    auto wptr = [&](const zkp_poly_ref& r, const fr_t** p) {
+        if (!sliced) return ptr(r, p);
+        if (!CHECK_REF(r) || r.len < count + 8) return false;
+        *p = r.buf->d + r.off;
+        return true;
+    };
     bool ok = true;
-    for (int j = 0; j < 4; j++) ok = ok && ptr(q->wires[j], &a.w[j]) && ptr(q->sigma[j], &a.sigma[j]);
-    ok = ok && ptr(q->z, &a.z) && ptr(q->pi, &a.pi) && ptr(q->l1, &a.l1) && ptr(q->linear, &a.linear);
+    for (int j = 0; j < 4; j++) ok = ok && wptr(q->wires[j], &a.w[j]) && ptr(q->sigma[j], &a.sigma[j]);
+    ok = ok && wptr(q->z, &a.z) && wptr(q->pi, &a.pi) && wptr(q->l1, &a.l1) && ptr(q->linear, &a.linear);
     for (int j = 0; j < 11; j++) ok = ok && ptr(q->sel[j], &a.sel[j]);
     if (!ok) return ZKP_ERR_INVALID;
     int rc;
@@ -669,6 +681,7 @@ int zkp_quotient_range_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* q
     a.n8 = n8;
     a.first = first;
     a.count = count;
+    a.sliced = sliced ? 1 : 0;
     a.out = out->d + out_off;
     if (count == 0) return ZKP_OK;
     ProfScope prof(ctx, "quotient");

@@ -83,7 +83,7 @@ class QuotientArgs(ctypes.Structure):
     _fields_ = [("wires", PolyRef * 4), ("z", PolyRef), ("pi", PolyRef), ("l1", PolyRef),
                 ("sel", PolyRef * 11), ("sigma", PolyRef * 4), ("linear", PolyRef),
                 ("challenges", (ctypes.c_uint64 * 4) * 7), ("zh_inv", (ctypes.c_uint64 * 4) * 8),
-                ("widget_mask", ctypes.c_uint32)]
+                ("widget_mask", ctypes.c_uint32), ("sliced", ctypes.c_uint32)]
 
 
 SIGNATURES.update({

@@ -108,22 +108,29 @@ class Prover:
             if comm is not None:
                 # sharded proof: the buffers NCCL gathers into are torch tensors the kernels address too;
                 # E7 is padded to a whole number of rounds of `world` polynomials
+                # sharded proof: each GPU transforms one of the seven polynomials to the 8n coset and the
+                # ranks exchange SLICES (all-to-all): rank s only ever needs the evaluations its part of the
+                # quotient reads, [s per, (s + 1) per + 8) of each polynomial.  E7 holds those slices.
                 torch = comm.torch
                 G = comm.world
                 slots = -(-7 // G) * G
+                self._hl = 8 * n // G + 8
                 dev = torch.device("cuda", c.device)
-                self._t_E7 = torch.empty(slots * 8 * n * 4, dtype=torch.int64, device=dev)
+                self._t_E7 = torch.empty(slots * self._hl * 4, dtype=torch.int64, device=dev)
                 self._t_T = torch.empty(8 * n * 4, dtype=torch.int64, device=dev)
                 self._t_stage = torch.empty(8 * n * 4, dtype=torch.int64, device=dev)
-                E7 = c.wrap(self._t_E7.data_ptr(), slots * 8 * n)
+                self._t_send = torch.empty(G * self._hl * 4, dtype=torch.int64, device=dev)
+                self._full8 = c.wrap(self._t_stage.data_ptr(), 8 * n)
+                E7 = c.wrap(self._t_E7.data_ptr(), slots * self._hl)
                 Tbuf = c.wrap(self._t_T.data_ptr(), 8 * n)
             else:
                 E7, Tbuf = c.alloc(7 * 8 * n), c.alloc(8 * n)
+            e8n = 8 * n if comm is None else self._hl      # elements each coset vector occupies in E7
             ws = {"W": c.alloc(4 * n), "Z": c.alloc(n), "P7": P7, "E7": E7, "S": S,
                   "wp": [_View(P7, j * S, n + 2) for j in range(4)], "PI": _View(P7, 4 * S, n),
                   "zp": _View(P7, 5 * S, n + 3), "L1": _View(P7, 6 * S, n),
-                  "e8": [_View(E7, j * 8 * n, 8 * n) for j in range(4)], "pi8": _View(E7, 4 * 8 * n, 8 * n),
-                  "z8": _View(E7, 5 * 8 * n, 8 * n), "l18": _View(E7, 6 * 8 * n, 8 * n),
+                  "e8": [_View(E7, j * e8n, e8n) for j in range(4)], "pi8": _View(E7, 4 * e8n, e8n),
+                  "z8": _View(E7, 5 * e8n, e8n), "l18": _View(E7, 6 * e8n, e8n),
                   "T": Tbuf, "R": c.alloc(n + 3),
                   "AGG": c.alloc(5 * n), "WZ": c.alloc(5 * n), "SAGG": c.alloc(n + 3), "WZW": c.alloc(n + 3)}
             self._ws = ws
@@ -292,21 +299,23 @@ class Prover:
             ctx.ntt_dev(ws["L1"], n, ws["l18"], k8, False, True)
             side.sync()
         else:
-            # sharded proof: the seven coset transforms are dealt out one per GPU and all-gathered
-            # over NVLink (each is as large as the whole proving-key column it will meet)
-            G, rank = comm.world, comm.rank
+            # sharded proof: the seven coset transforms are dealt out one per GPU; every rank then needs only
+            # its slice of each (plus the 8 "next gate" evaluations), so the exchange is an all-to-all of
+            # slices over NVLink -- 1/G of the bytes an all-gather of whole vectors would move
+            G, rank, hl = comm.world, comm.rank, self._hl
             for r0 in range(0, 7, G):
                 j = r0 + rank
                 if j < 7:
-                    ctx.ntt_dev(_View(ws["P7"], j * ws["S"], n + 3), n + 3, _View(ws["E7"], j * n8, n8), k8, False, True)
+                    ctx.ntt_dev(_View(ws["P7"], j * ws["S"], n + 3), n + 3, self._full8, k8, False, True)
                 ctx.sync()
-                comm.all_gather_device(self._t_E7[r0 * n8 * 4:(r0 + G) * n8 * 4],
-                                       self._t_E7[(r0 + rank) * n8 * 4:(r0 + rank + 1) * n8 * 4], self._t_stage)
+                comm.exchange_slices(self._t_E7[r0 * hl * 4:(r0 + G) * hl * 4], self._t_stage, self._t_send, n8)
         qa = QuotientArgs()
+        wl = n8 if comm is None else self._hl       # whole coset vectors, or this rank's slices + halo
         for j in range(4):
-            qa.wires[j] = ref(ws["e8"][j], 0, n8)
+            qa.wires[j] = ref(ws["e8"][j], 0, wl)
             qa.sigma[j] = ref(pk.eval8["s_sigma_%d" % (j + 1)], 0, n8)
-        qa.z, qa.pi, qa.l1 = ref(ws["z8"], 0, n8), ref(ws["pi8"], 0, n8), ref(ws["l18"], 0, n8)
+        qa.z, qa.pi, qa.l1 = ref(ws["z8"], 0, wl), ref(ws["pi8"], 0, wl), ref(ws["l18"], 0, wl)
+        qa.sliced = 0 if comm is None else 1
         for j, s in enumerate(SELECTORS):
             qa.sel[j] = ref(pk.eval8[s], 0, n8)
         qa.linear = ref(pk.eval8["linear"], 0, n8)

@@ -44,6 +44,21 @@ class Communicator:
         self.torch.cuda.synchronize()
 
 
+    def exchange_slices(self, recv, full, send, n):
+        """All-to-all of slices: this rank holds ``full`` (n Fr as 4 int64 each); rank s receives its
+        elements [s per, (s + 1) per + 8) (indices mod n, per = n / world) from every rank.  ``recv``
+        ends up as [source rank][per + 8] Fr."""
+        torch, G = self.torch, self.world
+        per = n // G
+        f4 = full[:n * 4].view(n, 4)
+        s3 = send[:G * (per + 8) * 4].view(G, per + 8, 4)
+        s3[:, :per] = f4.view(G, per, 4)
+        starts = ((torch.arange(G, device=full.device) + 1) * per) % n
+        s3[:, per:] = f4[starts[:, None] + torch.arange(8, device=full.device)[None, :]]
+        self.dist.all_to_all_single(recv, send[:G * (per + 8) * 4])
+        torch.cuda.synchronize()
+
+
 class LocalCommunicator:
     """world_size 1 stand-in (and the unit-test double)."""
     rank, world = 0, 1

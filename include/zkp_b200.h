@@ -199,6 +199,10 @@ typedef struct zkp_quotient_args {
     uint64_t zh_inv[8][4];        /* 1 / Z_H on the coset: period 8 */
     uint32_t widget_mask;         /* bit0 range, 1 logic, 2 fixed-base, 3 var-base: clear = selector
                                      polynomial identically zero, widget skipped (contributes 0) */
+    uint32_t sliced;              /* zkp_quotient_range_dev only: wires, z, pi, l1 hold just the evaluations
+                                     [first, first + count + 8) (indices mod 8n: the 8-element halo is the
+                                     "next gate" of the last points) -- what a rank receives when the coset
+                                     transforms are dealt out over GPUs and exchanged by all-to-all */
 } zkp_quotient_args;
 int zkp_quotient_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* args, zkp_buf* out, size_t out_off);
 /* Only the evaluations [first, first + count) of the same vector (out[i] for those i): one rank's
