@@ -56,7 +56,8 @@ class Communicator:
         starts = ((torch.arange(G, device=full.device) + 1) * per) % n
         s3[:, per:] = f4[starts[:, None] + torch.arange(8, device=full.device)[None, :]]
         self.dist.all_to_all_single(recv, send[:G * (per + 8) * 4])
-        torch.cuda.synchronize()
+        if full.is_cuda:
+            torch.cuda.synchronize()
 
 
 class LocalCommunicator:

@@ -111,6 +111,52 @@ def test_sharded_commit_two_ranks_gloo():
     assert res[0][2] == res[1][2]     # every rank derives the same commitment -> same transcript
 
 
+def _slice_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dusk_plonk_b200.sharding import Communicator
+        comm = Communicator()
+        for n in (64, 1024):
+            per = n // world
+            # element i of rank r's vector: limbs (r, i, i * i, 7)
+            i = torch.arange(n, dtype=torch.int64)
+            full = torch.stack([torch.full_like(i, rank), i, i * i, torch.full_like(i, 7)], dim=1).reshape(-1).clone()
+            send = torch.empty(world * (per + 8) * 4, dtype=torch.int64)
+            recv = torch.empty(world * (per + 8) * 4, dtype=torch.int64)
+            comm.exchange_slices(recv, full, send, n)
+            got = recv.view(world, per + 8, 4)
+            idx = (rank * per + torch.arange(per + 8, dtype=torch.int64)) % n     # my slice + the 8-element halo
+            for src in range(world):
+                want = torch.stack([torch.full_like(idx, src), idx, idx * idx, torch.full_like(idx, 7)], dim=1)
+                assert torch.equal(got[src], want), (n, src)
+        q.put((rank, "ok", None))
+    except Exception:
+        import traceback
+        q.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slice_exchange_gloo(world):
+    """The all-to-all of quotient slices of the sharded proof (Communicator.exchange_slices): rank s receives
+    elements [s per, (s + 1) per + 8) mod n of every rank's vector -- the halo wraps around for the last rank."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slice_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), [r[2] for r in res if r[1] != "ok"]
+
+
 def test_shard_ranges_cover_exactly():
     from dusk_plonk_b200.sharding import shard_range
     for total in (0, 1, 7, 39, 65543):
