@@ -59,3 +59,20 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(base, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "zkp_oracle" not in txt, f
+
+
+def test_round_driver_entry_points_reject_bad_arguments_without_a_gpu():
+    """Argument checks of the native round driver happen before any CUDA call: ZKP_ERR_INVALID, not a crash."""
+    import ctypes
+    import dusk_plonk_b200 as z
+    lib = z.load_library()
+    out = ctypes.c_void_p()
+    assert lib.zkp_prover_create(None, None, None, ctypes.byref(out)) == z.ZKP_ERR_INVALID
+    assert lib.zkp_prover_prove(None, None, None, None, None, None, None, None, None, None, None) == z.ZKP_ERR_INVALID
+    assert lib.zkp_prover_prove_witness(None, None, None, 0, None, None, None, None, None, None) == z.ZKP_ERR_INVALID
+    assert lib.zkp_prover_set_wiring(None, None, 0, None, 0) == z.ZKP_ERR_INVALID
+    assert lib.zkp_prover_destroy(None) == z.ZKP_OK
+    assert lib.zkp_poly_eval2_dev(None, None, None, 0, None, None) == z.ZKP_ERR_INVALID
+    assert lib.zkp_transcript_append(None, b"x", None, 0) == z.ZKP_ERR_INVALID
+    assert lib.zkp_linearization_scalars(5, None, None, None) == z.ZKP_ERR_INVALID
+    assert lib.zkp_g1_compress(None, None) == z.ZKP_ERR_INVALID
