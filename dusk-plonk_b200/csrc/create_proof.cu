@@ -19,6 +19,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "host_inv.h"
 
 struct zkp_prover {
     zkp_ctx* ctx = nullptr;
@@ -120,15 +121,11 @@ struct HostField {
         while (e) { if (e & 1) acc = mul(acc, base); base = sqr(base); e >>= 1; }
         return acc;
     }
-    static el inv(const el& a) {  // a^(p-2); 0 -> 0
-        uint64_t e[N]; memcpy(e, C().p, sizeof e);
-        e[0] -= 2;  // p is odd and > 2: no borrow
-        el acc = one();
-        for (int i = 64 * N - 1; i >= 0; i--) {
-            acc = sqr(acc);
-            if ((e[i / 64] >> (i % 64)) & 1) acc = mul(acc, a);
-        }
-        return acc;
+    static el inv(const el& a) {  // Montgomery form in and out; 0 -> 0.  Binary GCD (host_inv.h) on a R, then R^3 R^-1
+        static const el R3 = [] { el r2; memcpy(r2.l, C().r2, sizeof r2.l); return mul(r2, r2); }();
+        el x;
+        hostinv::inv_mod<N>(a.l, C().p, x.l);
+        return mul(x, R3);
     }
 };
 

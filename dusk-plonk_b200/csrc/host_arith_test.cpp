@@ -2,6 +2,7 @@
 // can be unit-tested without a GPU.  Built and driven by tests/test_host_arith.py.
 #include "arith.cuh"
 #include "g1.cuh"
+#include "host_inv.h"
 #include <cstring>
 using namespace zkp;
 
@@ -45,5 +46,10 @@ void ht_xyzz_to_affine(const uint32_t* acc, uint32_t* aff) {
     g1_xyzz A; std::memcpy(&A, acc, sizeof(A));
     g1_affine Q = xyzz_to_affine(A);
     std::memcpy(aff, &Q, sizeof(Q));
+}
+// plain modular inverse by the binary-GCD routine of host_inv.h: y, m, out as N64 x u64 (N64 = 4 or 6)
+void ht_inv_mod(const uint64_t* y, const uint64_t* m, uint64_t* out, int n64) {
+    if (n64 == 4) hostinv::inv_mod<4>(y, m, out);
+    else hostinv::inv_mod<6>(y, m, out);
 }
 }

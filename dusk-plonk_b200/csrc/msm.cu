@@ -30,6 +30,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "host_inv.h"
 
 namespace zkp {
 
@@ -713,14 +714,17 @@ static inline fq mul(const fq& a, const fq& b) {
     }
     fq r; memcpy(r.l, t, 48); return r;
 }
-static inline fq inv(const fq& a) {  // a^(p-2)
-    uint64_t e[6]; memcpy(e, P, 48); e[0] -= 2;
-    fq acc; memcpy(acc.l, ONE, 48);
-    for (int i = 383; i >= 0; i--) {
-        acc = mul(acc, acc);
-        if ((e[i / 64] >> (i % 64)) & 1) acc = mul(acc, a);
-    }
-    return acc;
+// a^-1 in Montgomery form for a in Montgomery form: plain inverse x = (a R)^-1 by binary GCD
+// (host_inv.h, ~5 us instead of the ~37 us of a Fermat chain), then x R^3 R^-1 = R / a.
+static inline fq inv(const fq& a) {
+    static const fq R3 = [] {
+        fq r2;
+        for (int i = 0; i < 6; i++) r2.l[i] = (uint64_t)FqParams::r2(2 * i) | ((uint64_t)FqParams::r2(2 * i + 1) << 32);
+        return mul(r2, r2);   // R^4 / R
+    }();
+    fq x;
+    hostinv::inv_mod<6>(a.l, P, x.l);
+    return mul(x, R3);
 }
 }  // namespace hostfq
 

@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "host_inv.h"
 
 namespace zkp {
 
@@ -203,14 +204,16 @@ static inline fr mul(const fr& a, const fr& b) {
     }
     fr r; memcpy(r.l, t, 32); return r;
 }
-static inline fr inv(const fr& a) {  // a^(r-2)
-    uint64_t e[4]; memcpy(e, P, 32); e[0] -= 2;
-    fr acc; memcpy(acc.l, ONE, 32);
-    for (int i = 255; i >= 0; i--) {
-        acc = mul(acc, acc);
-        if ((e[i / 64] >> (i % 64)) & 1) acc = mul(acc, a);
-    }
-    return acc;
+// a^-1 in Montgomery form: plain inverse of (a R) by binary GCD (host_inv.h), times R^3 R^-1
+static inline fr inv(const fr& a) {
+    static const fr R3 = [] {
+        fr r2;
+        for (int i = 0; i < 4; i++) r2.l[i] = (uint64_t)FrParams::r2(2 * i) | ((uint64_t)FrParams::r2(2 * i + 1) << 32);
+        return mul(r2, r2);
+    }();
+    fr x;
+    hostinv::inv_mod<4>(a.l, P, x.l);
+    return mul(x, R3);
 }
 }  // namespace hostfr
 

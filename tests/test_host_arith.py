@@ -111,3 +111,31 @@ def test_xyzz_group_law_with_edge_cases(L):
     assert toaff(acc) is None
     L.ht_xyzz_add(p(acc), p(a3))
     assert toaff(acc) == curve.mul(G, R_MOD - 60)
+
+
+def test_binary_gcd_inversion_matches_big_integer_inverse(L):
+    """csrc/host_inv.h (the host inversion at every transcript synchronisation point): y^-1 mod m for both
+    moduli, edge values (1, m - 1, powers of two around the 31 / 64-bit approximation boundaries, short
+    values) and random ones; 0 maps to 0 like the Fermat chain it replaces."""
+    import random
+    rng = random.Random(3)
+
+    def limbs(v, n):
+        return np.array([(v >> (64 * i)) & ((1 << 64) - 1) for i in range(n)], dtype=np.uint64)
+
+    def val(a):
+        return sum(int(x) << (64 * i) for i, x in enumerate(a))
+
+    for m, n in ((R_MOD, 4), (P_MOD, 6)):
+        mm = limbs(m, n)
+        cases = [1, 2, 3, m - 1, m - 2, (m - 1) // 2, (m + 1) // 2, 2 ** 31, 2 ** 31 - 1, 2 ** 33, 2 ** 62, 2 ** 64 - 1,
+                 2 ** 64, 2 ** 65 + 1, 2 ** 127, 2 ** 128 + 5]
+        cases += [rng.randrange(1, m) for _ in range(3000)]
+        cases += [(rng.randrange(1, 2 ** rng.randrange(1, 64 * n)) % m) or 1 for _ in range(1000)]
+        for y in cases:
+            out = np.zeros(n, dtype=np.uint64)
+            L.ht_inv_mod(p(limbs(y, n)), p(mm), p(out), n)
+            assert val(out) == pow(y, -1, m), hex(y)
+        out = np.ones(n, dtype=np.uint64)
+        L.ht_inv_mod(p(limbs(0, n)), p(mm), p(out), n)
+        assert val(out) == 0
