@@ -429,7 +429,6 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
                  const uint64_t* pi_host, const zkp_buf* pi_dev, const uint64_t* blinders, uint64_t* comms,
                  uint64_t* evals, uint8_t* proof_bytes, uint8_t* transcript_out) {
     zkp_ctx* ctx = pr->ctx;
-    zkp_ctx* side = pr->side;
     const zkp_proving_key& key = pr->key;
     const size_t n = pr->n, S = pr->S, n8 = 8 * n;
     const unsigned k = pr->k, k8 = k + 3;
