@@ -111,7 +111,6 @@ __global__ void k_check(int* bad) {
     // a * b * R52^-1, then the same through 32-bit limbs: compare after converting a, b to 12 x u32
     auto to32 = [](const fq52::el& e) {
         fq_t r = fq_t::zero();
-        unsigned long long lo = 0, carry_bits = 0; (void)lo; (void)carry_bits;
         // 8 x 52 bits -> 12 x 32 bits
         unsigned long long v[8];
         for (int i = 0; i < 8; i++) v[i] = (unsigned long long)e.l[i];
