@@ -602,16 +602,47 @@ __global__ void __launch_bounds__(128, 4) msm_final_coop_kernel(const g1_xyzz* p
     if ((threadIdx.x & 31) == 0) cs_emit(sm, AX, threadIdx.x >> 5, 0, out + blockIdx.x);
 }
 
-// T[w][i] = 2^c * T[w-1][i]: one thread per point walks the windows (load-time only).
+// T[w][i] = 2^c * T[w-1][i]: one thread per point walks the windows (load-time only).  The conversions to
+// affine share inversions in groups of 8 windows (Montgomery's trick; the numerators wait in the table slot
+// itself): W = 16 costs 2 Fermat chains per point instead of 15.  Same field elements as xyzz_to_affine.
 __global__ void __launch_bounds__(128) srs_table_window_kernel(g1_affine* table, size_t n, unsigned c, unsigned W) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    constexpr unsigned G = 8;
     g1_affine p = msm_ld_affine(table + i);
     g1_xyzz acc = g1_xyzz::inf();
     xyzz_madd(acc, p);
-    for (unsigned w = 1; w < W; w++) {
-        for (unsigned j = 0; j < c; j++) xyzz_dbl(acc);
-        table[(size_t)w * n + i] = xyzz_to_affine(acc);
+    for (unsigned w0 = 1; w0 < W; w0 += G) {
+        const unsigned cnt = W - w0 < G ? W - w0 : G;
+        fq_t zz[G], zzz[G], pre[G];
+        fq_t run = fq_t::one();
+#pragma unroll 1
+        for (unsigned g = 0; g < cnt; g++) {
+#pragma unroll 1
+            for (unsigned j = 0; j < c; j++) xyzz_dbl(acc);
+            g1_affine xy;
+            xy.x = acc.x; xy.y = acc.y;
+            table[(size_t)(w0 + g) * n + i] = xy;                 // X, Y: divided below
+            zz[g] = acc.zz;                                       // zero marks the point at infinity
+            zzz[g] = acc.is_inf() ? fq_t::one() : acc.zzz;
+            pre[g] = run;
+            run = run * zzz[g];
+        }
+        fq_t inv = inverse(run);
+#pragma unroll 1
+        for (unsigned g = cnt; g-- > 0;) {
+            const fq_t t = inv * pre[g];                          // 1 / ZZZ_g
+            inv = inv * zzz[g];
+            g1_affine* slot = table + (size_t)(w0 + g) * n + i;
+            g1_affine out = g1_affine::inf();
+            if (!zz[g].is_zero()) {
+                const g1_affine xy = *slot;
+                const fq_t zi = zz[g] * t;                        // 1 / ZZ = (ZZ / ZZZ)^2
+                out.x = xy.x * sqr(zi);
+                out.y = xy.y * t;
+            }
+            *slot = out;
+        }
     }
 }
 
