@@ -1,13 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 zkplonk hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload msm|ntt] [--logn L]
-    python bench.py --impl reference ...        # CPU restatement on the host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload prove|msm|ntt|compile] [--logn L]
+    python bench.py --impl reference ...        # CPU restatement on the host cores (rank 0 only)
 
-A "step" is one pass of the hot path over one batch of synthetic input.  With N > 1 the
-driver launches one rank per GPU through torchrun; the path shards by independent
-commitments, so every rank processes its own batch (weak scaling) and the only
-collective is the timing barrier / max-reduce.
+A "step" is one pass of the hot path over one batch of synthetic input: by default ONE
+``create_proof`` of the synthetic 2^20-gate circuit (BASELINE config 5).  With N > 1 the driver
+launches one rank per GPU through torchrun and the SAME job is sharded over the N GPUs (strong
+scaling; SURVEY 8e: commits split by SRS ranges with a partial-sum gather, coset transforms and
+quotient slices dealt out per GPU, four-step NTT with an all-to-all for --workload ntt); every rank
+must end with byte-identical proofs, which is asserted inside the run together with the committed
+digest of the same proof (tests/golden/synthetic_proofs.json).  ``--independent`` restores one
+independent job per GPU (weak scaling, no data-path collective).  The 2^16-gate latency (BASELINE
+config 2) rides along as the extra key ``prove16``.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -96,14 +101,21 @@ def measured_peaks():
 
 
 def measured_traffic(workload, logn):
-    """DRAM bytes of the dominant kernel from the committed ncu --set full capture, if one exists for
-    this workload/size (profiles/traffic.json); else None."""
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this
+    workload/size (profiles/traffic.json: bytes + the capture file it was read from), or None.  A capture
+    older than the kernel's source file describes a different kernel and is refused."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        ent = json.load(open(p)).get("%s:%d" % (workload, logn))
-        if ent:
-            return ent["dram_bytes_per_launch"]
-    return None
+    if not os.path.exists(p):
+        return None, "no capture"
+    ent = json.load(open(p)).get("%s:%d" % (workload, logn))
+    if not ent:
+        return None, "no capture for this workload/size"
+    src = os.path.join(ROOT, ent.get("kernel_source", ""))
+    if ent.get("kernel_source_sha256") and os.path.exists(src):
+        import hashlib
+        if hashlib.sha256(open(src, "rb").read()).hexdigest() != ent["kernel_source_sha256"]:
+            return None, "capture %s predates the current %s: refused" % (ent.get("capture"), ent["kernel_source"])
+    return ent["dram_bytes_per_launch"], ent.get("capture")
 
 
 def imad_peak():
@@ -117,86 +129,23 @@ def imad_peak():
 
 
 # ---------------------------------------------------------------------------- reference arm
-def run_reference(args, rank, world):
-    """The reference's own CPU path cannot be built (Rust, absent crates): this arm times the
-    oracle's threaded C restatement on a bounded sample of the same workload."""
-    if rank != 0:
-        return
-    from oracle import cport
-    from oracle.fields import g1_to_mont_limbs
-    from oracle import curve
-    from oracle.rng import random_fr_raw_limbs
-    cport.build()
-    cores = cport.num_threads()
-    if args.workload == "prove":
-        cp, circ, bl = cpu_prover(args.logn)
-        fn = lambda: cp.create_proof(bl, circ)
-        n = 1
-        unit, metric = "proofs/s", "create_proof_throughput"
-        sample = ("one full create_proof of the 2^%d-gate synthetic circuit per step, C restatement, OpenMP "
-                  "(tuned: batch inversion, threaded loops)" % args.logn)
-        for _ in range(min(args.warmup, 1)):
-            fn()
-        steps = min(args.steps, 3)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            fn()
-        dt = (time.perf_counter() - t0) / steps
-        val = 1.0 / dt
-        line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": world,
-                "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (modular integer)", "data": "synthetic",
-                "config": workload_config(args), "prove_ms": dt * 1e3,
-                "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
-                "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
-        return
-    if args.workload == "msm":
-        logs = min(args.logn, 16)
-        n = 1 << logs
-        g = g1_to_mont_limbs([curve.G1_GEN])[0]
-        # SRS-shaped bases tau^i G are produced by the oracle's fixed-base routine
-        from oracle.fields import fr_to_raw_limbs
-        tau = 0x1234567890ABCDEF1234567890ABCDEF % (1 << 250)
-        dl, t = [], 1
-        from oracle.fields import R_MOD
-        for _ in range(n):
-            dl.append(t); t = t * tau % R_MOD
-        bases = cport.fixed_base_mul(g, fr_to_raw_limbs(dl))
-        sc = random_fr_raw_limbs(8349, n)
-        fn = lambda: cport.msm_g1(bases, sc)
-        unit, metric = "Melem/s", "g1_msm_throughput"
-        sample = "G1 MSM of 2^%d SRS-shaped points per step (workload size 2^%d), C restatement, OpenMP" % (logs, args.logn)
-    else:
-        logs = min(args.logn, 22)
-        n = 1 << logs
-        data = random_fr_raw_limbs(8349, n)
-        fn = lambda: cport.ntt(data, logs)
-        unit, metric = "Melem/s", "fr_ntt_throughput"
-        sample = "Fr NTT of 2^%d elements per step (workload size 2^%d), C restatement, OpenMP" % (logs, args.logn)
-    for _ in range(args.warmup):
-        fn()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        fn()
-    dt = (time.perf_counter() - t0) / args.steps
-    val = n / dt / 1e6
-    line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (modular integer)", "data": "synthetic",
-            "config": workload_config(args),
-            "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+def host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is one process that should use the
+    box's cores.  Must run before the oracle's OpenMP library is loaded."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
 
 
 def cpu_prover(logn):
-    """CPU restatement of compile + the witness for the same synthetic circuit (oracle side)."""
+    """CPU restatement of compile + the witness for the same synthetic circuit.  Oracle side only:
+    the circuit comes from the shared workload generator (host_mirror, pure numpy), the transcript is
+    the oracle's own Merlin -- nothing of the product (and no libzkp_b200.so) is loaded."""
     from oracle import cport, cprover, curve
     from oracle.fields import R_MOD, fr_to_raw_limbs, g1_to_mont_limbs
+    from oracle.merlin import Transcript
     from oracle.rng import SplitMix64
-    from dusk_plonk_b200.composer import synthetic_circuit
-    from dusk_plonk_b200.transcript import Transcript
+    from host_mirror.composer import synthetic_circuit
     circ = synthetic_circuit(logn)
     rng = SplitMix64(8349)
     tau = rng.fr()
@@ -210,36 +159,187 @@ def cpu_prover(logn):
     return cp, circ, bl
 
 
-def workload_config(args):
+def run_reference(args, rank, world):
+    """The reference's own CPU path cannot be built (Rust, absent crates): this arm times the
+    oracle's threaded C restatement on a bounded sample of the same workload, on rank 0 alone."""
+    if rank != 0:
+        return
+    cores_set = host_threads()
+    from oracle import cport
+    from oracle import curve
+    from oracle.fields import R_MOD, fr_to_raw_limbs, g1_to_mont_limbs
+    from oracle.rng import random_fr_raw_limbs
+    cport.build()
+    cores = cport.num_threads()
+    assert cores == cores_set, (cores, cores_set)
+    steps, warmup = args.steps, args.warmup
+    if args.workload in ("prove", "compile"):
+        t_c0 = time.perf_counter()
+        cp, circ, bl = cpu_prover(args.logn)
+        compile_s = time.perf_counter() - t_c0
+        if args.workload == "compile":
+            fn = None
+            steps, warmup = 1, 0
+            dt = compile_s
+            unit, metric, n = "compiles/s", "compile_throughput", 1
+            sample = ("SRS generation + PlonkKey::compile of the 2^%d-gate synthetic circuit, once; C restatement "
+                      "(OpenMP) driven from Python" % args.logn)
+        else:
+            fn = lambda: cp.create_proof(bl, circ)
+            # bounded: a 2^20-gate proof takes tens of seconds on the host cores
+            steps = min(steps, 3 if args.logn <= 16 else 1)
+            warmup = min(warmup, 1 if args.logn <= 16 else 0)
+            unit, metric, n = "proofs/s", "create_proof_throughput", 1
+            sample = ("one full create_proof of the 2^%d-gate synthetic circuit per step (%d step(s)), C restatement, "
+                      "OpenMP (tuned: batch inversion, threaded loops)" % (args.logn, steps))
+    elif args.workload == "msm":
+        logs = min(args.logn, 16)
+        n = 1 << logs
+        g = g1_to_mont_limbs([curve.G1_GEN])[0]
+        tau = 0x1234567890ABCDEF1234567890ABCDEF % (1 << 250)
+        dl, t = [], 1
+        for _ in range(n):
+            dl.append(t); t = t * tau % R_MOD
+        bases = cport.fixed_base_mul(g, fr_to_raw_limbs(dl))     # SRS-shaped bases tau^i G
+        sc = random_fr_raw_limbs(8349, n)
+        fn = lambda: cport.msm_g1(bases, sc)
+        unit, metric = "Melem/s", "g1_msm_throughput"
+        sample = "G1 MSM of 2^%d SRS-shaped points per step (workload size 2^%d), C restatement, OpenMP" % (logs, args.logn)
+    else:
+        logs = min(args.logn, 22)
+        n = 1 << logs
+        data = random_fr_raw_limbs(8349, n)
+        fn = lambda: cport.ntt(data, logs)
+        unit, metric = "Melem/s", "fr_ntt_throughput"
+        sample = "Fr NTT of 2^%d elements per step (workload size 2^%d), C restatement, OpenMP" % (logs, args.logn)
+    if fn is not None:
+        for _ in range(warmup):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        dt = (time.perf_counter() - t0) / steps
+    val = n / dt if unit.endswith("s/s") and n == 1 else n / dt / 1e6
+    line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong" if (world > 1 and not args.independent) else "weak", "vs_baseline": None,
+            "dtype": "u64 limbs (modular integer)", "data": "synthetic", "config": workload_config(args, world),
+            "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "omp_threads": cores}
     if args.workload == "prove":
-        return {"workload": "create_proof, synthetic 2^%d-gate add/mul circuit (n = 2^%d, quotient domain 8n = 2^%d), "
-                            "11 commits + 11 NTT(n) + 8 NTT(8n) + element-wise rounds" % (args.logn, args.logn, args.logn + 3),
-                "log2_gates": args.logn,
+        line["prove_ms"] = dt * 1e3
+        line["setup_s"] = compile_s
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world=1):
+    shard = world > 1 and not args.independent
+    if shard:
+        par = {"prove": "ONE proof over %d GPUs: commits sharded by SRS ranges (partial sums gathered over NCCL), coset "
+                        "transforms and quotient slices dealt out per GPU (all-to-all of slices over NVLink)" % world,
+               "compile": "ONE compile over %d GPUs, commits sharded by SRS ranges" % world,
+               "msm": "ONE MSM over %d GPUs: SRS ranges + 96-byte partial-sum all-gather" % world,
+               "ntt": "ONE transform over %d GPUs: four-step NTT, one NCCL all-to-all" % world}[args.workload]
+    else:
+        par = "%d independent job(s), one per GPU, no data-path collective" % world
+    if args.workload in ("prove", "compile"):
+        what = "create_proof" if args.workload == "prove" else "PlonkKey::compile (15 iNTT + 15 commits + 16 coset NTT(8n))"
+        return {"workload": "%s, synthetic 2^%d-gate add/mul circuit (n = 2^%d, quotient domain 8n = 2^%d), "
+                            "11 commits + 11 NTT(n) + 8 NTT(8n) + element-wise rounds" % (what, args.logn, args.logn, args.logn + 3),
+                "log2_gates": args.logn, "parallelism": par,
                 "l2": "proving key + workspace (%d MiB) stream through each proof: larger than L2" %
                       ((16 + 9) * (1 << (args.logn + 3)) * 32 >> 20)}
     if args.workload == "msm":
         return {"workload": "G1 MSM (KZG commit) over 2^%d SRS powers, uniform scalars" % args.logn,
-                "log2_n": args.logn, "l2": "inputs (bases+scalars) larger than L2"}
+                "log2_n": args.logn, "parallelism": par, "l2": "inputs (bases+scalars) larger than L2"}
     return {"workload": "Fr NTT, 2^%d elements, forward, natural order" % args.logn, "log2_n": args.logn,
-            "l2": "input larger than L2"}
+            "parallelism": par, "l2": "input larger than L2"}
+
+
+def golden_digest(logn):
+    p = os.path.join(ROOT, "tests", "golden", "synthetic_proofs.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(str(logn), {}).get("sha256")
+    return None
 
 
 # ------------------------------------------------------------------------------- GPU arm
+class ProveJob:
+    """compile + witness for the synthetic 2^logn-gate circuit on this rank's GPU; ``comm`` shards it."""
+
+    def __init__(self, z, ctx, logn, comm=None):
+        from host_mirror.composer import synthetic_circuit
+        from host_mirror.synthetic import SplitMix64
+        from dusk_plonk_b200.field import fr_to_mont1
+        from dusk_plonk_b200.plonk_params import PlonkParams
+        self.z, self.ctx, self.logn = z, ctx, logn
+        circ = self.circ = synthetic_circuit(logn)
+        rng = SplitMix64(8349)
+        tau = rng.fr()
+        t0 = time.perf_counter()
+        if comm is not None:
+            from dusk_plonk_b200.sharding import ShardedPlonkParams
+            pp = ShardedPlonkParams.setup_synthetic(ctx, comm, logn, fr_to_mont1(tau))
+        else:
+            pp = PlonkParams.setup_synthetic(ctx, logn, fr_to_mont1(tau))
+        ctx.sync()
+        self.srs_ms = (time.perf_counter() - t0) * 1e3
+        self.pp = pp
+        t0 = time.perf_counter()
+        self.prover = z.PlonkKey.compile(pp, circ)
+        ctx.sync()
+        self.compile_ms = (time.perf_counter() - t0) * 1e3
+        self.bl = [rng.fr() for _ in range(11)]
+        self.sharded = comm is not None
+        if self.sharded:    # the sharded proof takes host-gathered wire columns
+            self.wa_host = z.WitnessAssignment.from_circuit(circ, circ.n)
+            self.wa_host.wires_mont = pinned_copy(z, self.wa_host.wires_mont)
+            self.wa_host.dense_pi_mont = pinned_copy(z, self.wa_host.dense_pi_mont)
+            self.h2d = 5 * circ.n * 32 + 19 * 32
+        else:               # witness values in pinned host memory; the wire gather runs on the device
+            self.wa_host = z.WitnessValues.from_circuit(circ)
+            self.wa_host.witness_mont = pinned_copy(z, self.wa_host.witness_mont)
+            self.h2d = (self.wa_host.witness_mont.shape[0] + len(self.wa_host.pi_values) + 19) * 32
+        self.wa_dev = z.WitnessAssignment.from_circuit(circ, circ.n).to_device(ctx)
+        self.d2h = 11 * 96 + 17 * 32
+        self.proofs = []
+
+    def step(self):
+        self.proofs.append(self.prover.create_proof(self.bl, self.wa_dev)[0])
+
+    def e2e_step(self):
+        self.proofs.append(self.prover.create_proof(self.bl, self.wa_host)[0])
+
+    def digest(self):
+        import hashlib
+        raws = [getattr(p, "wire_bytes", None) or p.to_bytes() for p in self.proofs]
+        assert all(r == raws[0] for r in raws), "non-deterministic proofs"
+        return hashlib.sha256(raws[0]).hexdigest()
+
+
+def pinned_copy(z, a):
+    p = z.pinned_empty(a.shape, a.dtype)
+    p[...] = a
+    return p
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="prove", choices=["prove", "msm", "ntt"])
+    ap.add_argument("--workload", default="prove", choices=["prove", "msm", "ntt", "compile"])
     ap.add_argument("--logn", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard", action="store_true",
-                    help="N > 1: shard ONE job over the GPUs (SRS ranges + partial-sum gather for commits, four-step "
-                         "NTT with all-to-all) and report strong scaling; default is one independent job per GPU")
+    ap.add_argument("--no-prove16", action="store_true", help="skip the extra 2^16-gate latency key")
+    ap.add_argument("--independent", action="store_true",
+                    help="N > 1: one independent job per GPU (weak scaling) instead of ONE job sharded over the GPUs")
+    ap.add_argument("--shard", action="store_true", help="(default for N > 1; kept for old command lines)")
     args = ap.parse_args()
     if args.logn is None:
-        args.logn = {"prove": 16, "msm": 22, "ntt": 24}[args.workload]
+        args.logn = {"prove": 20, "msm": 24, "ntt": 24, "compile": 20}[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
     rank = env_int("RANK", 0)
@@ -251,7 +351,7 @@ def main():
         return
 
     import dusk_plonk_b200 as z
-    from dusk_plonk_b200.synthetic import random_fr_raw_limbs   # the product's own input generator
+    from host_mirror.synthetic import random_fr_raw_limbs   # workload generator (numpy)
 
     dist = None
     if world > 1:
@@ -264,54 +364,54 @@ def main():
     n = 1 << args.logn
     hbm_peak, hbm_src = measured_peaks()
     imad_pk, imad_src = imad_peak()
-    shard = args.shard and world > 1
+    shard = world > 1 and not args.independent
     comm = None
     if shard:
         import torch
         from dusk_plonk_b200.sharding import Communicator, FourStepNtt, ShardedPlonkParams
         comm = Communicator(torch.device("cuda", local_rank))
     # seeds: independent jobs differ per rank, a sharded job is the same job on every rank
-    jr = 0 if shard else rank
+    jr = 0 if shard or world == 1 else rank
 
-    def pinned_copy(a):
-        p = z.pinned_empty(a.shape, a.dtype)
-        p[...] = a
-        return p
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
 
-    if args.workload == "prove":
-        from dusk_plonk_b200.composer import synthetic_circuit
+    job = None
+    extra = {}
+    if args.workload == "compile":
+        # a13: SRS window table + key preprocessing; a step is one whole compile (device-resident key)
+        from host_mirror.composer import synthetic_circuit
+        from host_mirror.synthetic import SplitMix64
         from dusk_plonk_b200.field import fr_to_mont1
         from dusk_plonk_b200.plonk_params import PlonkParams
-        from dusk_plonk_b200.synthetic import SplitMix64
         circ = synthetic_circuit(args.logn)
-        rng = SplitMix64(8349)
-        tau = rng.fr()
-        if shard:
-            pp = ShardedPlonkParams.setup_synthetic(ctx, comm, args.logn, fr_to_mont1(tau))
-        else:
-            pp = PlonkParams.setup_synthetic(ctx, args.logn, fr_to_mont1(tau))
-        prover = z.PlonkKey.compile(pp, circ)
-        bl = [rng.fr() for _ in range(11)]
-        if shard:    # the sharded proof is driven round by round from Python: host-gathered wire columns
-            wa_host = z.WitnessAssignment.from_circuit(circ, circ.n)
-            wa_host.wires_mont = pinned_copy(wa_host.wires_mont)
-            wa_host.dense_pi_mont = pinned_copy(wa_host.dense_pi_mont)
-            h2d_prove = 5 * circ.n * 32 + 19 * 32
-        else:        # witness values in pinned host memory; the wire gather runs on the device
-            wa_host = z.WitnessValues.from_circuit(circ)
-            wa_host.witness_mont = pinned_copy(wa_host.witness_mont)
-            h2d_prove = (wa_host.witness_mont.shape[0] + len(wa_host.pi_values) + 19) * 32
-        wa_dev = z.WitnessAssignment.from_circuit(circ, circ.n).to_device(ctx)
-        proofs = []
-        step = lambda: proofs.append(prover.create_proof(bl, wa_dev)[0])
-        e2e_step = lambda: proofs.append(prover.create_proof(bl, wa_host)[0])
-        h2d, d2h = h2d_prove, 11 * 96 + 17 * 32
-        dominant = "msm_accumulate"
-        metric = "create_proof_throughput"
-        n = 1
+        taum = fr_to_mont1(SplitMix64(8349).fr())
+        t0 = time.perf_counter()
+        pp = (ShardedPlonkParams.setup_synthetic(ctx, comm, args.logn, taum) if shard
+              else PlonkParams.setup_synthetic(ctx, args.logn, taum))
+        ctx.sync()
+        extra["srs_setup_ms"] = (time.perf_counter() - t0) * 1e3
+        keep = []
+
+        def step():
+            keep.clear()
+            keep.append(z.PlonkKey.compile(pp, circ))
+        e2e_step = step
+        # host -> device: 11 selector columns + sigma encodings; device -> host: 15 commitments
+        h2d, d2h = 11 * circ.n * 32 + 4 * circ.n * 4, 15 * 96
+        dominant, metric, n = "msm_accumulate", "compile_throughput", 1
+    elif args.workload == "prove":
+        job = ProveJob(z, ctx, args.logn, comm)
+        step, e2e_step, h2d, d2h = job.step, job.e2e_step, job.h2d, job.d2h
+        extra["srs_setup_ms"], extra["compile_ms"] = job.srs_ms, job.compile_ms
+        dominant, metric, n = "msm_accumulate", "create_proof_throughput", 1
     elif args.workload == "msm":
         tau = random_fr_raw_limbs(4242 + jr, 1)[0]
-        host_scalars = pinned_copy(random_fr_raw_limbs(8349 + jr, n))
+        host_scalars = pinned_copy(z, random_fr_raw_limbs(8349 + jr, n))
         dev_scalars = ctx.upload(host_scalars)
         if shard:
             lo, hi = z.sharding.shard_range(n, rank, world)
@@ -327,10 +427,9 @@ def main():
             step = lambda: ctx.msm_dev(srs, dev_scalars, 0, n)
             e2e_step = lambda: ctx.msm(srs, host_scalars)
             h2d, d2h = n * 32, 96
-        dominant = "msm_accumulate"
-        metric = "g1_msm_throughput"
+        dominant, metric = "msm_accumulate", "g1_msm_throughput"
     else:
-        host_data = pinned_copy(random_fr_raw_limbs(8349 + jr, n))
+        host_data = pinned_copy(z, random_fr_raw_limbs(8349 + jr, n))
         if shard:
             fs = FourStepNtt(ctx, comm, args.logn)
             fs.scatter_input(host_data)
@@ -350,15 +449,7 @@ def main():
             def e2e_step():   # in place on the pinned host vector, like Fft::dft by value
                 ctx.check(ctx.lib.zkp_ntt(ctx.h, host_data.ctypes.data, n, args.logn, 0, 0))
             h2d, d2h = n * 32, n * 32
-        dominant = "ntt"
-        metric = "fr_ntt_throughput"
-
-    def barrier():
-        ctx.sync()
-        if dist is not None:
-            import torch
-            torch.cuda.synchronize()
-            dist.barrier()
+        dominant, metric = "ntt", "fr_ntt_throughput"
 
     for _ in range(args.warmup):
         step()
@@ -379,8 +470,9 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     dom_ms, dom_cnt = ctx.prof_read(dominant)
-    prof_groups = {g: ctx.prof_read(g) for g in ("msm_sort", "msm_accumulate", "msm_reduce", "msm_combine", "ntt",
-                                                 "quotient", "perm_z", "poly_eval", "poly_lincomb", "poly_div")}
+    groups = ("msm_sort", "msm_accumulate", "msm_reduce", "msm_combine", "ntt", "quotient", "perm_z", "poly_eval",
+              "poly_lincomb", "poly_div")
+    prof_groups = {g: ctx.prof_read(g) for g in groups}
     ctx.prof_enable(False)
     ctx.prof_reset()
 
@@ -400,32 +492,72 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(t[0]), float(t[1])
 
+    # in-run parity: every rank holds byte-identical proofs, equal to the committed digest of this circuit
+    if job is not None:
+        dg = job.digest()
+        digests = [dg]
+        if dist is not None:
+            digests = [None] * world
+            dist.all_gather_object(digests, dg)
+        if shard:
+            assert all(d == digests[0] for d in digests), "ranks disagree on the proof bytes: %r" % (digests,)
+        gold = golden_digest(args.logn) if (shard or world == 1) else None
+        assert gold is None or dg == gold, "proof bytes differ from tests/golden/synthetic_proofs.json"
+        extra["proof_sha256"] = dg
+        extra["proof_check"] = ("%d rank(s) byte-identical" % len(digests) if shard or world == 1 else "independent proofs") + \
+            ("; equals the committed digest (GPU == CPU oracle, tests/golden/synthetic_proofs.json)" if gold else
+             "; no committed digest for this size")
+        # BASELINE config 2 rides along: latency of a 2^16-gate proof on one GPU (rank 0)
+        if not args.no_prove16 and args.logn != 16 and rank == 0:
+            ctx16 = z.Context(local_rank)
+            j16 = ProveJob(z, ctx16, 16)
+            for _ in range(3):
+                j16.step()
+            ctx16.sync()
+            ctx16.timer_start()
+            for _ in range(10):
+                j16.step()
+            ms16 = ctx16.timer_stop_ms() / 10
+            j16.e2e_step()
+            ctx16.sync()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                j16.e2e_step()
+            ctx16.sync()
+            e16 = (time.perf_counter() - t0) * 1e2
+            d16, g16 = j16.digest(), golden_digest(16)
+            assert g16 is None or d16 == g16, "2^16 proof bytes differ from the committed digest"
+            extra["prove16"] = {"prove_ms": ms16, "e2e_prove_ms": e16, "proofs_per_s": 1e3 / ms16, "n_gpus": 1,
+                                "proof_sha256": d16, "equals_golden": g16 is not None}
+            j16.prover.close()
+            ctx16.close()
+        if dist is not None:
+            dist.barrier()
+
     if rank == 0:
         ms_step = ms / args.steps
-        jobs = 1 if shard else world      # sharded: ONE job over all GPUs (strong scaling)
+        jobs = 1 if (shard or world == 1) else world      # sharded: ONE job over all GPUs (strong scaling)
         value = jobs * n / (ms_step * 1e-3) / 1e6
         e2e_val = jobs * n / (e2e_ms / args.steps * 1e-3) / 1e6
         dom_avg_ms = dom_ms / max(dom_cnt, 1)
         unit = "Melem/s"
-        extra = {}
-        if args.workload == "prove":
-            unit = "proofs/s"
+        if args.workload in ("prove", "compile"):
+            unit = "proofs/s" if args.workload == "prove" else "compiles/s"
             value, e2e_val = value * 1e6, e2e_val * 1e6
-            assert all(p == proofs[0] for p in proofs), "non-deterministic proofs"
-            # dominant kernel: msm_accumulate over the proof's 11 commits
+            # dominant kernel: msm_accumulate over the commits of a step (this rank's share when sharded)
             achieved = MSM_IMAD_PER_POINT * (msm_pts / max(dom_cnt, 1)) / (dom_avg_ms * 1e-3) / 1e12
             shares = {}
-            for g in ("msm_sort", "msm_accumulate", "msm_reduce", "msm_combine", "ntt", "quotient", "perm_z",
-                      "poly_eval", "poly_lincomb", "poly_div"):
+            for g in groups:
                 gm, gc = prof_groups.get(g, (0.0, 0))
-                shares[g] = {"ms_per_proof": gm / args.steps, "launch_groups_per_proof": gc / args.steps}
+                shares[g] = {"ms_per_step": gm / args.steps, "launch_groups_per_step": gc / args.steps}
             roofline = {"bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": imad_pk,
                         "unit": "T IMAD/s", "frac": achieved / imad_pk, "traffic": None, "peak_source": imad_src,
                         "kernel_ms": dom_avg_ms, "launches_per_step": dom_cnt / args.steps,
                         "kernel_share_of_step": dom_ms / args.steps / ms_step,
-                        "algorithmic": "48000 mul-adds per committed point (SURVEY 8d); %d points per proof" %
+                        "algorithmic": "48000 mul-adds per committed point (SURVEY 8d); %d points per step on this GPU" %
                                        (msm_pts // args.steps)}
-            extra = {"prove_ms": ms_step, "e2e_prove_ms": e2e_ms / args.steps, "kernel_groups": shares}
+            extra.update({"prove_ms" if args.workload == "prove" else "compile_ms": ms_step,
+                          "e2e_ms": e2e_ms / args.steps, "kernel_groups": shares})
         elif args.workload == "msm":
             # the roofline is per GPU: a sharded job's kernel on this rank sums n / world points
             n_local = n // world if shard else n
@@ -443,14 +575,12 @@ def main():
                         "peak_source": hbm_src, "kernel_ms": dom_avg_ms, "kernel_share_of_step": dom_avg_ms / ms_step,
                         "imad_achieved_T": imad, "imad_frac": imad / imad_pk, "imad_peak_source": imad_src,
                         "algorithmic": "64 B per element; 68*N*log2(N) mul-adds (SURVEY 8d)"}
-        roofline["traffic"] = measured_traffic(args.workload, args.logn)
+        roofline["traffic"], roofline["traffic_source"] = measured_traffic(args.workload, args.logn)
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong" if shard else "weak",
                 "vs_baseline": None, "dtype": "u32 limbs (modular integer)", "data": "synthetic",
-                "config": dict(workload_config(args), parallelism=(
-                    "one job sharded over %d GPUs (SRS ranges + 96-byte partial-sum all-gather; four-step NTT + "
-                    "all-to-all)" % world if shard else "%d independent job(s), one per GPU, no data-path collective" % world)),
+                "config": workload_config(args, world),
                 "roofline": roofline,
                 "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clocks}
@@ -458,6 +588,8 @@ def main():
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
+    if job is not None:
+        job.prover.close()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -465,18 +597,35 @@ def main():
 
 def cpu_baseline(args):
     """Oracle C restatement on the host cores, bounded sample (rank 0 only)."""
+    cores_set = host_threads()
     from oracle import cport
     from oracle.rng import random_fr_raw_limbs
     cport.build()
     cores = cport.num_threads()
-    if args.workload == "prove":
-        cp, circ, bl = cpu_prover(args.logn)
-        t0 = time.perf_counter()
-        cp.create_proof(bl, circ)
-        dt = time.perf_counter() - t0
-        return {"value": 1.0 / dt, "unit": "proofs/s", "cores": cores, "kind": "port", "prove_ms": dt * 1e3,
-                "sample": "one full create_proof of the same 2^%d-gate circuit (whole workload, not a sample); "
-                          "C restatement, OpenMP, tuned (batch inversion, threaded loops)" % args.logn}
+    if args.workload in ("prove", "compile"):
+        # a 2^20-gate proof costs the host cores the better part of a minute (plus minutes of CPU key
+        # set-up): the sample is one whole proof of the 2^16-gate circuit of the same family, scaled by the
+        # gate ratio (MSM ~ n / log n and NTT ~ n log n straddle linear); `bench.py --impl reference` times
+        # the full-size proof itself
+        logs = min(args.logn, 16)
+        scale = float(1 << (args.logn - logs))
+        t_c0 = time.perf_counter()
+        cp, circ, bl = cpu_prover(logs)
+        t_c = time.perf_counter() - t_c0
+        if args.workload == "compile":
+            dt = t_c
+            what = "SRS generation + compile"
+        else:
+            t0 = time.perf_counter()
+            cp.create_proof(bl, circ)
+            dt = time.perf_counter() - t0
+            what = "create_proof"
+        unit = "proofs/s" if args.workload == "prove" else "compiles/s"
+        return {"value": 1.0 / (dt * scale), "unit": unit, "cores": cores, "kind": "port",
+                "sample_ms": dt * 1e3, "sample_log2_gates": logs, "scaled_by": scale,
+                "sample": "one full %s of the 2^%d-gate synthetic circuit%s; C restatement, OpenMP, tuned (batch "
+                          "inversion, threaded loops)" % (what, logs, "" if scale == 1.0 else
+                                                          ", time scaled x%d to 2^%d gates" % (scale, args.logn))}
     if args.workload == "msm":
         from oracle import curve
         from oracle.fields import R_MOD, fr_to_raw_limbs, g1_to_mont_limbs

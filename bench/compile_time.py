@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import dusk_plonk_b200 as z  # noqa: E402
-from dusk_plonk_b200.composer import synthetic_circuit  # noqa: E402
+from host_mirror.composer import synthetic_circuit  # noqa: E402
 from dusk_plonk_b200.field import fr_to_mont1  # noqa: E402
 from dusk_plonk_b200.plonk_params import PlonkParams  # noqa: E402
 

@@ -4,7 +4,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import time, numpy as np
 import dusk_plonk_b200 as z
-from dusk_plonk_b200.synthetic import random_fr_raw_limbs
+from host_mirror.synthetic import random_fr_raw_limbs
 ctx = z.Context(0)
 tau = random_fr_raw_limbs(4242, 1)[0]
 for k in (16, 20):

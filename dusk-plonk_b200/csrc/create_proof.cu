@@ -36,6 +36,8 @@ struct zkp_prover {
     uint32_t* wire_idx = nullptr;   // [4][m]: witness index of wire j at gate i (src/prover.rs:114-119)
     uint32_t* pi_idx = nullptr;     // gate positions of the public inputs
     size_t m = 0, pi_count = 0, wv_cap = 0;
+    bool wiring_set = false;        // zkp_prover_set_wiring has been called (prove_witness needs it)
+    size_t max_wire_idx = 0;        // largest witness index the wiring reads (a witness array must cover it)
     zkp::fr_t* wv = nullptr;        // staging for the witness values and public-input values
 };
 
@@ -716,6 +718,12 @@ int zkp_prover_set_wiring(zkp_prover* pr, const uint32_t* wire_idx, size_t m, co
     if (pr->pi_idx) cudaFree(pr->pi_idx);
     pr->wire_idx = pr->pi_idx = nullptr;
     pr->m = pr->pi_count = 0;
+    // a stale or foreign wiring must be an error, not a silently different circuit: public inputs sit on
+    // gates of the n-domain, and prove_witness checks the witness array against the largest index read
+    for (size_t i = 0; i < pi_count; i++) if (pi_idx[i] >= pr->n) return ZKP_ERR_INVALID;
+    size_t mx = 0;
+    for (size_t i = 0; i < 4 * m; i++) if (wire_idx[i] > mx) mx = wire_idx[i];
+    pr->max_wire_idx = mx;
     if (m) {
         ZKP_CUDA(ctx, cudaMalloc(&pr->wire_idx, 4 * m * sizeof(uint32_t)));
         ZKP_CUDA(ctx, cudaMemcpy(pr->wire_idx, wire_idx, 4 * m * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -726,6 +734,7 @@ int zkp_prover_set_wiring(zkp_prover* pr, const uint32_t* wire_idx, size_t m, co
     }
     pr->m = m;
     pr->pi_count = pi_count;
+    pr->wiring_set = true;
     return ZKP_OK;
 }
 
@@ -733,8 +742,9 @@ int zkp_prover_prove_witness(zkp_prover* pr, const uint8_t transcript[203], cons
                              const uint64_t* pi_values, const uint64_t blinders[44], uint64_t commitments[132],
                              uint64_t evaluations[64], uint8_t proof_bytes[1040], uint8_t transcript_out[203]) {
     if (!pr || !transcript || !blinders || !commitments || !evaluations || (!witness && num_w) ||
-        (!pi_values && pr->pi_count) || (pr->m && !pr->wire_idx))
+        (!pi_values && pr->pi_count) || (pr->m && num_w <= pr->max_wire_idx))
         return ZKP_ERR_INVALID;
+    if (!pr->wiring_set) return ZKP_ERR_STATE;    // zkp_prover_set_wiring comes first
     zkp_ctx* ctx = pr->ctx;
     int rc;
     if ((rc = set_device(ctx))) return rc;
@@ -769,6 +779,26 @@ int zkp_prover_prove_witness(zkp_prover* pr, const uint8_t transcript[203], cons
 
 /* Merlin transcript operations on a serialized state (host code): what TranscriptProtocol needs
  * outside a proof (seeding with the verification key, public inputs) without leaving native code. */
+int zkp_transcript_init(uint8_t state[203], const uint8_t* label, uint32_t len) {
+    if (!state || (!label && len)) return ZKP_ERR_INVALID;
+    // STROBE-128 initial state: F([1, R + 2, 1, 0, 1, 96] || "STROBEv1.0.2"), then meta-AD of the
+    // protocol label "Merlin v1.0" and Merlin's own domain separator carrying the caller's label
+    drv::Transcript t;
+    memset(t.st, 0, 200);
+    const uint8_t hdr[6] = {1, drv::Transcript::RATE + 2, 1, 0, 1, 96};
+    memcpy(t.st, hdr, 6);
+    memcpy(t.st + 6, "STROBEv1.0.2", 12);
+    uint64_t w[25];
+    memcpy(w, t.st, 200);
+    zkp_keccak_f1600(w);
+    memcpy(t.st, w, 200);
+    t.pos = t.pos_begin = t.cur_flags = 0;
+    t.meta_ad("Merlin v1.0", 11, false);
+    t.append_message("dom-sep", label, len);
+    t.save(state);
+    return ZKP_OK;
+}
+
 int zkp_transcript_append(uint8_t state[203], const char* label, const uint8_t* msg, uint32_t len) {
     if (!state || !label || (!msg && len)) return ZKP_ERR_INVALID;
     drv::Transcript t;

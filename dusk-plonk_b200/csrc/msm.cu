@@ -23,7 +23,7 @@
 //   5. msm_merge[_giant]_kernel  buckets cut by chunk boundaries: add their partial sums
 //   6. msm_rowcol / weighted_planes / final_sum    sum_b (b+1) * B[b]: row + column sums of the
 //                             (hi, lo) weight grid, then two short bit-plane weighted sums
-//   7. host: one Fermat inversion -> affine
+//   7. host: one binary-GCD inversion per commit group (host_inv.h) -> affine
 // Addition in G1 is commutative and the result is normalised to affine, so the output is
 // bit-identical to any correct CPU evaluation regardless of accumulation order.
 #include <stdlib.h>
@@ -831,38 +831,50 @@ static int ensure(zkp_ctx* ctx, T** p, size_t* cap, size_t need) {
     return ZKP_OK;
 }
 
+static void msm_scratch_release(MsmScratch* s) {
+    if (!s) return;
+    cudaFree(s->digits); cudaFree(s->sorted); cudaFree(s->counts); cudaFree(s->offsets); cudaFree(s->cursor);
+    cudaFree(s->giant); cudaFree(s->meta); cudaFree(s->tile_sums); cudaFree(s->buckets); cudaFree(s->slots); cudaFree(s->planes);
+    cudaFree(s->top);
+    delete s;
+}
+
+// built in a local and published to the context only when every allocation and occupancy query has
+// succeeded: a half-initialised scratch must never be seen by the next commit
+static int msm_scratch_build(zkp_ctx* ctx, MsmScratch* s) {
+    ZKP_CUDA(ctx, cudaMalloc(&s->top, sizeof(long long)));
+    ZKP_CUDA(ctx, cudaMalloc(&s->meta, 4 * MSM_MAX_BATCH * sizeof(uint32_t)));
+    ZKP_CUDA(ctx, cudaMalloc(&s->tile_sums, 1024 * MSM_MAX_BATCH * sizeof(uint32_t)));
+    int mb = 3;  // measured best on B200 (2^22: 22.3 / 21.8 / 23.1 / 23.7 / 24.4 ms for 2..6 blocks per SM)
+    if (const char* e = getenv("ZKP_MSM_BLOCKS_PER_SM")) {  // tuning knob: 2 or 3, applies to every job size
+        mb = atoi(e);
+        s->acc_variant_forced = true;
+    }
+    mb = mb <= 2 ? 2 : 3;
+    s->acc_variant = mb;
+    int nb = 0;
+    if (mb == 2) ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<2>, 128, 0));
+    else ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<3>, 128, 0));
+    s->acc_blocks_per_sm = nb > 0 ? nb : 1;
+    int nb2 = 0;
+    ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, msm_accumulate_kernel<2>, 128, 0));
+    s->acc_blocks_per_sm2 = nb2 > 0 ? nb2 : 1;
+    return ZKP_OK;
+}
+
 static int msm_scratch(zkp_ctx* ctx, MsmScratch** out) {
     if (!ctx->msm) {
-        ctx->msm = new MsmScratch();
-        ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->top, sizeof(long long)));
-        ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->meta, 4 * MSM_MAX_BATCH * sizeof(uint32_t)));
-        ZKP_CUDA(ctx, cudaMalloc(&ctx->msm->tile_sums, 1024 * MSM_MAX_BATCH * sizeof(uint32_t)));
-        int mb = 3;  // measured best on B200 (2^22: 22.3 / 21.8 / 23.1 / 23.7 / 24.4 ms for 2..6 blocks per SM)
-        if (const char* e = getenv("ZKP_MSM_BLOCKS_PER_SM")) {  // tuning knob: 2 or 3, applies to every job size
-            mb = atoi(e);
-            ctx->msm->acc_variant_forced = true;
-        }
-        mb = mb <= 2 ? 2 : 3;
-        ctx->msm->acc_variant = mb;
-        int nb = 0;
-        if (mb == 2) ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<2>, 128, 0));
-        else ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<3>, 128, 0));
-        ctx->msm->acc_blocks_per_sm = nb > 0 ? nb : 1;
-        int nb2 = 0;
-        ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, msm_accumulate_kernel<2>, 128, 0));
-        ctx->msm->acc_blocks_per_sm2 = nb2 > 0 ? nb2 : 1;
+        MsmScratch* s = new MsmScratch();
+        const int rc = msm_scratch_build(ctx, s);
+        if (rc) { msm_scratch_release(s); return rc; }
+        ctx->msm = s;
     }
     *out = ctx->msm;
     return ZKP_OK;
 }
 
 void msm_free(zkp_ctx* ctx) {
-    MsmScratch* s = ctx->msm;
-    if (!s) return;
-    cudaFree(s->digits); cudaFree(s->sorted); cudaFree(s->counts); cudaFree(s->offsets); cudaFree(s->cursor);
-    cudaFree(s->giant); cudaFree(s->meta); cudaFree(s->tile_sums); cudaFree(s->buckets); cudaFree(s->slots); cudaFree(s->planes);
-    cudaFree(s->top);
-    delete s;
+    msm_scratch_release(ctx->msm);
     ctx->msm = nullptr;
 }
 

@@ -69,6 +69,7 @@ SIGNATURES = {
     "zkp_commit": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "zkp_commit_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp]),
     "zkp_msm_set_window": (_int, [_vp, _uint]),
+    "zkp_transcript_init": (_int, [_vp, _vp, ctypes.c_uint32]),
 }
 
 

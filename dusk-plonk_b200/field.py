@@ -91,15 +91,37 @@ def g1_from_bytes(b):
     return None if x == 0 and y == 0 else (x, y)
 
 
-def g1_decompress(b):
-    """Inverse of ``transcript.g1_compress`` (48-byte zcash-style compressed G1)."""
-    assert len(b) == 48 and b[0] & 0x80, "not a compressed point"
+def g1_mul(p, k):
+    """Host double-and-add (decoding checks only)."""
+    acc = None
+    while k:
+        if k & 1:
+            acc = g1_add(acc, p)
+        p = g1_add(p, p)
+        k >>= 1
+    return acc
+
+
+def g1_decompress(b, subgroup_check=True):
+    """Inverse of ``transcript.g1_compress`` (48-byte zcash-style compressed G1).  Untrusted bytes:
+    every malformed encoding raises ``ValueError`` (never ``assert``): wrong length / missing compression
+    flag, x >= p, stray bits in the encoding of infinity, x not on the curve, and -- BLS12-381 G1 has a
+    cofactor -- points outside the r-torsion ([r]P != O) unless ``subgroup_check`` is False."""
+    if len(b) != 48 or not b[0] & 0x80:
+        raise ValueError("not a compressed G1 point")
     if b[0] & 0x40:
+        if b[0] & 0x3F or any(b[1:]):
+            raise ValueError("non-canonical encoding of the point at infinity")
         return None
     x = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:], "big")
+    if x >= P_MOD:
+        raise ValueError("non-canonical x coordinate")
     y2 = (pow(x, 3, P_MOD) + 4) % P_MOD
     y = pow(y2, (P_MOD + 1) // 4, P_MOD)          # p = 3 mod 4
-    assert y * y % P_MOD == y2, "x is not on the curve"
+    if y * y % P_MOD != y2:
+        raise ValueError("x is not on the curve")
     if (y > P_MOD - y) != bool(b[0] & 0x20):
         y = P_MOD - y
+    if subgroup_check and g1_mul((x, y), R_MOD) is not None:
+        raise ValueError("point is not in the prime-order subgroup")
     return (x, y)

@@ -10,7 +10,7 @@ is x exactly.
 """
 import numpy as np
 
-from .composer import SELECTORS, SynthesizedCircuit, Plonk
+from host_mirror.composer import SELECTORS, SynthesizedCircuit, Plonk
 from .field import R_MOD, fr_column_to_mont, fr_from_mont, fr_to_mont, g1_from_mont
 from .plonk_params import Error
 from .transcript import Transcript

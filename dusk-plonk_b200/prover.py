@@ -9,7 +9,7 @@ import numpy as np
 
 from .field import R_MOD, K1, K2, K3, fr_from_mont, fr_to_mont, fr_to_mont1, g1_from_mont
 from .ffi import QuotientArgs, BufferView as _View
-from .composer import SELECTORS, SynthesizedCircuit, Plonk
+from host_mirror.composer import SELECTORS, SynthesizedCircuit, Plonk
 from .widgets import linearization_scalars
 from .plonk_params import PlonkParams
 
@@ -67,14 +67,16 @@ class Proof:
     @classmethod
     def from_bytes(cls, data):
         from .field import g1_decompress
-        assert len(data) == 48 * 11 + 32 * 16
+        if len(data) != 48 * 11 + 32 * 16:
+            raise ValueError("a proof is 1040 bytes")
         p = cls()
         for i, c in enumerate(COMM_NAMES):
             setattr(p, c, g1_decompress(data[48 * i:48 * (i + 1)]))
         off = 48 * 11
         for i, k in enumerate(cls.WIRE_EVAL_ORDER):
             v = int.from_bytes(data[off + 32 * i:off + 32 * (i + 1)], "little")
-            assert v < _r, "non-canonical scalar"
+            if v >= _r:
+                raise ValueError("non-canonical scalar")
             p.evaluations[k] = v
         return p
 
@@ -196,9 +198,11 @@ class Prover:
         n = self.size
         np_ = self._native_prover()
         if isinstance(wa, WitnessValues):
-            if self._wiring_of is not wa.wires:           # same circuit shape as the last proof: already set
+            key = (id(wa.wires), id(wa.pi_indexes))
+            if self._wiring_of != key:                    # same circuit shape as the last proof: already set
                 np_.set_wiring(wa.wires, wa.pi_indexes)
-                self._wiring_of = wa.wires
+                self._wiring_of = key
+                self._wiring_keep = (wa.wires, wa.pi_indexes)   # keeps the ids alive
             rc, comms, evals, raw = np_.prove_witness(st, wa.witness_mont, wa.pi_values_mont, bl)
         else:
             wires_host = None if wa.wires_dev is not None else np.ascontiguousarray(wa.wires_mont).reshape(4 * n, 4)
@@ -219,9 +223,7 @@ class Prover:
         synthesized composer / ``SynthesizedCircuit`` / ``WitnessAssignment``.  Raises
         ``plonk_params.Error`` where the reference returns ``Err``.  Returns
         (Proof, public_inputs)."""
-        ctx, pk, n, k = self.ctx, self.prover_key, self.size, self.prover_key.k
-        ref = ctx.ref
-        ws = self._workspace()
+        n = self.size
         T = trace if trace is not None else None
         if isinstance(circuit, Plonk):
             circuit = SynthesizedCircuit.from_composer(circuit)
@@ -240,6 +242,11 @@ class Prover:
         bl = fr_to_mont(blinders)
         if use_native:
             return self._create_proof_native(tr, wa, bl)
+        # only the Python-driven rounds (sharded / traced proofs) need the Python-side workspace: the native
+        # driver owns an identical one (zkp_prover_create)
+        ctx, pk, k = self.ctx, self.prover_key, self.prover_key.k
+        ref = ctx.ref
+        ws = self._workspace()
         proof = Proof()
 
         # round 1: wires -> iNTT -> blind -> commit (src/prover.rs:107-158)

@@ -1,10 +1,10 @@
 """Seeded synthetic inputs for benchmarks: SplitMix64 so that C, CUDA-host and Python
-generators agree, seed 8349 echoing the reference's tests (``tests/range.rs:22``).  Part of the
-product's workload generator (with ``composer.synthetic_circuit``); the test oracle keeps its own
-copy so that neither side imports the other."""
+generators agree, seed 8349 echoing the reference's tests (``tests/range.rs:22``).  Workload
+generator (with ``composer.synthetic_circuit``); the test oracle keeps its own copy (``oracle/rng.py``)
+so that neither side imports the other."""
 import numpy as np
 
-from .field import R_MOD
+R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 
 _M64 = (1 << 64) - 1
 

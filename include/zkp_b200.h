@@ -40,7 +40,7 @@ extern "C" {
 #define ZKP_ERR_CUDA (-2)      /* CUDA runtime failure; see zkp_last_error()                     */
 #define ZKP_ERR_DEGREE (-3)    /* polynomial degree exceeds the SRS: PlonkParams::commit's Err   */
 #define ZKP_ERR_NOMEM (-4)
-#define ZKP_ERR_STATE (-5)     /* prover round called out of order                               */
+#define ZKP_ERR_STATE (-5)     /* call out of order (zkp_prover_prove_witness before set_wiring)   */
 
 typedef struct zkp_ctx zkp_ctx;
 typedef struct zkp_srs zkp_srs;   /* device-resident [tau^i]_1 powers (PlonkParams after trim)  */
@@ -279,6 +279,9 @@ int zkp_prover_prove_witness(zkp_prover* prover, const uint8_t transcript[203], 
  * linearisation (challenges = alpha beta gamma range logic fixed var z; evals in `Evaluations`
  * order; out = scalars of q_m q_l q_r q_o q_4 q_c q_range q_logic q_fixed q_var z s_sigma_4),
  * compressed G1 and the 64-byte wide reduction of challenge_scalar. */
+/* Transcript::new(label) (merlin): the 203-byte state IS the transcript object of a host that keeps
+ * Merlin inside this library (the merlin crate does not expose its STROBE state). */
+int zkp_transcript_init(uint8_t state[203], const uint8_t* label, uint32_t len);
 int zkp_transcript_append(uint8_t state[203], const char* label, const uint8_t* msg, uint32_t len);
 int zkp_transcript_challenge(uint8_t state[203], const char* label, uint8_t* out, uint32_t len);
 int zkp_linearization_scalars(unsigned k, const uint64_t challenges[32], const uint64_t evals[60],

@@ -379,6 +379,18 @@ class Proof:
     def __eq__(self, o):
         return all(getattr(self, c) == getattr(o, c) for c in self.COMM_NAMES) and self.evaluations == o.evaluations
 
+    # field order of ``Evaluations`` (src/prover/linearization_poly.rs:113-130)
+    WIRE_EVAL_ORDER = ("a_eval", "b_eval", "c_eval", "d_eval", "a_next_eval", "b_next_eval", "d_next_eval",
+                       "q_arith_eval", "q_c_eval", "q_l_eval", "q_r_eval", "s_sigma_1_eval", "s_sigma_2_eval",
+                       "s_sigma_3_eval", "r_poly_eval", "perm_eval")
+
+    def to_bytes(self):
+        """1040-byte wire form (src/prover/proof.rs:36-66 derives SCALE Encode: fixed-size fields in declaration
+        order): 11 compressed G1 then 16 little-endian scalars.  Oracle-side serialiser (own code path)."""
+        from .merlin import compress_g1
+        out = b"".join(compress_g1(getattr(self, c)) for c in self.COMM_NAMES)
+        return out + b"".join((self.evaluations[k] % R_MOD).to_bytes(32, "little") for k in self.WIRE_EVAL_ORDER)
+
 
 def create_proof(pk, circ, commit, transcript, blinders, trace=None):
     """``Prover::create_proof`` (src/prover.rs:67-474).  ``blinders``: 4 x 2 + 3 scalars in

@@ -1,7 +1,7 @@
 """Circuits shared by the CPU and GPU tests: the reference's own test circuits
 (tests/range.rs, tests/logic.rs, tests/ecc.rs, README.md TestCircuit) restated on the
 Python composer."""
-from dusk_plonk_b200.composer import (Plonk, Constraint, JUBJUB_GENERATOR, jubjub_mul, R_MOD)
+from host_mirror.composer import (Plonk, Constraint, JUBJUB_GENERATOR, jubjub_mul, R_MOD)
 
 
 def range_circuit(a, bits=76):
@@ -100,4 +100,41 @@ def mul_point_circuit(scalar=0x1234567890ABCDEF1234567, base_mult=7):
     pt = cs.append_point(jubjub_mul(JUBJUB_GENERATOR, base_mult))
     res = cs.component_mul_point(ws, pt)
     cs.assert_equal_public_point(res, jubjub_mul(JUBJUB_GENERATOR, base_mult * scalar))
+    return cs
+
+
+# ---- the three DummyCircuits of tests/ecc.rs, with free (a, b, c) so that the reference's negative cases
+# (an honest prover key, a witness that violates the curve relation) can be replayed
+def ecc_mul_generator_circuit(a=7, b=None):
+    """tests/ecc.rs:19-62 (mul_generator_works): b == a * G; negative case :81-97 passes b = 8 G for a = 7."""
+    cs = Plonk.initialize()
+    wa = cs.append_witness(a)
+    wb = cs.append_point(jubjub_mul(JUBJUB_GENERATOR, a) if b is None else b)
+    wx = cs.component_mul_generator(wa, JUBJUB_GENERATOR)
+    cs.assert_equal_point(wb, wx)
+    return cs
+
+
+def ecc_add_point_circuit(a=None, b=None, c=None, sa=7, sb=8):
+    """tests/ecc.rs:109-160 (add_point_works): c == a + b; negative case :216-232 passes c = 9 G."""
+    from host_mirror.composer import jubjub_add
+    a = jubjub_mul(JUBJUB_GENERATOR, sa) if a is None else a
+    b = jubjub_mul(JUBJUB_GENERATOR, sb) if b is None else b
+    c = jubjub_add(a, b) if c is None else c
+    cs = Plonk.initialize()
+    wa, wb, wc = cs.append_point(a), cs.append_point(b), cs.append_point(c)
+    wx = cs.component_add_point(wa, wb)
+    cs.assert_equal_point(wc, wx)
+    return cs
+
+
+def ecc_mul_point_circuit(a=7, b=None, c=None, sb=8):
+    """tests/ecc.rs:236-290 (mul_point_works): c == a * b; negative case :303-318 passes an unrelated c."""
+    b = jubjub_mul(JUBJUB_GENERATOR, sb) if b is None else b
+    c = jubjub_mul(b, a) if c is None else c
+    cs = Plonk.initialize()
+    wa = cs.append_witness(a)
+    wb, wc = cs.append_point(b), cs.append_point(c)
+    wx = cs.component_mul_point(wa, wb)
+    cs.assert_equal_point(wc, wx)
     return cs

@@ -80,8 +80,8 @@ def msm_vectors(quick=False):
 
 def proof_vectors(quick=False):
     import circuits
-    from dusk_plonk_b200.composer import SynthesizedCircuit
-    from dusk_plonk_b200.transcript import Transcript
+    from host_mirror.composer import SynthesizedCircuit
+    from oracle.merlin import Transcript
     out = []
     for name, build, label in (("range", lambda: circuits.range_circuit((1 << 64) - 1), b"demo"),
                                ("readme", circuits.readme_circuit, b"demo"),

@@ -20,7 +20,7 @@ def main():
     import dusk_plonk_b200 as z
     from dusk_plonk_b200.sharding import Communicator, FourStepNtt, ShardedPlonkParams
     from dusk_plonk_b200.plonk_params import PlonkParams
-    from dusk_plonk_b200.composer import SynthesizedCircuit
+    from host_mirror.composer import SynthesizedCircuit
     from oracle import cport, plonk as oplonk
     from oracle.fields import fr_to_mont_limbs
     from oracle.rng import SplitMix64, random_fr_raw_limbs
@@ -53,7 +53,8 @@ def main():
     prover = z.PlonkKey.compile_with_circuit(sp, b"demo", circ)
     commit = oplonk.default_commit(tau=tau)
     opk, ovk = oplonk.compile_circuit(circ, commit, sp.total_len)
-    otr = z.Transcript.base(b"demo", oplonk.vk_transcript_list(ovk), circ.m)
+    from oracle.merlin import Transcript as OTranscript
+    otr = OTranscript.base(b"demo", oplonk.vk_transcript_list(ovk), circ.m)
     bl = [rng.fr() for _ in range(11)]
     gproof, gpi = prover.create_proof(bl, circ)
     oproof, opi = oplonk.create_proof(opk, circ, commit, otr, bl)

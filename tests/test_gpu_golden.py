@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import dusk_plonk_b200 as z
-from dusk_plonk_b200.composer import SynthesizedCircuit
+from host_mirror.composer import SynthesizedCircuit
 from dusk_plonk_b200.field import R_MOD, fr_from_mont, fr_to_mont, fr_to_mont1, g1_from_mont
 from dusk_plonk_b200.plonk_params import PlonkParams
 

@@ -4,11 +4,14 @@
 Mirrors the reference's integration tests (tests/range.rs, tests/logic.rs, tests/ecc.rs,
 README TestCircuit): compile -> create_proof -> verify; unsatisfied circuits make
 create_proof return Err.  Blinders, SRS trapdoor and transcript are shared explicit inputs."""
+import os
+
 import numpy as np
 import pytest
 
 import dusk_plonk_b200 as z
-from dusk_plonk_b200.composer import SynthesizedCircuit
+from host_mirror.composer import SynthesizedCircuit
+from oracle.merlin import Transcript as OTranscript
 from dusk_plonk_b200.field import fr_from_mont, fr_to_mont, fr_to_mont1
 from dusk_plonk_b200.plonk_params import Error, PlonkParams
 from oracle import plonk as oplonk
@@ -144,7 +147,7 @@ def both_sides(ctx, cs, label=b"demo", seed=8349):
     prover = z.PlonkKey.compile_with_circuit(pp, label, circ)
     commit = oplonk.default_commit(tau=tau)
     opk, ovk = oplonk.compile_circuit(circ, commit, pp.srs.n)
-    otr = z.Transcript.base(label, oplonk.vk_transcript_list(ovk), circ.m)
+    otr = OTranscript.base(label, oplonk.vk_transcript_list(ovk), circ.m)   # the oracle hashes with its own Merlin
     bl = [rng.fr() for _ in range(11)]
     return circ, tau, prover, commit, opk, ovk, otr, bl
 
@@ -214,7 +217,7 @@ def test_prove_2p16_gates_bit_exact_vs_c_prover(ctx, cport):
     """BASELINE config 2: the synthetic 2^16-gate circuit.  Every commitment of the key and the whole
     proof (11 commitments + 16 evaluations) equal the threaded C restatement; the restated verifier
     accepts the GPU proof."""
-    from dusk_plonk_b200.composer import synthetic_circuit
+    from host_mirror.composer import synthetic_circuit
     from oracle import cprover, curve
     from oracle.fields import fr_to_raw_limbs, g1_to_mont_limbs
     k = 16
@@ -224,7 +227,7 @@ def test_prove_2p16_gates_bit_exact_vs_c_prover(ctx, cport):
     pp = PlonkParams.setup_synthetic(ctx, k, fr_to_mont1(tau))
     prover = z.PlonkKey.compile(pp, circ)
     # the CPU side gets the very same SRS points the GPU generated
-    cp = cprover.CProver(circ, pp.srs.download(), b"plonk", z.Transcript)
+    cp = cprover.CProver(circ, pp.srs.download(), b"plonk", OTranscript)
     for nm in list(oplonk.SELECTORS) + ["s_sigma_%d" % i for i in (1, 2, 3, 4)]:
         assert prover.verifier_key[nm] == cp.vk[nm], nm
     bl = [rng.fr() for _ in range(11)]
@@ -238,7 +241,7 @@ def test_prove_2p16_gates_bit_exact_vs_c_prover(ctx, cport):
         assert getattr(gproof, c) == getattr(cproof, c), c
     assert gproof.evaluations == cproof.evaluations
     vk = dict(cp.vk)
-    tr = z.Transcript.base(b"plonk", oplonk.vk_transcript_list(vk), circ.m)
+    tr = OTranscript.base(b"plonk", oplonk.vk_transcript_list(vk), circ.m)
     assert oplonk.verify(vk, circ.n, gproof, circ.pi_indexes, gpi, tr, oplonk.trapdoor_kzg_check(tau))
 
 
@@ -250,7 +253,7 @@ def test_mul_point_circuit_bit_exact_vs_c_prover(ctx, cport):
     tau = rng.fr()
     pp = PlonkParams.setup_synthetic(ctx, 12, fr_to_mont1(tau))
     prover = z.PlonkKey.compile_with_circuit(pp, b"demo", circ)
-    cp = cprover.CProver(circ, prover.keypair.srs.download(), b"demo", z.Transcript)
+    cp = cprover.CProver(circ, prover.keypair.srs.download(), b"demo", OTranscript)
     for nm in list(oplonk.SELECTORS) + ["s_sigma_%d" % i for i in (1, 2, 3, 4)]:
         assert prover.verifier_key[nm] == cp.vk[nm], nm
     bl = [rng.fr() for _ in range(11)]
@@ -261,7 +264,7 @@ def test_mul_point_circuit_bit_exact_vs_c_prover(ctx, cport):
         assert getattr(gproof, c) == getattr(cproof, c), c
     assert gproof.evaluations == cproof.evaluations
     vk = dict(cp.vk)
-    tr = z.Transcript.base(b"demo", oplonk.vk_transcript_list(vk), circ.m)
+    tr = OTranscript.base(b"demo", oplonk.vk_transcript_list(vk), circ.m)
     assert oplonk.verify(vk, circ.n, gproof, circ.pi_indexes, gpi, tr, oplonk.trapdoor_kzg_check(tau))
     assert z.Proof.from_bytes(gproof.to_bytes()) == gproof
 
@@ -302,6 +305,86 @@ def test_negative_cases_of_the_reference_suites(ctx, name):
         prover.create_proof(bl, badc)
     with pytest.raises(oplonk.ProverError):
         oplonk.create_proof(opk, badc, commit, otr, bl)
+
+
+@pytest.mark.parametrize("name", ["mul_generator", "add_point", "mul_point"])
+def test_negative_ecc_cases_of_the_reference(ctx, name):
+    """tests/ecc.rs:81-97 (mul_generator: b = 8 G for a = 7), :216-232 (add_point: c = 9 G != 7 G + 8 G),
+    :303-318 (mul_point: unrelated c): the honest key proves and verifies the honest witness, and
+    ``create_proof`` returns Err for a witness of the same shape that violates the curve relation -- on the
+    GPU and in the oracle alike."""
+    from host_mirror.composer import JUBJUB_GENERATOR as G, jubjub_mul
+    if name == "mul_generator":
+        good, bad = circuits.ecc_mul_generator_circuit(7), circuits.ecc_mul_generator_circuit(7, jubjub_mul(G, 8))
+    elif name == "add_point":
+        good, bad = circuits.ecc_add_point_circuit(), circuits.ecc_add_point_circuit(c=jubjub_mul(G, 9))
+        ident = circuits.ecc_add_point_circuit(a=jubjub_mul(G, 5), b=(0, 1), c=jubjub_mul(G, 5))   # :175-194 identity works
+    else:
+        good, bad = circuits.ecc_mul_point_circuit(7), circuits.ecc_mul_point_circuit(7, c=jubjub_mul(G, 12345))
+    circ, tau, prover, commit, opk, ovk, otr, bl = both_sides(ctx, good)
+    proof, pi = prover.create_proof(bl, circ)
+    oproof, _ = oplonk.create_proof(opk, circ, commit, otr, bl)
+    assert proof.to_bytes() == oproof.to_bytes()
+    assert oplonk.verify(ovk, circ.n, proof, circ.pi_indexes, pi, otr, oplonk.trapdoor_kzg_check(tau))
+    if name == "add_point":
+        ic = SynthesizedCircuit.from_composer(ident)
+        assert ic.m == circ.m
+        iproof, ipi = prover.create_proof(bl, ic)
+        assert oplonk.verify(ovk, circ.n, iproof, circ.pi_indexes, ipi, otr, oplonk.trapdoor_kzg_check(tau))
+    badc = SynthesizedCircuit.from_composer(bad)
+    assert badc.m == circ.m
+    with pytest.raises(Error):
+        prover.create_proof(bl, badc)
+    with pytest.raises(oplonk.ProverError):
+        oplonk.create_proof(opk, badc, commit, otr, bl)
+
+
+def _synthetic_setup(ctx, k):
+    from host_mirror.composer import synthetic_circuit
+    circ = synthetic_circuit(k)
+    rng = SplitMix64(8349)
+    tau = rng.fr()
+    pp = PlonkParams.setup_synthetic(ctx, k, fr_to_mont1(tau))
+    prover = z.PlonkKey.compile(pp, circ)
+    bl = [rng.fr() for _ in range(11)]
+    return circ, tau, pp, prover, bl
+
+
+@pytest.mark.parametrize("k", [12, 16, 20])
+def test_synthetic_proof_equals_committed_oracle_digest(ctx, k):
+    """The proofs bench.py times (seed 8349, BASELINE configs 2 and 5): wire bytes of the native driver against
+    the sha256 the CPU oracle produced for the same circuit (tests/golden/make_synthetic_digests.py) -- no
+    oracle code in this test."""
+    import hashlib
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "synthetic_proofs.json")))
+    circ, tau, pp, prover, bl = _synthetic_setup(ctx, k)
+    proof, _ = prover.create_proof(bl, circ)
+    assert proof.wire_bytes == proof.to_bytes()
+    assert hashlib.sha256(proof.wire_bytes).hexdigest() == gold[str(k)]["sha256"]
+    prover.close()
+
+
+def test_prove_2p20_gates_bit_exact_vs_c_prover(ctx, cport):
+    """BASELINE config 5 on one GPU: the synthetic 2^20-gate circuit through the native driver.  All 15 key
+    commitments, the 11 proof commitments, the 16 evaluations and the 1040 wire bytes equal the threaded C
+    restatement run here on the same SRS points; the restated verifier accepts."""
+    from oracle import cprover
+    circ, tau, pp, prover, bl = _synthetic_setup(ctx, 20)
+    cp = cprover.CProver(circ, pp.srs.download(), b"plonk", OTranscript)
+    for nm in list(oplonk.SELECTORS) + ["s_sigma_%d" % i for i in (1, 2, 3, 4)]:
+        assert prover.verifier_key[nm] == cp.vk[nm], nm
+    cproof, cpi = cp.create_proof(bl, circ)
+    gproof, gpi = prover.create_proof(bl, circ)
+    assert gpi == cpi
+    for c in oplonk.Proof.COMM_NAMES:
+        assert getattr(gproof, c) == getattr(cproof, c), c
+    assert gproof.evaluations == cproof.evaluations
+    assert gproof.wire_bytes == cproof.to_bytes()
+    vk = dict(cp.vk)
+    tr = OTranscript.base(b"plonk", oplonk.vk_transcript_list(vk), circ.m)
+    assert oplonk.verify(vk, circ.n, gproof, circ.pi_indexes, gpi, tr, oplonk.trapdoor_kzg_check(tau))
+    prover.close()
 
 
 @pytest.mark.parametrize("name", ["range", "readme", "logic"])

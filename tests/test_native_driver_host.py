@@ -59,6 +59,21 @@ def test_merlin_known_answer_through_native_ops(lib):
     assert bytes(out).hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
 
 
+def test_transcript_init_is_merlin_new(lib):
+    """zkp_transcript_init == merlin's Transcript::new(label): a host that keeps Merlin inside the library
+    never needs the crate's (private) STROBE state.  The KAT again, with no Python Merlin in the loop."""
+    st = np.zeros(203, dtype=np.uint8)
+    lab = np.frombuffer(b"test protocol", dtype=np.uint8).copy()
+    assert lib.zkp_transcript_init(_ptr(st), _ptr(lab), len(lab)) == 0
+    assert bytes(st) == bytes(_state(transcript.MerlinTranscript(b"test protocol")))
+    msg = np.frombuffer(b"some data", dtype=np.uint8).copy()
+    assert lib.zkp_transcript_append(_ptr(st), b"some label", _ptr(msg), len(msg)) == 0
+    out = np.zeros(32, dtype=np.uint8)
+    assert lib.zkp_transcript_challenge(_ptr(st), b"challenge", _ptr(out), 32) == 0
+    assert bytes(out).hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+    assert lib.zkp_transcript_init(None, _ptr(lab), 3) == ffi.ZKP_ERR_INVALID
+
+
 def test_wide_reduction(lib):
     rng = random.Random(6)
     cases = [bytes(64), bytes([255]) * 64, R.to_bytes(32, "little") + bytes(32), bytes(32) + R.to_bytes(32, "little")]

@@ -71,8 +71,8 @@ def _srs(cport, tau, n):
 @pytest.mark.parametrize("name,faithful", [("range", False), ("range", True), ("logic_curve", False), ("readme", False)])
 def test_c_prover_equals_python_prover(cport, name, faithful):
     import circuits
-    from dusk_plonk_b200.composer import SynthesizedCircuit
-    from dusk_plonk_b200.transcript import Transcript
+    from host_mirror.composer import SynthesizedCircuit
+    from oracle.merlin import Transcript
     from oracle import plonk, cprover
     from oracle.rng import SplitMix64
     cs = {"range": lambda: circuits.range_circuit((1 << 64) - 1), "readme": circuits.readme_circuit,

@@ -29,8 +29,8 @@ def test_bilinearity_and_non_degeneracy():
 def test_verifier_with_real_pairing_accepts_and_rejects():
     """Proof::verify + batch_check end to end with the 2-pairing product (tests/range.rs:66-76)."""
     import circuits
-    from dusk_plonk_b200.composer import SynthesizedCircuit
-    from dusk_plonk_b200.transcript import Transcript
+    from host_mirror.composer import SynthesizedCircuit
+    from oracle.merlin import Transcript
     from oracle import plonk
     from oracle.rng import SplitMix64
     circ = SynthesizedCircuit.from_composer(circuits.range_circuit((1 << 64) - 1))

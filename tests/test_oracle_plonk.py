@@ -3,7 +3,7 @@ transcript.  Follows the reference's integration tests (tests/range.rs:66-97 etc
 positive -> create_proof + verify succeed; negative -> create_proof errs."""
 import pytest
 
-from dusk_plonk_b200.composer import SELECTORS, SynthesizedCircuit, jubjub_on_curve, JUBJUB_GENERATOR
+from host_mirror.composer import SELECTORS, SynthesizedCircuit, jubjub_on_curve, JUBJUB_GENERATOR
 from dusk_plonk_b200.transcript import MerlinTranscript, Transcript
 from dusk_plonk_b200 import widgets
 from oracle import plonk, curve
@@ -102,7 +102,8 @@ def setup(cs, label=b"demo", seed=8349):
     tau = rng.fr()
     commit = plonk.default_commit(tau=tau)
     pk, vk = plonk.compile_circuit(circ, commit, 1 << 20)
-    tr = Transcript.base(label, plonk.vk_transcript_list(vk), circ.m)
+    from oracle.merlin import Transcript as OTranscript
+    tr = OTranscript.base(label, plonk.vk_transcript_list(vk), circ.m)
     bl = [rng.fr() for _ in range(11)]
     return circ, tau, commit, pk, vk, tr, bl
 

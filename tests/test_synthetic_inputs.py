@@ -2,7 +2,7 @@
 oracle's copy (oracle/rng.py) produce the same streams, so GPU and CPU arms see the same workload."""
 import numpy as np
 
-from dusk_plonk_b200.synthetic import SplitMix64, random_fr_raw_limbs
+from host_mirror.synthetic import SplitMix64, random_fr_raw_limbs
 from oracle import rng as orng
 
 
