@@ -4,7 +4,7 @@
 #include <stdio.h>
 
 #include "../dusk-plonk_b200/csrc/arith.cuh"
-#include "fq_inv32.cuh"
+#include "../dusk-plonk_b200/csrc/fq_inv32.cuh"
 
 using namespace zkp;
 

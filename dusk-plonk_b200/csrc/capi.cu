@@ -335,7 +335,7 @@ static int srs_alloc(zkp_ctx* ctx, size_t n, zkp_srs** out) {
     s->c = forced ? (forced < 2 ? 2 : forced) : msm_choose_window(n);
     s->W = 255 / s->c + 1;
     if ((size_t)s->W * n >= (1ull << 31)) { delete s; return ZKP_ERR_INVALID; }
-    cudaError_t e = cudaMalloc(&s->d, (n ? (size_t)s->W * n : 1) * sizeof(g1_affine));
+    cudaError_t e = cudaMalloc(&s->d, (n ? n : 1) * sizeof(g1_affine));
     if (e != cudaSuccess) {
         delete s;
         cuda_fail(ctx, e, "cudaMalloc(srs table)", __FILE__, __LINE__);
@@ -358,7 +358,7 @@ int zkp_srs_load(zkp_ctx* ctx, const uint64_t* xy, size_t n, zkp_srs** out) {
         delete s;
         return cuda_fail(ctx, e, "srs upload", __FILE__, __LINE__);
     }
-    if ((rc = srs_build_table(ctx, s))) { cudaFree(s->d); delete s; return rc; }
+    if ((rc = srs_build_table(ctx, s))) { cudaFree(s->d); cudaFree(s->tab); delete s; return rc; }
     *out = s;
     return ZKP_OK;
 }
@@ -377,7 +377,7 @@ int zkp_srs_generate_range(zkp_ctx* ctx, const uint64_t tau[4], size_t first, si
     memcpy(t.l, tau, 32);
     rc = srs_generate(ctx, t, first, n, s->d);
     if (!rc) rc = srs_build_table(ctx, s);
-    if (rc) { cudaFree(s->d); delete s; return rc; }
+    if (rc) { cudaFree(s->d); cudaFree(s->tab); delete s; return rc; }
     *out = s;
     return ZKP_OK;
 }
@@ -397,6 +397,7 @@ int zkp_srs_free(zkp_ctx* ctx, zkp_srs* srs) {
     if ((rc = set_device(ctx))) return rc;
     ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ZKP_CUDA(ctx, cudaFree(srs->d));
+    if (srs->tab) ZKP_CUDA(ctx, cudaFree(srs->tab));
     delete srs;
     return ZKP_OK;
 }

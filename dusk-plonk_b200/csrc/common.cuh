@@ -27,7 +27,8 @@ struct zkp_buf {
 };
 
 struct zkp_srs {
-    zkp::g1_affine* d = nullptr;  // table: row w holds 2^(c w) * P_i, i < n; row 0 = the SRS powers
+    zkp::g1_affine* d = nullptr;  // the SRS powers P_i, i < n (96-byte points: download / trim)
+    zkp::g1_tab* tab = nullptr;   // window table: row w holds 2^(c w) * P_i in 128-byte entries
     size_t n = 0;
     unsigned c = 0, W = 0;        // window bits / number of table rows (fixed at load time)
 };

@@ -17,6 +17,12 @@ struct alignas(16) g1_affine {
     static ZKP_HD g1_affine inf() { g1_affine r; r.x = fq_t::zero(); r.y = fq_t::zero(); return r; }
 };
 
+// window-table slot (msm.cu): x in bytes [0, 48), y in [64, 112) of a 128-byte entry
+struct alignas(128) g1_tab {
+    fq_t x; uint32_t pad0[4];
+    fq_t y; uint32_t pad1[4];
+};
+
 struct alignas(16) g1_xyzz {
     fq_t x, y, zz, zzz;
     ZKP_HD bool is_inf() const { return zz.is_zero(); }

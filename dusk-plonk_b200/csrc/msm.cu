@@ -15,6 +15,10 @@
 //   1. msm_digits_kernel      Fr Montgomery -> canonical, signed digits, bucket histogram
 //   2. msm_scan_*_kernel      bucket offsets (three-launch tiled exclusive scan)
 //   3. msm_scatter_kernel     counting sort of (table index, sign) by bucket
+//   3b. msm_affine_round_kernel (large jobs)  batched-affine pairwise rounds: every bucket's entries are
+//                             added in pairs, level after level, in AFFINE coordinates -- 6 Fq
+//                             multiplications per addition instead of 10, the one inversion per
+//                             thread (binary GCD, ~88 multiplication times) shared by its K pairs
 //   4. msm_accumulate_kernel  one thread per chunk of L consecutive sorted entries, whatever
 //                             buckets they fall in: XYZZ mixed additions (8M + 2S each, 384-bit
 //                             Montgomery on the integer pipe) -- the hot kernel; equal work per
@@ -30,6 +34,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "fq_inv32.cuh"
 #include "host_inv.h"
 
 namespace zkp {
@@ -47,11 +52,15 @@ struct MsmScratch {
     uint32_t* digits = nullptr;   // [nb][W * n]  bucket | sign << 31, 0xffffffff = zero digit
     uint32_t* sorted = nullptr;   // [nb][W * n]  table index | sign << 31, grouped by bucket
     uint32_t* counts = nullptr;   // [nb][B]
-    uint32_t* offsets = nullptr;  // [nb][B]
+    uint32_t* offsets = nullptr;  // [levels][nb][B]  level r: offsets of ceil(count / 2^r) (level 0 = the sort's)
     uint32_t* cursor = nullptr;   // [nb][B]
     uint32_t* giant = nullptr;    // [nb][B]      buckets whose merge needs a whole block
     uint32_t* meta = nullptr;     // [nb][4]      entries, giant count, overflow flag, pad
-    uint32_t* tile_sums = nullptr;  // [MSM_MAX_BATCH][1024] scan scratch
+    uint32_t* tile_sums = nullptr;  // [levels][MSM_MAX_BATCH][1024] scan scratch
+    uint32_t* totals = nullptr;     // [levels][MSM_MAX_BATCH] entries left at each level
+    uint32_t* plan = nullptr;       // [nb][E/2 + B]  source position | single flag of every output of a round
+    g1_affine* aff[2] = {nullptr, nullptr};  // ping-pong outputs of the batched-affine rounds
+    size_t cap_plan = 0, cap_aff[2] = {0, 0}, cap_offsets = 0;
     g1_xyzz* buckets = nullptr;   // [nb][B]
     g1_xyzz* slots = nullptr;     // [nb][2 * chunks]  head / tail partial sums of each chunk
     g1_xyzz* planes = nullptr;    // [nb][c * plane chunks] + [nb][32] + [nb]
@@ -60,6 +69,10 @@ struct MsmScratch {
     int acc_variant = 3;
     bool acc_variant_forced = false;
     int acc_blocks_per_sm2 = 0;   // occupancy of the 2-blocks/SM build used for small jobs
+    int aff_blocks_per_sm = 0;    // occupancy of the batched-affine round kernel
+    int aff_rounds_forced = -1;   // ZKP_MSM_AFFINE_ROUNDS: tuning / A-B knob (0 = XYZZ only)
+    size_t aff_kmax = 192;        // most pairs one thread (one inversion) takes per round (ZKP_MSM_AFFINE_KMAX)
+    size_t aff_min_pairs = (size_t)1 << 22;   // a round must have this many outputs to beat XYZZ (ZKP_MSM_AFFINE_MIN)
 };
 
 static constexpr uint32_t DIGIT_ZERO = 0xffffffffu;
@@ -71,6 +84,32 @@ __device__ __forceinline__ fr_t msm_ld_fr(const fr_t* p) {
     r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
     r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
+}
+
+// Table entry: one affine point in a 128-byte slot, x in the first 64-byte DRAM atom and y in the second.
+// The gathers of the accumulation are random single-point reads; a 96-byte point straddles atoms (measured:
+// ~200 bytes of DRAM traffic per point read), whereas a padded entry costs exactly two atoms -- and exactly
+// one when only x is needed (the forward pass of the batched-affine rounds).
+__device__ __forceinline__ g1_affine msm_ld_tab(const g1_tab* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    g1_affine r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const uint4 v = __ldg(q + i), u = __ldg(q + 4 + i);
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        w[12 + 4 * i] = u.x; w[12 + 4 * i + 1] = u.y; w[12 + 4 * i + 2] = u.z; w[12 + 4 * i + 3] = u.w;
+    }
+    return r;
+}
+__device__ __forceinline__ void msm_st_tab(g1_tab* p, const g1_affine& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        q[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        q[4 + i] = make_uint4(w[12 + 4 * i], w[12 + 4 * i + 1], w[12 + 4 * i + 2], w[12 + 4 * i + 3]);
+    }
 }
 
 __device__ __forceinline__ g1_affine msm_ld_affine(const g1_affine* p) {
@@ -156,59 +195,75 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
     return ws[wid] + incl - v;
 }
 
-// grid (tiles, nb): tile_sums[pb][tile] = sum of the tile's counters
+// Levels: level r scans ceil(count / 2^r) -- the bucket sizes after r batched-affine pairing rounds
+// (level 0 is the sort itself).  All levels of all polynomials share the three launches:
+// blockIdx.y = level * nb + polynomial.
+static constexpr unsigned MSM_MAX_LEVELS = 9;   // level 0 + up to 8 pairing rounds
+
+__device__ __forceinline__ uint32_t level_count(uint32_t c, unsigned lvl) { return (c + ((1u << lvl) - 1u)) >> lvl; }
+
+// grid (tiles, levels * nb): tile_sums[level][pb][tile] = sum of the tile's counters at that level
 __global__ void __launch_bounds__(SCAN_T) msm_scan_tiles_kernel(const uint32_t* counts, uint32_t B, uint32_t tiles,
-                                                               uint32_t* tile_sums) {
+                                                               unsigned nb, uint32_t* tile_sums) {
     __shared__ uint32_t ws[33];
-    const unsigned pb = blockIdx.y;
+    const unsigned pb = blockIdx.y % nb, lvl = blockIdx.y / nb;
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER;
     const uint32_t* c = counts + (size_t)pb * B;
     uint32_t sum = 0;
     if (base + SCAN_PER <= B) {
         const uint4 a = *reinterpret_cast<const uint4*>(c + base), b2 = *reinterpret_cast<const uint4*>(c + base + 4);
-        sum = a.x + a.y + a.z + a.w + b2.x + b2.y + b2.z + b2.w;
+        sum = level_count(a.x, lvl) + level_count(a.y, lvl) + level_count(a.z, lvl) + level_count(a.w, lvl) +
+              level_count(b2.x, lvl) + level_count(b2.y, lvl) + level_count(b2.z, lvl) + level_count(b2.w, lvl);
     } else {
-        for (uint32_t i = base; i < B && i < base + SCAN_PER; i++) sum += c[i];
+        for (uint32_t i = base; i < B && i < base + SCAN_PER; i++) sum += level_count(c[i], lvl);
     }
     uint32_t total;
     block_exclusive_scan(sum, ws, &total);
-    if (threadIdx.x == 0) tile_sums[(size_t)pb * tiles + blockIdx.x] = total;
+    if (threadIdx.x == 0) tile_sums[(size_t)blockIdx.y * tiles + blockIdx.x] = total;
 }
 
-// one block per polynomial: exclusive scan of its <= 1024 tile sums in place; meta[4 pb] = entries
-__global__ void __launch_bounds__(1024) msm_scan_sums_kernel(uint32_t* tile_sums, uint32_t tiles, uint32_t* meta) {
+// one block per (level, polynomial): exclusive scan of its <= 1024 tile sums in place;
+// totals[level][pb] = entries at that level, meta[4 pb] = entries of the sort (level 0)
+__global__ void __launch_bounds__(1024) msm_scan_sums_kernel(uint32_t* tile_sums, uint32_t tiles, unsigned nb,
+                                                            uint32_t* totals, uint32_t* meta) {
     __shared__ uint32_t ws[33];
-    const unsigned pb = blockIdx.x;
-    uint32_t* t = tile_sums + (size_t)pb * tiles;
+    const unsigned pb = blockIdx.x % nb, lvl = blockIdx.x / nb;
+    uint32_t* t = tile_sums + (size_t)blockIdx.x * tiles;
     const uint32_t v = threadIdx.x < tiles ? t[threadIdx.x] : 0;
     uint32_t total;
     const uint32_t ex = block_exclusive_scan(v, ws, &total);
     if (threadIdx.x < tiles) t[threadIdx.x] = ex;
-    if (threadIdx.x == 0) { meta[4 * pb] = total; meta[4 * pb + 1] = 0; }
+    if (threadIdx.x == 0) {
+        totals[lvl * MSM_MAX_BATCH + pb] = total;
+        if (lvl == 0) { meta[4 * pb] = total; meta[4 * pb + 1] = 0; }
+    }
 }
 
-// grid (tiles, nb): offsets / cursor of the tile's buckets
+// grid (tiles, levels * nb): offsets[level][pb][.] of the tile's buckets (+ the scatter cursors at level 0)
 __global__ void __launch_bounds__(SCAN_T) msm_scan_apply_kernel(const uint32_t* counts, uint32_t B, uint32_t tiles,
-                                                               const uint32_t* tile_sums, uint32_t* offsets,
-                                                               uint32_t* cursor) {
+                                                               unsigned nb, const uint32_t* tile_sums,
+                                                               uint32_t* offsets, uint32_t* cursor) {
     __shared__ uint32_t ws[33];
-    const unsigned pb = blockIdx.y;
+    const unsigned pb = blockIdx.y % nb, lvl = blockIdx.y / nb;
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER;
     const uint32_t* c = counts + (size_t)pb * B;
     uint32_t v[SCAN_PER];
     uint32_t sum = 0;
 #pragma unroll
     for (unsigned i = 0; i < SCAN_PER; i++) {
-        v[i] = base + i < B ? c[base + i] : 0;
+        v[i] = base + i < B ? level_count(c[base + i], lvl) : 0;
         sum += v[i];
     }
     uint32_t total;
-    uint32_t run = block_exclusive_scan(sum, ws, &total) + tile_sums[(size_t)pb * tiles + blockIdx.x];
-    uint32_t* o = offsets + (size_t)pb * B;
+    uint32_t run = block_exclusive_scan(sum, ws, &total) + tile_sums[(size_t)blockIdx.y * tiles + blockIdx.x];
+    uint32_t* o = offsets + (size_t)blockIdx.y * B;
     uint32_t* cu = cursor + (size_t)pb * B;
 #pragma unroll
     for (unsigned i = 0; i < SCAN_PER; i++) {
-        if (base + i < B) { o[base + i] = run; cu[base + i] = run; }
+        if (base + i < B) {
+            o[base + i] = run;
+            if (lvl == 0) cu[base + i] = run;
+        }
         run += v[i];
     }
 }
@@ -228,28 +283,421 @@ __global__ void msm_scatter_kernel(const __grid_constant__ MsmBatch batch, const
     }
 }
 
-// The hot kernel.  Thread t owns the L consecutive sorted entries [t L, (t+1) L) whatever buckets
-// they belong to, so every thread does the same number of mixed additions for ANY digit
+// ---- batched-affine pairing rounds ------------------------------------------------------------------
+// Round r halves every bucket: output j of bucket b is the sum of its entries 2j and 2j + 1 of level r - 1
+// (a bucket with an odd count passes its last entry through).  Affine addition costs
+//     lambda = (y2 - y1) / (x2 - x1),  x3 = lambda^2 - x1 - x2,  y3 = lambda (x1 - x3) - y1
+// i.e. 3 multiplications once 1 / (x2 - x1) is known, and Montgomery's trick turns the K inversions of a
+// thread into 3 (K - 1) multiplications plus ONE inversion: 6 per addition against 10 for the XYZZ mixed
+// addition, plus 88 / K for the binary-GCD inversion (fq_inv32.cuh).  Entries of a bucket are contiguous in
+// the sorted order at every level, so a round is: plan (where are my two inputs) -> forward pass (running
+// product of the denominators, parked in the x slot of the output) -> inversion -> backward pass (the
+// additions).  Thread t of a block owns outputs base + i * 128 + t: every global access of a warp is to 32
+// neighbouring slots.  Exceptional pairs are exact: an operand at infinity (x = y = 0) passes the other
+// through, equal points are doubled through the same inversion (denominator 2 y, numerator 3 x^2), opposite
+// points give infinity.
+
+// plan[q] = position of the first input of output q at the previous level | (1 << 31 if it has no partner)
+__global__ void __launch_bounds__(256) msm_affine_plan_kernel(const uint32_t* offsets, const uint32_t* counts,
+                                                             const uint32_t* totals, uint32_t B, unsigned nb,
+                                                             unsigned r, size_t plan_stride, uint32_t* plan) {
+    const unsigned pb = blockIdx.y;
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= totals[r * MSM_MAX_BATCH + pb]) return;
+    const uint32_t* off_out = offsets + ((size_t)r * nb + pb) * B;
+    const uint32_t* off_in = offsets + ((size_t)(r - 1) * nb + pb) * B;
+    uint32_t blo = 0, bhi = B;      // the last bucket whose offset is <= q is never an empty one
+    while (bhi - blo > 1) {
+        const uint32_t mid = (blo + bhi) >> 1;
+        if (off_out[mid] <= q) blo = mid; else bhi = mid;
+    }
+    const uint32_t j = q - off_out[blo];
+    const uint32_t cin = level_count(counts[(size_t)pb * B + blo], r - 1);
+    plan[(size_t)pb * plan_stride + q] = (off_in[blo] + 2 * j) | ((2 * j + 1 >= cin) ? 0x80000000u : 0u);
+}
+
+__device__ __forceinline__ fq_t msm_ld_fq(const fq_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    fq_t r;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const uint4 v = q[i];
+        r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w;
+    }
+    return r;
+}
+__device__ __forceinline__ void msm_st_fq(fq_t* p, const fq_t& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 3; i++) q[i] = make_uint4(v.l[4 * i], v.l[4 * i + 1], v.l[4 * i + 2], v.l[4 * i + 3]);
+}
+
+// Montgomery-domain inverse through the binary GCD: inv_mod gives (a R)^-1; times R^3 (Montgomery) = R / a
+__device__ __noinline__ fq_t fq_inverse_bingcd(const fq_t& a) {
+    const uint32_t r3w[12] = {0xd94ca1e0u, 0xed48ac6bu, 0x03a7adf8u, 0x315f831eu, 0x615e29ddu, 0x9a53352au,
+                              0x921e1761u, 0x34c04e5eu, 0x65724728u, 0x2512d435u, 0x91755d4du, 0x0aa63460u};
+    fq_t m = fq_t::modulus(), x, r3;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r3.l[i] = r3w[i];
+    fqinv::inv_mod<12>(a.l, m.l, 0x7ffdu /* -p^-1 mod 2^15 */, 51, x.l);
+    return x * r3;
+}
+
+// inputs of a round: FIRST -> table entries named by the sorted list (128-byte slots, y at chunk 4);
+// later rounds -> the dense affine points of the previous level (96 bytes, y at chunk 3)
+template <bool FIRST>
+struct AffSource {
+    const g1_tab* table; const uint32_t* sorted; const g1_affine* in;
+    static constexpr int YOFF = FIRST ? 4 : 3;
+};
+
+enum { PAIR_ADD = 0, PAIR_DBL = 1, PAIR_TAKE1 = 2, PAIR_TAKE2 = 3, PAIR_INF = 4 };
+
+// Operand staging.  The inputs of a pair sit behind a chain of dependent loads (plan -> sorted list -> table),
+// and a thread alternates between that chain and ~3000 cycles of multiplications: left alone, a third of
+// the issue slots are lost to the loads (ncu, first version of this kernel: long-scoreboard stalls 2.2 per
+// issue, integer pipe 61 %).  Here the addresses run two pairs ahead in registers and the operands one pair
+// ahead through cp.async into shared memory -- each thread stages only its own data ([stage][chunk][thread]
+// of 16-byte chunks, conflict-free), so the pipeline needs no barrier and no extra registers:
+//   chunks 0-5 first point (x, y), 6-11 second point, 12-14 running product before this pair.
+static constexpr int AFF_CHUNKS = 15, AFF_STAGES = 2;
+static constexpr size_t AFF_SMEM = (size_t)AFF_STAGES * AFF_CHUNKS * 128 * sizeof(uint4);
+
+__device__ __forceinline__ void cp_async16(uint4* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+struct AffPair {                      // where the inputs of one output live (16-byte chunk pointers)
+    const uint4 *a1, *a2;             // a2 == nullptr: a lone entry that passes through
+    bool n1, n2;                      // negate y (sign of the digit; first round only)
+};
+// The address chain is itself pipelined so that no instruction consumes a load issued in the same
+// iteration: plan word three pairs ahead, the two sorted-list entries it names two pairs ahead (first
+// round only), pointers formed when the cp.async is issued.
+struct AffIdx { uint32_t pl, e1, e2; };
+
+template <bool FIRST>
+__device__ __forceinline__ AffIdx aff_idx(const AffSource<FIRST>& src, uint32_t pl) {
+    AffIdx r;
+    r.pl = pl; r.e1 = r.e2 = 0;
+    if (FIRST) {
+        r.e1 = src.sorted[pl & 0x7fffffffu];
+        if (!(pl & 0x80000000u)) r.e2 = src.sorted[pl + 1];
+    }
+    return r;
+}
+template <bool FIRST>
+__device__ __forceinline__ AffPair aff_pair(const AffSource<FIRST>& src, const AffIdx& x) {
+    AffPair p;
+    const bool single = (x.pl & 0x80000000u) != 0;
+    if (FIRST) {
+        p.a1 = reinterpret_cast<const uint4*>(src.table + (x.e1 & 0x7fffffffu)); p.n1 = (x.e1 & 0x80000000u) != 0;
+        p.a2 = single ? nullptr : reinterpret_cast<const uint4*>(src.table + (x.e2 & 0x7fffffffu));
+        p.n2 = (x.e2 & 0x80000000u) != 0;
+    } else {
+        p.a1 = reinterpret_cast<const uint4*>(src.in + (x.pl & 0x7fffffffu)); p.n1 = false;
+        p.a2 = single ? nullptr : p.a1 + 6; p.n2 = false;
+    }
+    return p;
+}
+
+__device__ __forceinline__ fq_t aff_ld(const uint4* st, int chunk) {
+    fq_t r;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const uint4 v = st[(chunk + i) * 128];
+        r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w;
+    }
+    return r;
+}
+
+// kind of the pair and its denominator; the common case (two finite points, different x) reads no y
+template <int YOFF>
+__device__ __forceinline__ int aff_classify(const uint4* st, const AffPair& p, const fq_t& x1, const fq_t& x2,
+                                            bool have_y, fq_t* d) {
+    const bool z1 = x1.is_zero(), z2 = x2.is_zero(), eq = (x1 == x2);
+    if (!(z1 || z2 || eq)) { *d = x2 - x1; return PAIR_ADD; }
+    fq_t y1 = have_y ? aff_ld(st, 3) : msm_ld_fq(reinterpret_cast<const fq_t*>(p.a1 + YOFF));
+    fq_t y2 = have_y ? aff_ld(st, 9) : msm_ld_fq(reinterpret_cast<const fq_t*>(p.a2 + YOFF));
+    *d = fq_t::one();
+    if (z1 && y1.is_zero()) return PAIR_TAKE2;
+    if (z2 && y2.is_zero()) return PAIR_TAKE1;
+    if (!eq) { *d = x2 - x1; return PAIR_ADD; }
+    if (p.n1) y1 = neg(y1);
+    if (p.n2) y2 = neg(y2);
+    if (!(y1 == y2) || y1.is_zero()) return PAIR_INF;             // P + (-P), or a point of order two
+    *d = dbl(y1);
+    return PAIR_DBL;
+}
+
+// cp.async the x coordinates of a pair (forward pass) / everything the addition needs (backward pass)
+__device__ __forceinline__ void aff_issue_x(uint4* st, const AffPair& p) {
+    if (p.a2) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { cp_async16(st + c * 128, p.a1 + c); cp_async16(st + (6 + c) * 128, p.a2 + c); }
+    }
+    cp_async_commit();
+}
+template <int YOFF>
+__device__ __forceinline__ void aff_issue_all(uint4* st, const AffPair& p, const fq_t* prev) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) { cp_async16(st + c * 128, p.a1 + c); cp_async16(st + (3 + c) * 128, p.a1 + YOFF + c); }
+    if (p.a2) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { cp_async16(st + (6 + c) * 128, p.a2 + c); cp_async16(st + (9 + c) * 128, p.a2 + YOFF + c); }
+        if (prev) {
+            const uint4* g3 = reinterpret_cast<const uint4*>(prev);
+#pragma unroll
+            for (int c = 0; c < 3; c++) cp_async16(st + (12 + c) * 128, g3 + c);
+        }
+    }
+    cp_async_commit();
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(128, 3) msm_affine_round_kernel(const g1_tab* table, const uint32_t* sorted,
+                                                                 size_t entry_stride, const g1_affine* in,
+                                                                 size_t in_stride, g1_affine* out, size_t out_stride,
+                                                                 const uint32_t* plan, size_t plan_stride,
+                                                                 const uint32_t* totals_r, uint32_t K) {
+    extern __shared__ uint4 aff_sm[];
+    const unsigned pb = blockIdx.y, t = threadIdx.x;
+    const uint32_t total = totals_r[pb];
+    const uint64_t base64 = (uint64_t)blockIdx.x * K * 128u;
+    if (base64 + t >= total) return;
+    const uint32_t q0 = (uint32_t)base64 + t;
+    uint32_t Kt = (total - q0 + 127u) / 128u;       // outputs q0 + 128 i below total
+    if (Kt > K) Kt = K;
+    const AffSource<FIRST> src = {table, sorted + (size_t)pb * entry_stride, in + (size_t)pb * in_stride};
+    out += (size_t)pb * out_stride;
+    plan += (size_t)pb * plan_stride;
+    uint4* const sm = aff_sm + t;
+    constexpr int STAGE = AFF_CHUNKS * 128;
+
+    // ---- forward: running product of the denominators, parked in out[q].x
+    fq_t acc = fq_t::one();
+    {
+        // pipeline registers: cur = pair i (operands landed), nxt = pair i + 1 (in flight), ix = entries of
+        // pair i + 2, pl3 = plan word of pair i + 3
+        AffPair cur = aff_pair<FIRST>(src, aff_idx<FIRST>(src, plan[q0])), nxt = cur;
+        aff_issue_x(sm, cur);
+        if (Kt > 1) nxt = aff_pair<FIRST>(src, aff_idx<FIRST>(src, plan[q0 + 128u]));
+        AffIdx ix = {0x80000000u, 0, 0};
+        if (Kt > 2) ix = aff_idx<FIRST>(src, plan[q0 + 256u]);
+        uint32_t pl3 = Kt > 3 ? plan[q0 + 384u] : 0x80000000u;
+        for (uint32_t i = 0; i < Kt; i++) {
+            if (i + 1 < Kt) aff_issue_x(sm + ((i + 1) & 1u) * STAGE, nxt); else cp_async_commit();
+            const AffPair nn = aff_pair<FIRST>(src, ix);             // pair i + 2 (entries loaded last iteration)
+            if (i + 3 < Kt) ix = aff_idx<FIRST>(src, pl3);
+            if (i + 4 < Kt) pl3 = plan[q0 + 128u * (i + 4)];
+            cp_async_wait1();
+            if (cur.a2) {
+                const uint4* st = sm + (i & 1u) * STAGE;
+                fq_t d;
+                const int kind = aff_classify<AffSource<FIRST>::YOFF>(st, cur, aff_ld(st, 0), aff_ld(st, 6), false, &d);
+                if (kind <= PAIR_DBL) acc = acc * d;
+            }
+            msm_st_fq(&out[q0 + 128u * i].x, acc);
+            cur = nxt; nxt = nn;
+        }
+    }
+    fq_t inv = fq_inverse_bingcd(acc);
+    // ---- backward: 1 / d_i = inv * prefix_(i-1), inv <- inv * d_i, then the addition itself
+    {
+        AffPair cur = aff_pair<FIRST>(src, aff_idx<FIRST>(src, plan[q0 + 128u * (Kt - 1)])), nxt = cur;
+        aff_issue_all<AffSource<FIRST>::YOFF>(sm + ((Kt - 1) & 1u) * STAGE, cur, Kt > 1 ? &out[q0 + 128u * (Kt - 2)].x : nullptr);
+        if (Kt > 1) nxt = aff_pair<FIRST>(src, aff_idx<FIRST>(src, plan[q0 + 128u * (Kt - 2)]));
+        AffIdx ix = {0x80000000u, 0, 0};
+        if (Kt > 2) ix = aff_idx<FIRST>(src, plan[q0 + 128u * (Kt - 3)]);
+        uint32_t pl3 = Kt > 3 ? plan[q0 + 128u * (Kt - 4)] : 0x80000000u;
+        for (uint32_t i = Kt; i-- > 0;) {
+            if (i >= 1) aff_issue_all<AffSource<FIRST>::YOFF>(sm + ((i - 1) & 1u) * STAGE, nxt, i >= 2 ? &out[q0 + 128u * (i - 2)].x : nullptr);
+            else cp_async_commit();
+            const AffPair nn = aff_pair<FIRST>(src, ix);             // pair i - 2
+            if (i >= 3) ix = aff_idx<FIRST>(src, pl3);
+            if (i >= 4) pl3 = plan[q0 + 128u * (i - 4)];
+            cp_async_wait1();
+            const uint4* st = sm + (i & 1u) * STAGE;
+            g1_affine res;
+            res.x = aff_ld(st, 0);
+            res.y = aff_ld(st, 3);
+            if (cur.n1) res.y = neg(res.y);
+            if (cur.a2) {
+                const fq_t x2 = aff_ld(st, 6);
+                fq_t d;
+                const int kind = aff_classify<AffSource<FIRST>::YOFF>(st, cur, res.x, x2, true, &d);
+                if (kind <= PAIR_DBL) {
+                    const fq_t prev = i ? aff_ld(st, 12) : fq_t::one();
+                    const fq_t dinv = inv * prev;
+                    inv = inv * d;
+                    fq_t num;
+                    if (kind == PAIR_ADD) {
+                        fq_t y2 = aff_ld(st, 9);
+                        if (cur.n2) y2 = neg(y2);
+                        num = y2 - res.y;
+                    } else {
+                        const fq_t xx = sqr(res.x);
+                        num = dbl(xx) + xx;
+                    }
+                    const fq_t lam = num * dinv;
+                    const fq_t x3 = sqr(lam) - res.x - x2;
+                    res.y = lam * (res.x - x3) - res.y;
+                    res.x = x3;
+                } else if (kind == PAIR_TAKE2) {
+                    res.x = x2;
+                    res.y = aff_ld(st, 9);
+                    if (cur.n2) res.y = neg(res.y);
+                } else if (kind == PAIR_INF) {
+                    res = g1_affine::inf();
+                }
+            }
+            uint4* o = reinterpret_cast<uint4*>(out + q0 + 128u * i);
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(&res);
+#pragma unroll
+            for (int k = 0; k < 6; k++) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            cur = nxt; nxt = nn;
+        }
+    }
+}
+
+// First round: the inputs are random table entries.  Staging them through cp.async was measured SLOWER here
+// (15 uncoalesced 16-byte copies per pair keep the load/store unit's queue full: ncu mio_throttle 2.0 per issue,
+// 12.1 ms against 9.6 ms at 2^22), so this round loads straight into registers: the x coordinates of the next
+// pair one iteration ahead in the forward pass, the address chain (plan word -> sorted-list entries) two
+// ahead in both passes.
+__device__ __forceinline__ fq_t msm_ldg_fq(const uint4* q) {
+    fq_t r;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const uint4 v = __ldg(q + i);
+        r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w;
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(128, 3) msm_affine_first_kernel(const g1_tab* table, const uint32_t* sorted,
+                                                                 size_t entry_stride, g1_affine* out, size_t out_stride,
+                                                                 const uint32_t* plan, size_t plan_stride,
+                                                                 const uint32_t* totals_r, uint32_t K) {
+    const unsigned pb = blockIdx.y, t = threadIdx.x;
+    const uint32_t total = totals_r[pb];
+    const uint64_t base64 = (uint64_t)blockIdx.x * K * 128u;
+    if (base64 + t >= total) return;
+    const uint32_t q0 = (uint32_t)base64 + t;
+    uint32_t Kt = (total - q0 + 127u) / 128u;
+    if (Kt > K) Kt = K;
+    const AffSource<true> src = {table, sorted + (size_t)pb * entry_stride, nullptr};
+    out += (size_t)pb * out_stride;
+    plan += (size_t)pb * plan_stride;
+    constexpr int YOFF = AffSource<true>::YOFF;
+
+    fq_t acc = fq_t::one();
+    {
+        AffPair cur = aff_pair<true>(src, aff_idx<true>(src, plan[q0]));
+        AffIdx ix = {0x80000000u, 0, 0};
+        if (Kt > 1) ix = aff_idx<true>(src, plan[q0 + 128u]);
+        uint32_t pl2 = Kt > 2 ? plan[q0 + 256u] : 0x80000000u;
+        fq_t x1 = fq_t::zero(), x2 = fq_t::zero();
+        if (cur.a2) { x1 = msm_ldg_fq(cur.a1); x2 = msm_ldg_fq(cur.a2); }
+        for (uint32_t i = 0; i < Kt; i++) {
+            const AffPair nxt = aff_pair<true>(src, ix);             // pair i + 1 (entries loaded last iteration)
+            if (i + 2 < Kt) ix = aff_idx<true>(src, pl2);
+            if (i + 3 < Kt) pl2 = plan[q0 + 128u * (i + 3)];
+            fq_t nx1 = fq_t::zero(), nx2 = fq_t::zero();
+            if (i + 1 < Kt && nxt.a2) { nx1 = msm_ldg_fq(nxt.a1); nx2 = msm_ldg_fq(nxt.a2); }
+            if (cur.a2) {
+                fq_t d;
+                const int kind = aff_classify<YOFF>(nullptr, cur, x1, x2, false, &d);
+                if (kind <= PAIR_DBL) acc = acc * d;
+            }
+            msm_st_fq(&out[q0 + 128u * i].x, acc);
+            cur = nxt; x1 = nx1; x2 = nx2;
+        }
+    }
+    fq_t inv = fq_inverse_bingcd(acc);
+    {
+        AffPair cur = aff_pair<true>(src, aff_idx<true>(src, plan[q0 + 128u * (Kt - 1)]));
+        AffIdx ix = {0x80000000u, 0, 0};
+        if (Kt > 1) ix = aff_idx<true>(src, plan[q0 + 128u * (Kt - 2)]);
+        uint32_t pl2 = Kt > 2 ? plan[q0 + 128u * (Kt - 3)] : 0x80000000u;
+        for (uint32_t i = Kt; i-- > 0;) {
+            const AffPair nxt = aff_pair<true>(src, ix);             // pair i - 1
+            if (i >= 2) ix = aff_idx<true>(src, pl2);
+            if (i >= 3) pl2 = plan[q0 + 128u * (i - 3)];
+            g1_affine res = msm_ld_tab(reinterpret_cast<const g1_tab*>(cur.a1));
+            if (cur.n1) res.y = neg(res.y);
+            if (cur.a2) {
+                const fq_t x2 = msm_ldg_fq(cur.a2);
+                const bool z1 = res.x.is_zero(), z2 = x2.is_zero(), eq = (res.x == x2);
+                int kind = PAIR_ADD;
+                fq_t y2 = msm_ldg_fq(cur.a2 + YOFF);
+                if (cur.n2) y2 = neg(y2);
+                if (z1 || z2 || eq) {                                // same decisions as aff_classify
+                    if (z1 && res.y.is_zero()) kind = PAIR_TAKE2;
+                    else if (z2 && y2.is_zero()) kind = PAIR_TAKE1;
+                    else if (!eq) kind = PAIR_ADD;
+                    else if (!(res.y == y2) || res.y.is_zero()) kind = PAIR_INF;
+                    else kind = PAIR_DBL;
+                }
+                if (kind <= PAIR_DBL) {
+                    const fq_t prev = i ? msm_ld_fq(&out[q0 + 128u * (i - 1)].x) : fq_t::one();
+                    const fq_t dinv = inv * prev;
+                    fq_t num;
+                    if (kind == PAIR_ADD) {
+                        inv = inv * (x2 - res.x);
+                        num = y2 - res.y;
+                    } else {
+                        inv = inv * dbl(res.y);
+                        const fq_t xx = sqr(res.x);
+                        num = dbl(xx) + xx;
+                    }
+                    const fq_t lam = num * dinv;
+                    const fq_t x3 = sqr(lam) - res.x - x2;
+                    res.y = lam * (res.x - x3) - res.y;
+                    res.x = x3;
+                } else if (kind == PAIR_TAKE2) {
+                    res.x = x2; res.y = y2;
+                } else if (kind == PAIR_INF) {
+                    res = g1_affine::inf();
+                }
+            }
+            uint4* o = reinterpret_cast<uint4*>(out + q0 + 128u * i);
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(&res);
+#pragma unroll
+            for (int k = 0; k < 6; k++) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            cur = nxt;
+        }
+    }
+}
+
+// The hot kernel of the XYZZ path.  Thread t owns the L consecutive sorted entries [t L, (t+1) L) whatever
+// buckets they belong to, so every thread does the same number of mixed additions for ANY digit
 // distribution.  A bucket that lies inside one chunk is written directly; a bucket cut by a chunk
 // boundary leaves partial sums in the chunk's head slot (first segment of the chunk) or tail slot
 // (last segment), which msm_merge_kernel adds up.
+// GATHER: entries are (table index, sign) pairs of the sort; otherwise they are the affine points the
+// batched-affine rounds left at level `lvl` (bucket b then holds ceil(count / 2^lvl) of them).
 // MB = resident blocks per SM the register allocation is bounded for (2: 174 registers, 3: 168).  Small,
 // one-wave jobs run best with 2, large ones with 3; 4 .. 6 (128 .. 80 registers, spills) were measured
 // slower.
-template <int MB>
-__global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const g1_affine* table, const uint32_t* sorted,
+template <int MB, bool GATHER>
+__global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const void* points, const uint32_t* sorted,
                                                             const uint32_t* offsets, const uint32_t* counts,
-                                                            const uint32_t* meta, uint32_t B, uint32_t L,
+                                                            const uint32_t* totals, unsigned lvl, uint32_t B, uint32_t L,
                                                             uint32_t nchunks, size_t entry_stride, g1_xyzz* buckets,
                                                             g1_xyzz* slots) {
     const unsigned pb = blockIdx.y;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t total = meta[4 * pb];
+    const uint32_t total = totals[pb];
     const uint64_t start64 = (uint64_t)t * L;
     if (start64 >= total) return;
     const uint32_t start = (uint32_t)start64;
     const uint32_t end = start + L < total ? start + L : total;
-    sorted += (size_t)pb * entry_stride;
+    const g1_tab* table = static_cast<const g1_tab*>(points);                       // GATHER: the window table
+    const g1_affine* dense = static_cast<const g1_affine*>(points) + (GATHER ? 0 : (size_t)pb * entry_stride);
+    if (GATHER) sorted += (size_t)pb * entry_stride;
     offsets += (size_t)pb * B; counts += (size_t)pb * B;
     buckets += (size_t)pb * B; slots += (size_t)pb * 2 * nchunks;
     // bucket holding entry `start`: the last b with offsets[b] <= start
@@ -258,7 +706,7 @@ __global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const g1_affine
         const uint32_t mid = (blo + bhi) >> 1;
         if (offsets[mid] <= start) blo = mid; else bhi = mid;
     }
-    uint32_t bk = blo, bbeg = offsets[bk], bend = bbeg + counts[bk];
+    uint32_t bk = blo, bbeg = offsets[bk], bend = bbeg + level_count(counts[bk], lvl);
     uint32_t seg = start;
     bool first = true;
     g1_xyzz acc = g1_xyzz::inf();
@@ -268,13 +716,18 @@ __global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const g1_affine
             else slots[2 * t] = acc;                     // continuation from the previous chunk
             first = false;
             do { bk++; } while (counts[bk] == 0);
-            bbeg = offsets[bk]; bend = bbeg + counts[bk];
+            bbeg = offsets[bk]; bend = bbeg + level_count(counts[bk], lvl);
             seg = j;
             acc = g1_xyzz::inf();
         }
-        const uint32_t e = sorted[j];
-        g1_affine q = msm_ld_affine(table + (e & 0x7fffffffu));
-        if (e & 0x80000000u) q.y = neg(q.y);
+        g1_affine q;
+        if (GATHER) {
+            const uint32_t e = sorted[j];
+            q = msm_ld_tab(table + (e & 0x7fffffffu));
+            if (e & 0x80000000u) q.y = neg(q.y);
+        } else {
+            q = msm_ld_affine(dense + j);
+        }
         xyzz_madd(acc, q);
     }
     if (seg == bbeg && end == bend) buckets[bk] = acc;
@@ -283,13 +736,13 @@ __global__ void __launch_bounds__(128, MB) msm_accumulate_kernel(const g1_affine
 
 // One thread per bucket: empty -> infinity; inside one chunk -> already written; otherwise add the
 // partial sums of the chunks it spans (buckets spanning > GIANT_PARTS chunks go to the block kernel).
-__global__ void __launch_bounds__(128, 4) msm_merge_kernel(const uint32_t* offsets, const uint32_t* counts, uint32_t B,
-                                                       uint32_t L, uint32_t nchunks, const g1_xyzz* slots,
+__global__ void __launch_bounds__(128, 4) msm_merge_kernel(const uint32_t* offsets, const uint32_t* counts, unsigned lvl,
+                                                       uint32_t B, uint32_t L, uint32_t nchunks, const g1_xyzz* slots,
                                                        g1_xyzz* buckets, uint32_t* giant, uint32_t* meta) {
     const unsigned pb = blockIdx.y;
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    const uint32_t cnt = counts[(size_t)pb * B + b], beg = offsets[(size_t)pb * B + b];
+    const uint32_t cnt = level_count(counts[(size_t)pb * B + b], lvl), beg = offsets[(size_t)pb * B + b];
     g1_xyzz* out = buckets + (size_t)pb * B + b;
     if (cnt == 0) { *out = g1_xyzz::inf(); return; }
     const uint32_t t0 = beg / L, t1 = (beg + cnt - 1) / L;
@@ -306,7 +759,7 @@ __global__ void __launch_bounds__(128, 4) msm_merge_kernel(const uint32_t* offse
 
 // One block per giant bucket (e.g. a top window holding only the carry digit).
 __global__ void __launch_bounds__(128) msm_merge_giant_kernel(const uint32_t* offsets, const uint32_t* counts,
-                                                             uint32_t B, uint32_t L, uint32_t nchunks,
+                                                             unsigned lvl, uint32_t B, uint32_t L, uint32_t nchunks,
                                                              const g1_xyzz* slots, g1_xyzz* buckets,
                                                              const uint32_t* giant, const uint32_t* meta) {
     extern __shared__ uint4 smem_raw[];
@@ -314,7 +767,7 @@ __global__ void __launch_bounds__(128) msm_merge_giant_kernel(const uint32_t* of
     const unsigned pb = blockIdx.y, tid = threadIdx.x;
     if (blockIdx.x >= meta[4 * pb + 1]) return;
     const uint32_t b = giant[(size_t)pb * B + blockIdx.x];
-    const uint32_t cnt = counts[(size_t)pb * B + b], beg = offsets[(size_t)pb * B + b];
+    const uint32_t cnt = level_count(counts[(size_t)pb * B + b], lvl), beg = offsets[(size_t)pb * B + b];
     const uint32_t t0 = beg / L, t1 = (beg + cnt - 1) / L;
     slots += (size_t)pb * 2 * nchunks;
     g1_xyzz v = g1_xyzz::inf();
@@ -605,11 +1058,14 @@ __global__ void __launch_bounds__(128, 4) msm_final_coop_kernel(const g1_xyzz* p
 // T[w][i] = 2^c * T[w-1][i]: one thread per point walks the windows (load-time only).  The conversions to
 // affine share inversions in groups of 8 windows (Montgomery's trick; the numerators wait in the table slot
 // itself): W = 16 costs 2 Fermat chains per point instead of 15.  Same field elements as xyzz_to_affine.
-__global__ void __launch_bounds__(128) srs_table_window_kernel(g1_affine* table, size_t n, unsigned c, unsigned W) {
+// Row 0 is the SRS itself (96-byte points, kept for download / trim); the table has 128-byte entries.
+__global__ void __launch_bounds__(128) srs_table_window_kernel(const g1_affine* powers, g1_tab* table, size_t n,
+                                                              unsigned c, unsigned W) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     constexpr unsigned G = 8;
-    g1_affine p = msm_ld_affine(table + i);
+    g1_affine p = msm_ld_affine(powers + i);
+    msm_st_tab(table + i, p);
     g1_xyzz acc = g1_xyzz::inf();
     xyzz_madd(acc, p);
     for (unsigned w0 = 1; w0 < W; w0 += G) {
@@ -622,7 +1078,7 @@ __global__ void __launch_bounds__(128) srs_table_window_kernel(g1_affine* table,
             for (unsigned j = 0; j < c; j++) xyzz_dbl(acc);
             g1_affine xy;
             xy.x = acc.x; xy.y = acc.y;
-            table[(size_t)(w0 + g) * n + i] = xy;                 // X, Y: divided below
+            msm_st_tab(table + (size_t)(w0 + g) * n + i, xy);     // X, Y: divided below
             zz[g] = acc.zz;                                       // zero marks the point at infinity
             zzz[g] = acc.is_inf() ? fq_t::one() : acc.zzz;
             pre[g] = run;
@@ -633,15 +1089,15 @@ __global__ void __launch_bounds__(128) srs_table_window_kernel(g1_affine* table,
         for (unsigned g = cnt; g-- > 0;) {
             const fq_t t = inv * pre[g];                          // 1 / ZZZ_g
             inv = inv * zzz[g];
-            g1_affine* slot = table + (size_t)(w0 + g) * n + i;
+            g1_tab* slot = table + (size_t)(w0 + g) * n + i;
             g1_affine out = g1_affine::inf();
             if (!zz[g].is_zero()) {
-                const g1_affine xy = *slot;
+                const g1_affine xy = msm_ld_tab(slot);
                 const fq_t zi = zz[g] * t;                        // 1 / ZZ = (ZZ / ZZZ)^2
                 out.x = xy.x * sqr(zi);
                 out.y = xy.y * t;
             }
-            *slot = out;
+            msm_st_tab(slot, out);
         }
     }
 }
@@ -814,8 +1270,15 @@ unsigned msm_choose_window(size_t n) {
 
 // Fills rows 1 .. W-1 of the table from row 0 (the SRS powers themselves).
 int srs_build_table(zkp_ctx* ctx, zkp_srs* srs) {
-    if (srs->n == 0 || srs->W <= 1) return ZKP_OK;
-    srs_table_window_kernel<<<(unsigned)((srs->n + 127) / 128), 128, 0, ctx->stream>>>(srs->d, srs->n, srs->c, srs->W);
+    if (srs->n == 0) return ZKP_OK;
+    if (!srs->tab) {
+        cudaError_t e = cudaMalloc(&srs->tab, (size_t)srs->W * srs->n * sizeof(g1_tab));
+        if (e != cudaSuccess) {
+            cuda_fail(ctx, e, "cudaMalloc(srs window table)", __FILE__, __LINE__);
+            return e == cudaErrorMemoryAllocation ? ZKP_ERR_NOMEM : ZKP_ERR_CUDA;
+        }
+    }
+    srs_table_window_kernel<<<(unsigned)((srs->n + 127) / 128), 128, 0, ctx->stream>>>(srs->d, srs->tab, srs->n, srs->c, srs->W);
     ZKP_LAUNCHED(ctx);
     ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ZKP_OK;
@@ -835,7 +1298,7 @@ static void msm_scratch_release(MsmScratch* s) {
     if (!s) return;
     cudaFree(s->digits); cudaFree(s->sorted); cudaFree(s->counts); cudaFree(s->offsets); cudaFree(s->cursor);
     cudaFree(s->giant); cudaFree(s->meta); cudaFree(s->tile_sums); cudaFree(s->buckets); cudaFree(s->slots); cudaFree(s->planes);
-    cudaFree(s->top);
+    cudaFree(s->top); cudaFree(s->totals); cudaFree(s->plan); cudaFree(s->aff[0]); cudaFree(s->aff[1]);
     delete s;
 }
 
@@ -844,7 +1307,8 @@ static void msm_scratch_release(MsmScratch* s) {
 static int msm_scratch_build(zkp_ctx* ctx, MsmScratch* s) {
     ZKP_CUDA(ctx, cudaMalloc(&s->top, sizeof(long long)));
     ZKP_CUDA(ctx, cudaMalloc(&s->meta, 4 * MSM_MAX_BATCH * sizeof(uint32_t)));
-    ZKP_CUDA(ctx, cudaMalloc(&s->tile_sums, 1024 * MSM_MAX_BATCH * sizeof(uint32_t)));
+    ZKP_CUDA(ctx, cudaMalloc(&s->tile_sums, (size_t)MSM_MAX_LEVELS * 1024 * MSM_MAX_BATCH * sizeof(uint32_t)));
+    ZKP_CUDA(ctx, cudaMalloc(&s->totals, MSM_MAX_LEVELS * MSM_MAX_BATCH * sizeof(uint32_t)));
     int mb = 3;  // measured best on B200 (2^22: 22.3 / 21.8 / 23.1 / 23.7 / 24.4 ms for 2..6 blocks per SM)
     if (const char* e = getenv("ZKP_MSM_BLOCKS_PER_SM")) {  // tuning knob: 2 or 3, applies to every job size
         mb = atoi(e);
@@ -853,12 +1317,23 @@ static int msm_scratch_build(zkp_ctx* ctx, MsmScratch* s) {
     mb = mb <= 2 ? 2 : 3;
     s->acc_variant = mb;
     int nb = 0;
-    if (mb == 2) ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<2>, 128, 0));
-    else ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<3>, 128, 0));
+    if (mb == 2) ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<2, true>, 128, 0));
+    else ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel<3, true>, 128, 0));
     s->acc_blocks_per_sm = nb > 0 ? nb : 1;
     int nb2 = 0;
-    ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, msm_accumulate_kernel<2>, 128, 0));
+    ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, msm_accumulate_kernel<2, true>, 128, 0));
     s->acc_blocks_per_sm2 = nb2 > 0 ? nb2 : 1;
+    int nb3 = 0;
+    ZKP_CUDA(ctx, cudaFuncSetAttribute(msm_affine_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM));
+    ZKP_CUDA(ctx, cudaFuncSetAttribute(msm_affine_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AFF_SMEM));
+    // three 60 KB blocks per SM need the large shared-memory carve-out; the default heuristic may pick less
+    ZKP_CUDA(ctx, cudaFuncSetAttribute(msm_affine_round_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    ZKP_CUDA(ctx, cudaFuncSetAttribute(msm_affine_round_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    ZKP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb3, msm_affine_round_kernel<true>, 128, AFF_SMEM));
+    s->aff_blocks_per_sm = nb3 > 0 ? nb3 : 1;
+    if (const char* e = getenv("ZKP_MSM_AFFINE_ROUNDS")) s->aff_rounds_forced = atoi(e);
+    if (const char* e = getenv("ZKP_MSM_AFFINE_MIN")) s->aff_min_pairs = (size_t)atoll(e);
+    if (const char* e = getenv("ZKP_MSM_AFFINE_KMAX")) { s->aff_kmax = (size_t)atoll(e); if (s->aff_kmax < 8) s->aff_kmax = 8; }
     return ZKP_OK;
 }
 
@@ -933,17 +1408,24 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
 
     const uint32_t B = 1u << (c - 1);
     const size_t E = (size_t)W * n;  // upper bound on the entries of one polynomial
-    if (E >= (1ull << 32)) return ZKP_ERR_INVALID;
+    if (E >= (1ull << 31)) return ZKP_ERR_INVALID;
+    // batched-affine pairing rounds while a round still has enough pairs to amortise its inversions
+    unsigned R = 0;
+    while (R + 1 < MSM_MAX_LEVELS && ((E * nb) >> (R + 1)) >= s->aff_min_pairs) R++;
+    if (s->aff_rounds_forced >= 0) R = (unsigned)s->aff_rounds_forced < MSM_MAX_LEVELS - 1 ? (unsigned)s->aff_rounds_forced : MSM_MAX_LEVELS - 1;
+    const unsigned levels = R + 1;
+    const size_t ER = (E >> R) + (R ? B : 0);   // upper bound on what is left for the XYZZ pass
     // chunk length: one wave of resident threads when the job is small, 128-entry chunks (many
     // waves, negligible tail) when it is large
     // small jobs (about one wave) run best with the unconstrained 2-blocks/SM build, large ones with 3
-    const int variant = (s->acc_variant_forced || E * nb >= ((size_t)1 << 23)) ? s->acc_variant : 2;
-    const size_t resident =
+    const int variant = (s->acc_variant_forced || ER * nb >= ((size_t)1 << 23)) ? s->acc_variant : 2;
+    size_t resident =
         (size_t)ctx->sm_count * (variant == 2 ? s->acc_blocks_per_sm2 : s->acc_blocks_per_sm) * 128;
-    size_t L = (E * nb + resident - 1) / resident;
+    if (resident == 0) resident = 128;
+    size_t L = (ER * nb + resident - 1) / resident;
     if (L < 8) L = 8;
     if (L > 128) L = 128;
-    const uint32_t nchunks = (uint32_t)((E + L - 1) / L);
+    const uint32_t nchunks = (uint32_t)((ER + L - 1) / L);
     // two-level bucket reduction: weight v = hi * 2^h + lo
     const unsigned h = c / 2;
     const uint32_t ncols = 1u << h, nrows = (B >> h) + 1;
@@ -956,16 +1438,23 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     if ((rc = ensure(ctx, &s->sorted, &s->cap_sorted, E * nb))) return rc;
     if (s->cap_buckets < (size_t)B * nb) {
         const size_t need = (size_t)B * nb;
-        size_t c1 = s->cap_buckets, c2 = c1, c3 = c1, c4 = c1, c5 = c1;
+        size_t c1 = s->cap_buckets, c3 = c1, c4 = c1, c5 = c1;
         if ((rc = ensure(ctx, &s->counts, &c1, need))) return rc;
-        if ((rc = ensure(ctx, &s->offsets, &c2, need))) return rc;
         if ((rc = ensure(ctx, &s->cursor, &c3, need))) return rc;
         if ((rc = ensure(ctx, &s->giant, &c4, need))) return rc;
         if ((rc = ensure(ctx, &s->buckets, &c5, need))) return rc;
         s->cap_buckets = need;
     }
+    if ((rc = ensure(ctx, &s->offsets, &s->cap_offsets, (size_t)levels * B * nb))) return rc;
     if ((rc = ensure(ctx, &s->slots, &s->cap_slots, (size_t)2 * nchunks * nb))) return rc;
     if ((rc = ensure(ctx, &s->planes, &s->cap_planes, nplanes))) return rc;
+    // outputs of round r (1-based) per polynomial: at most (E >> r) + B
+    const size_t half = (E >> 1) + B, quarter = (E >> 2) + B;
+    if (R >= 1) {
+        if ((rc = ensure(ctx, &s->plan, &s->cap_plan, half * nb))) return rc;
+        if ((rc = ensure(ctx, &s->aff[0], &s->cap_aff[0], half * nb))) return rc;
+    }
+    if (R >= 2 && (rc = ensure(ctx, &s->aff[1], &s->cap_aff[1], quarter * nb))) return rc;
     g1_xyzz* rowcol = s->planes;
     g1_xyzz* planes = rowcol + (size_t)nb * (nrows + ncols);
     g1_xyzz* sums = planes + (size_t)nb * 32;
@@ -980,11 +1469,12 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     ZKP_LAUNCHED(ctx);
     {
         const uint32_t tiles = (B + SCAN_TILE - 1) / SCAN_TILE;  // <= 1024 for c <= 22
-        msm_scan_tiles_kernel<<<dim3(tiles, nb), SCAN_T, 0, st>>>(s->counts, B, tiles, s->tile_sums);
+        msm_scan_tiles_kernel<<<dim3(tiles, levels * nb), SCAN_T, 0, st>>>(s->counts, B, tiles, nb, s->tile_sums);
         ZKP_LAUNCHED(ctx);
-        msm_scan_sums_kernel<<<nb, 1024, 0, st>>>(s->tile_sums, tiles, s->meta);
+        msm_scan_sums_kernel<<<levels * nb, 1024, 0, st>>>(s->tile_sums, tiles, nb, s->totals, s->meta);
         ZKP_LAUNCHED(ctx);
-        msm_scan_apply_kernel<<<dim3(tiles, nb), SCAN_T, 0, st>>>(s->counts, B, tiles, s->tile_sums, s->offsets, s->cursor);
+        msm_scan_apply_kernel<<<dim3(tiles, levels * nb), SCAN_T, 0, st>>>(s->counts, B, tiles, nb, s->tile_sums,
+                                                                           s->offsets, s->cursor);
         ZKP_LAUNCHED(ctx);
     }
     msm_scatter_kernel<<<dim3((unsigned)((n + 255) / 256), nb), 256, 0, st>>>(
@@ -993,12 +1483,53 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     }
     {
     ProfScope prof(ctx, "msm_accumulate");
+    // pairing rounds: level r - 1 -> level r; outputs ping-pong between aff[0] (odd rounds) and aff[1]
+    for (unsigned r = 1; r <= R; r++) {
+        const size_t bound = (E >> r) + B;                    // outputs of this round per polynomial
+        // pairs per thread: whole waves of resident blocks (a partly filled last wave costs as much as a full
+        // one), at most kmax pairs per inversion, at least 8
+        const size_t slots = (size_t)ctx->sm_count * s->aff_blocks_per_sm;
+        const size_t kmax = s->aff_kmax;
+        size_t waves = (bound * nb + slots * 128 * kmax - 1) / (slots * 128 * kmax);
+        if (waves == 0) waves = 1;
+        size_t K = (bound * nb + waves * slots * 128 - 1) / (waves * slots * 128);
+        if (K < 8) K = 8;
+        if (K > kmax) K = kmax;
+        msm_affine_plan_kernel<<<dim3((unsigned)((bound + 255) / 256), nb), 256, 0, st>>>(
+            s->offsets, s->counts, s->totals, B, nb, r, half, s->plan);
+        ZKP_LAUNCHED(ctx);
+        const dim3 rgrid((unsigned)((bound + K * 128 - 1) / (K * 128)), nb);
+        g1_affine* outp = s->aff[(r - 1) & 1];
+        const size_t out_stride = ((r - 1) & 1) ? quarter : half;
+        if (r == 1) {
+            msm_affine_first_kernel<<<rgrid, 128, 0, st>>>(srs->tab, s->sorted, E, outp, out_stride, s->plan, half,
+                                                           s->totals + r * MSM_MAX_BATCH, (uint32_t)K);
+        } else {
+            const g1_affine* inp = s->aff[r & 1];
+            const size_t in_stride = (r & 1) ? quarter : half;
+            msm_affine_round_kernel<false><<<rgrid, 128, AFF_SMEM, st>>>(nullptr, nullptr, 0, inp, in_stride, outp, out_stride,
+                                                                  s->plan, half, s->totals + r * MSM_MAX_BATCH, (uint32_t)K);
+        }
+        ZKP_LAUNCHED(ctx);
+    }
     const dim3 agrid((nchunks + 127) / 128, nb);
+    const uint32_t* offR = s->offsets + (size_t)R * nb * B;
+    const uint32_t* totR = s->totals + R * MSM_MAX_BATCH;
+    if (R == 0) {
 #define ZKP_ACC(...) msm_accumulate_kernel<__VA_ARGS__><<<agrid, 128, 0, st>>>( \
-        srs->d, s->sorted, s->offsets, s->counts, s->meta, B, (uint32_t)L, nchunks, E, s->buckets, s->slots)
-    if (variant == 2) ZKP_ACC(2);
-    else ZKP_ACC(3);
+        srs->tab, s->sorted, offR, s->counts, totR, 0u, B, (uint32_t)L, nchunks, E, s->buckets, s->slots)
+        if (variant == 2) ZKP_ACC(2, true);
+        else ZKP_ACC(3, true);
 #undef ZKP_ACC
+    } else {
+        const g1_affine* pts = s->aff[(R - 1) & 1];
+        const size_t pstride = ((R - 1) & 1) ? quarter : half;
+#define ZKP_ACC(...) msm_accumulate_kernel<__VA_ARGS__><<<agrid, 128, 0, st>>>( \
+        pts, nullptr, offR, s->counts, totR, R, B, (uint32_t)L, nchunks, pstride, s->buckets, s->slots)
+        if (variant == 2) ZKP_ACC(2, false);
+        else ZKP_ACC(3, false);
+#undef ZKP_ACC
+    }
     ZKP_LAUNCHED(ctx);
     }
     if (ctx->after_accumulate) {
@@ -1008,7 +1539,8 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     }
     {
     ProfScope prof(ctx, "msm_reduce");
-    msm_merge_kernel<<<dim3((B + 127) / 128, nb), 128, 0, st>>>(s->offsets, s->counts, B, (uint32_t)L, nchunks, s->slots,
+    const uint32_t* offR = s->offsets + (size_t)R * nb * B;
+    msm_merge_kernel<<<dim3((B + 127) / 128, nb), 128, 0, st>>>(offR, s->counts, R, B, (uint32_t)L, nchunks, s->slots,
                                                                s->buckets, s->giant, s->meta);
     ZKP_LAUNCHED(ctx);
     {
@@ -1016,7 +1548,7 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
         const uint32_t gmax = nchunks / GIANT_PARTS < B ? nchunks / GIANT_PARTS : B;
         if (gmax) {
             msm_merge_giant_kernel<<<dim3(gmax, nb), 128, 128 * sizeof(g1_xyzz), st>>>(
-                s->offsets, s->counts, B, (uint32_t)L, nchunks, s->slots, s->buckets, s->giant, s->meta);
+                offR, s->counts, R, B, (uint32_t)L, nchunks, s->slots, s->buckets, s->giant, s->meta);
             ZKP_LAUNCHED(ctx);
         }
     }
