@@ -236,8 +236,9 @@ def run_reference(args, rank, world):
 def workload_config(args, world=1):
     shard = world > 1 and not args.independent
     if shard:
-        par = {"prove": "ONE proof over %d GPUs: commits sharded by SRS ranges (partial sums gathered over NCCL), coset "
-                        "transforms and quotient slices dealt out per GPU (all-to-all of slices over NVLink)" % world,
+        par = {"prove": "ONE proof over %d GPUs, native driver: commits sharded by SRS ranges (partial sums gathered over "
+                        "NCCL), the 8n quotient domain split by cosets (n-point transforms, point-wise quotient, one "
+                        "slab exchange for the inverse transform)" % world,
                "compile": "ONE compile over %d GPUs, commits sharded by SRS ranges" % world,
                "msm": "ONE MSM over %d GPUs: SRS ranges + 96-byte partial-sum all-gather" % world,
                "ntt": "ONE transform over %d GPUs: four-step NTT, one NCCL all-to-all" % world}[args.workload]
@@ -278,9 +279,9 @@ class ProveJob:
         rng = SplitMix64(8349)
         tau = rng.fr()
         t0 = time.perf_counter()
-        if comm is not None:
-            from dusk_plonk_b200.sharding import ShardedPlonkParams
-            pp = ShardedPlonkParams.setup_synthetic(ctx, comm, logn, fr_to_mont1(tau))
+        if comm is not None:   # native multi-GPU driver: zkp_comm (NCCL inside libzkp_b200.so)
+            from dusk_plonk_b200.plonk_params import ShardedNativeParams
+            pp = ShardedNativeParams.setup_synthetic(ctx, comm, logn, fr_to_mont1(tau))
         else:
             pp = PlonkParams.setup_synthetic(ctx, logn, fr_to_mont1(tau))
         ctx.sync()
@@ -292,15 +293,11 @@ class ProveJob:
         self.compile_ms = (time.perf_counter() - t0) * 1e3
         self.bl = [rng.fr() for _ in range(11)]
         self.sharded = comm is not None
-        if self.sharded:    # the sharded proof takes host-gathered wire columns
-            self.wa_host = z.WitnessAssignment.from_circuit(circ, circ.n)
-            self.wa_host.wires_mont = pinned_copy(z, self.wa_host.wires_mont)
-            self.wa_host.dense_pi_mont = pinned_copy(z, self.wa_host.dense_pi_mont)
-            self.h2d = 5 * circ.n * 32 + 19 * 32
-        else:               # witness values in pinned host memory; the wire gather runs on the device
-            self.wa_host = z.WitnessValues.from_circuit(circ)
-            self.wa_host.witness_mont = pinned_copy(z, self.wa_host.witness_mont)
-            self.h2d = (self.wa_host.witness_mont.shape[0] + len(self.wa_host.pi_values) + 19) * 32
+        # witness values in pinned host memory; the wire gather runs on the device (every rank of a sharded
+        # proof ships the same values to its own GPU)
+        self.wa_host = z.WitnessValues.from_circuit(circ)
+        self.wa_host.witness_mont = pinned_copy(z, self.wa_host.witness_mont)
+        self.h2d = (self.wa_host.witness_mont.shape[0] + len(self.wa_host.pi_values) + 19) * 32
         self.wa_dev = z.WitnessAssignment.from_circuit(circ, circ.n).to_device(ctx)
         self.d2h = 11 * 96 + 17 * 32
         self.proofs = []
@@ -365,11 +362,13 @@ def main():
     hbm_peak, hbm_src = measured_peaks()
     imad_pk, imad_src = imad_peak()
     shard = world > 1 and not args.independent
-    comm = None
+    comm = ncomm = None
     if shard:
         import torch
         from dusk_plonk_b200.sharding import Communicator, FourStepNtt, ShardedPlonkParams
         comm = Communicator(torch.device("cuda", local_rank))
+        if args.workload in ("prove", "compile"):
+            ncomm = z.NativeComm.from_torch_distributed(ctx)
     # seeds: independent jobs differ per rank, a sharded job is the same job on every rank
     jr = 0 if shard or world == 1 else rank
 
@@ -391,7 +390,8 @@ def main():
         circ = synthetic_circuit(args.logn)
         taum = fr_to_mont1(SplitMix64(8349).fr())
         t0 = time.perf_counter()
-        pp = (ShardedPlonkParams.setup_synthetic(ctx, comm, args.logn, taum) if shard
+        from dusk_plonk_b200.plonk_params import ShardedNativeParams
+        pp = (ShardedNativeParams.setup_synthetic(ctx, ncomm, args.logn, taum) if shard
               else PlonkParams.setup_synthetic(ctx, args.logn, taum))
         ctx.sync()
         extra["srs_setup_ms"] = (time.perf_counter() - t0) * 1e3
@@ -405,7 +405,7 @@ def main():
         h2d, d2h = 11 * circ.n * 32 + 4 * circ.n * 4, 15 * 96
         dominant, metric, n = "msm_accumulate", "compile_throughput", 1
     elif args.workload == "prove":
-        job = ProveJob(z, ctx, args.logn, comm)
+        job = ProveJob(z, ctx, args.logn, ncomm)
         step, e2e_step, h2d, d2h = job.step, job.e2e_step, job.h2d, job.d2h
         extra["srs_setup_ms"], extra["compile_ms"] = job.srs_ms, job.compile_ms
         dominant, metric, n = "msm_accumulate", "create_proof_throughput", 1
@@ -461,12 +461,19 @@ def main():
     ctx.prof_reset()
     l0 = ctx.launches
     pts0 = ctx.msm_points
+    comm0 = ncomm.stats() if ncomm is not None else (0, 0)
     ctx.timer_start()
     for _ in range(args.steps):
         step()
     ms = ctx.timer_stop_ms()
     launches = ctx.launches - l0
     msm_pts = ctx.msm_points - pts0
+    if ncomm is not None:
+        c1 = ncomm.stats()
+        extra["nccl"] = {"collectives_per_step": (c1[0] - comm0[0]) / args.steps,
+                         "bytes_sent_per_rank_per_step": (c1[1] - comm0[1]) / args.steps,
+                         "where": "inside libzkp_b200.so (zkp_comm): partial-commitment gathers, the coset exchange of "
+                                  "the quotient's inverse transform, the gather of t(X)"}
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     dom_ms, dom_cnt = ctx.prof_read(dominant)
@@ -590,6 +597,8 @@ def main():
         print(json.dumps(line), flush=True)
     if job is not None:
         job.prover.close()
+    if ncomm is not None:
+        ncomm.close()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "comm.cuh"
 
 using namespace zkp;
 
@@ -441,6 +442,31 @@ int zkp_commit_batch_dev(zkp_ctx* ctx, const zkp_srs* srs, const zkp_poly_ref* p
     if (rc) return rc;
     for (unsigned i = 0; i < count; i++) status[i] = ovf[i] ? ZKP_ERR_DEGREE : ZKP_OK;
     return ZKP_OK;
+}
+
+int zkp_commit_batch_sharded_dev(zkp_ctx* ctx, zkp_comm* comm, const zkp_srs* srs, const zkp_poly_ref* polys,
+                                 unsigned count, uint64_t* out_xy, int* status) {
+    if (!ctx || !srs || !polys || !out_xy || !status || count == 0 || count > 8) return ZKP_ERR_INVALID;
+    const fr_t* ptrs[8];
+    size_t lens[8];
+    int ovf[8];
+    for (unsigned i = 0; i < count; i++) {
+        if (!polys[i].buf || polys[i].off + polys[i].len > polys[i].buf->n) return ZKP_ERR_INVALID;
+        ptrs[i] = polys[i].buf->d + polys[i].off;
+        lens[i] = polys[i].len;
+    }
+    int rc = msm_commit_sharded(ctx, comm, srs, ptrs, lens, count, reinterpret_cast<g1_affine*>(out_xy), ovf);
+    if (rc) return rc;
+    for (unsigned i = 0; i < count; i++) status[i] = ovf[i] ? ZKP_ERR_DEGREE : ZKP_OK;
+    return ZKP_OK;
+}
+
+int zkp_coset8_ntt_dev(zkp_ctx* ctx, const zkp_buf* in, size_t in_off, size_t len_in, zkp_buf* out, size_t out_off,
+                       unsigned k, unsigned first, unsigned count) {
+    if (!ctx || !in || !out || k > 25 || count == 0 || first + count > 8) return ZKP_ERR_INVALID;
+    const size_t n = (size_t)1 << k;
+    if (in_off + len_in > in->n || len_in > 2 * n || out_off + (size_t)count * n > out->n) return ZKP_ERR_INVALID;
+    return coset8_forward(ctx, in->d + in_off, len_in, out->d + out_off, k, first, count);
 }
 
 int zkp_poly_degree_dev(zkp_ctx* ctx, const zkp_buf* coeffs, size_t off, size_t n, long long* top) {

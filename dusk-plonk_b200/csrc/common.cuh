@@ -16,6 +16,7 @@
 namespace zkp {
 
 struct NttDomain;  // ntt.cu
+struct Coset8Tab;  // ntt.cu
 struct MsmScratch; // msm.cu
 
 }  // namespace zkp
@@ -33,6 +34,8 @@ struct zkp_srs {
     unsigned c = 0, W = 0;        // window bits / number of table rows (fixed at load time)
 };
 
+struct zkp_comm;   // comm.cuh
+
 struct zkp_ctx {
     int device = 0;
     int sm_count = 0;
@@ -43,6 +46,7 @@ struct zkp_ctx {
     uint64_t msm_points = 0;  // points summed by msm_run since creation (roofline accounting)
     unsigned msm_window = 0;
     std::map<unsigned, zkp::NttDomain*> domains;
+    std::map<unsigned, zkp::Coset8Tab*> coset8;   // key 8 k + u: scaling tables of coset u of the 8n domain
     zkp::fr_t* ntt_scratch = nullptr;
     size_t ntt_scratch_n = 0;
     zkp::MsmScratch* msm = nullptr;
@@ -116,6 +120,8 @@ inline int set_device(zkp_ctx* ctx) {
 int ntt_run(zkp_ctx* ctx, const fr_t* in, size_t in_stride, size_t len_in, fr_t* out,
             size_t out_stride, unsigned k, bool inverse, bool coset, unsigned batch);
 void ntt_free_domains(zkp_ctx* ctx);
+int coset8_forward(zkp_ctx* ctx, const fr_t* in, size_t len_in, fr_t* out, unsigned k, unsigned first, unsigned count);
+int coset8_inverse_local(zkp_ctx* ctx, fr_t* data, unsigned k, unsigned first, unsigned count);
 int ntt_elements(zkp_ctx* ctx, unsigned k, fr_t* out);
 fr_t fft_constant_host(unsigned k, int kind);
 int ntt_permute(zkp_ctx* ctx, const fr_t* in, fr_t* out, size_t A, size_t B, size_t w);
@@ -126,6 +132,10 @@ int ntt_scale_matrix(zkp_ctx* ctx, fr_t* data, size_t rows, size_t cols, size_t 
 int msm_run(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* scalars_dev, size_t n, g1_affine* out_host);
 int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_dev, const size_t* lens, unsigned nb,
                   g1_affine* out_host, int* overflow);
+int msm_run_batch_ex(zkp_ctx* ctx, zkp_comm* cm, const zkp_srs* srs, const fr_t* const* scalars_dev, const size_t* lens,
+                     const size_t* offs, unsigned nb, g1_affine* out_host, int* overflow);
+int msm_commit_sharded(zkp_ctx* ctx, zkp_comm* cm, const zkp_srs* srs, const fr_t* const* polys, const size_t* lens,
+                       unsigned nb, g1_affine* out_host, int* overflow);
 unsigned msm_choose_window(size_t n);
 int srs_build_table(zkp_ctx* ctx, zkp_srs* srs);
 int msm_highest_nonzero(zkp_ctx* ctx, const fr_t* scalars_dev, size_t n, long long* out);

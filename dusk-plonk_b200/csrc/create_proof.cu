@@ -19,6 +19,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "comm.cuh"
 #include "host_inv.h"
 
 struct zkp_prover {
@@ -36,6 +37,14 @@ struct zkp_prover {
     uint32_t* wire_idx = nullptr;   // [4][m]: witness index of wire j at gate i (src/prover.rs:114-119)
     uint32_t* pi_idx = nullptr;     // gate positions of the public inputs
     size_t m = 0, pi_count = 0, wv_cap = 0;
+    // one proof over several GPUs (zkp_prover_create_sharded): this rank owns cosets u0 .. u0 + nloc - 1 of the
+    // 8n domain (nl = nloc * n evaluations per vector) and coefficient slab [rank * slab, (rank + 1) * slab) of
+    // every n-chunk of the quotient
+    zkp_comm* comm = nullptr;
+    bool sharded = false;
+    unsigned nloc = 8, u0 = 0;
+    size_t nl = 0, slab = 0;
+    zkp_buf *TL = nullptr, *YA = nullptr, *TS = nullptr;   // local quotient values, exchanged terms, combined slabs
     bool wiring_set = false;        // zkp_prover_set_wiring has been called (prove_witness needs it)
     size_t max_wire_idx = 0;        // largest witness index the wiring reads (a witness array must cover it)
     zkp::fr_t* wv = nullptr;        // staging for the witness values and public-input values
@@ -370,6 +379,53 @@ __global__ void scatter_pi_kernel(const fr_t* values, const uint32_t* idx, size_
     if (i < n) pi[i] = values[c];
 }
 
+// t_(i' + n q) = sum_u c[q][u] Y_u[i'], c[q][u] = g^(-n q) w_8^(-u q): the cross-coset step of the 8n-point
+// inverse coset transform (derivation: ntt.cu, "cosets of the n-domain").  y[u][i'], out[q][i'], i' < slab.
+struct CombineArgs { fr_t c[8][8]; const fr_t* y; fr_t* out; size_t slab; };
+
+__global__ void __launch_bounds__(128) coset8_combine_kernel(const __grid_constant__ CombineArgs a) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.slab) return;
+    fr_t y[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const uint4* p = reinterpret_cast<const uint4*>(a.y + (size_t)u * a.slab + i);
+        const uint4 lo = p[0], hi = p[1];
+        y[u].l[0] = lo.x; y[u].l[1] = lo.y; y[u].l[2] = lo.z; y[u].l[3] = lo.w;
+        y[u].l[4] = hi.x; y[u].l[5] = hi.y; y[u].l[6] = hi.z; y[u].l[7] = hi.w;
+    }
+#pragma unroll 1
+    for (int q = 0; q < 8; q++) {
+        fr_t t = a.c[q][0] * y[0];
+#pragma unroll
+        for (int u = 1; u < 8; u++) t = t + a.c[q][u] * y[u];
+        uint4* o = reinterpret_cast<uint4*>(a.out + (size_t)q * a.slab + i);
+        o[0] = make_uint4(t.l[0], t.l[1], t.l[2], t.l[3]);
+        o[1] = make_uint4(t.l[4], t.l[5], t.l[6], t.l[7]);
+    }
+}
+
+static int coset8_combine(zkp_ctx* ctx, const fr_t* y, fr_t* out, size_t slab, unsigned k) {
+    CombineArgs a;
+    const fr w8i = F::inv(fr_load(reinterpret_cast<const uint64_t*>(fft_constant_host(3, 0).l)));
+    const fr gni = F::inv(F::pow(F::from_u64(7), (uint64_t)1 << k));
+    fr gq = F::one();
+    for (int q = 0; q < 8; q++) {
+        const fr wq = F::pow(w8i, (uint64_t)q);     // w_8^-q
+        fr v = gq;                                   // g^(-n q) w_8^(-q u)
+        for (int u = 0; u < 8; u++) {
+            fr_store(reinterpret_cast<uint64_t*>(a.c[q][u].l), v);
+            v = F::mul(v, wq);
+        }
+        gq = F::mul(gq, gni);
+    }
+    a.y = y; a.out = out; a.slab = slab;
+    ProfScope prof(ctx, "ntt");
+    coset8_combine_kernel<<<(unsigned)((slab + 127) / 128), 128, 0, ctx->stream>>>(a);
+    ZKP_LAUNCHED(ctx);
+    return ZKP_OK;
+}
+
 #define TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
 static inline zkp_poly_ref ref(const zkp_buf* b, size_t off, size_t len) { zkp_poly_ref r; r.buf = b; r.off = off; r.len = len; return r; }
@@ -397,7 +453,13 @@ static void run_side_job(void* arg) {
     j->rc = ZKP_ERR_CUDA;
     if (cudaEventRecord(pr->ev_main, ctx->stream) != cudaSuccess) return;
     if (cudaStreamWaitEvent(side->stream, pr->ev_main, 0) != cudaSuccess) return;
-    j->rc = ntt_run(side, j->in, j->in_stride, j->len_in, j->out, n8, pr->k + 3, false, true, j->batch);
+    if (pr->sharded) {   // the rank's cosets of each polynomial: n-point transforms, no data from other ranks
+        j->rc = ZKP_OK;
+        for (unsigned b = 0; b < j->batch && j->rc == ZKP_OK; b++)
+            j->rc = coset8_forward(side, j->in + b * j->in_stride, j->len_in, j->out + b * pr->nl, pr->k, pr->u0, pr->nloc);
+    } else {
+        j->rc = ntt_run(side, j->in, j->in_stride, j->len_in, j->out, n8, pr->k + 3, false, true, j->batch);
+    }
     if (j->rc == ZKP_OK && cudaEventRecord(pr->ev_side, side->stream) != cudaSuccess) j->rc = ZKP_ERR_CUDA;
 }
 
@@ -422,7 +484,7 @@ static int commit_group(zkp_prover* pr, const zkp_poly_ref* polys, unsigned coun
     size_t lens[8];
     int ovf[8];
     for (unsigned i = 0; i < count; i++) { ptrs[i] = polys[i].buf->d + polys[i].off; lens[i] = polys[i].len; }
-    TRY(msm_run_batch(pr->ctx, pr->srs, ptrs, lens, count, reinterpret_cast<g1_affine*>(out_xy), ovf));
+    TRY(msm_commit_sharded(pr->ctx, pr->comm, pr->srs, ptrs, lens, count, reinterpret_cast<g1_affine*>(out_xy), ovf));
     for (unsigned i = 0; i < count; i++) if (ovf[i]) return ZKP_ERR_DEGREE;  // commit(..)? in the reference
     return ZKP_OK;
 }
@@ -458,7 +520,7 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     // (reference order: src/prover.rs:229, quotient_poly.rs:54-58,145 -- same values, earlier)
     zkp_poly_ref wp[4];
     for (unsigned j = 0; j < 4; j++) wp[j] = ref(pr->P7, j * S, n + 2);
-    SideJob wires8 = {pr, pr->P7->d, S, n + 3, pr->E7->d, 5, ZKP_OK};
+    SideJob wires8 = {pr, pr->P7->d, S, n + 3, pr->E7->d, 5, ZKP_OK};   // sharded: local cosets, stride nl
     TRY(commit_group_with(pr, wp, 4, comms, &wires8));
     static const char* const wl[4] = {"a_w", "b_w", "c_w", "d_w"};
     for (unsigned j = 0; j < 4; j++) tr.append_commitment(wl[j], comms + 12 * j);
@@ -474,7 +536,8 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     TRY(ntt_run(ctx, pr->Z->d, 0, n, pr->P7->d + 5 * S, 0, k, true, false, 1));
     TRY(zkp_poly_blind_dev(ctx, pr->P7, 5 * S, n, blinders + 32, 3));
     // z on the 8n coset needs no further challenge either: second stream, under the z commitment's reduction
-    SideJob z8 = {pr, pr->P7->d + 5 * S, 0, n + 3, pr->E7->d + 5 * n8, 1, ZKP_OK};
+    const size_t evn = pr->sharded ? pr->nl : n8;      // evaluations each coset-domain vector holds on this rank
+    SideJob z8 = {pr, pr->P7->d + 5 * S, 0, n + 3, pr->E7->d + 5 * evn, 1, ZKP_OK};
     TRY(commit_group_with(pr, &zp, 1, comms + 12 * 4, &z8));
     tr.append_commitment("z", comms + 12 * 4);
 
@@ -493,21 +556,37 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     const fr n_inv = fr_load(pr->n_inv);
     const fr l1c = F::mul(alpha2, n_inv);
     TRY(zkp_buf_fill(ctx, pr->P7, 6 * S, n, l1c.l));
-    TRY(ntt_run(ctx, pr->P7->d + 6 * S, 0, n, pr->E7->d + 6 * n8, 0, k8, false, true, 1));
+    if (pr->sharded) TRY(coset8_forward(ctx, pr->P7->d + 6 * S, n, pr->E7->d + 6 * evn, k, pr->u0, pr->nloc));
+    else TRY(ntt_run(ctx, pr->P7->d + 6 * S, 0, n, pr->E7->d + 6 * n8, 0, k8, false, true, 1));
     ZKP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pr->ev_side, 0));
     zkp_quotient_args qa;
     memset(&qa, 0, sizeof qa);
-    for (unsigned j = 0; j < 4; j++) { qa.wires[j] = ref(pr->E7, j * n8, n8); qa.sigma[j] = key.eval8[S1 + j]; }
-    qa.pi = ref(pr->E7, 4 * n8, n8);
-    qa.z = ref(pr->E7, 5 * n8, n8);
-    qa.l1 = ref(pr->E7, 6 * n8, n8);
+    for (unsigned j = 0; j < 4; j++) { qa.wires[j] = ref(pr->E7, j * evn, evn); qa.sigma[j] = key.eval8[S1 + j]; }
+    qa.pi = ref(pr->E7, 4 * evn, evn);
+    qa.z = ref(pr->E7, 5 * evn, evn);
+    qa.l1 = ref(pr->E7, 6 * evn, evn);
     for (unsigned j = 0; j < 11; j++) qa.sel[j] = key.eval8[j];
     qa.linear = key.linear8;
     for (unsigned j = 0; j < 7; j++) memcpy(qa.challenges[j], ch[j].l, 32);
     memcpy(qa.zh_inv, key.zh_inv, sizeof qa.zh_inv);
     qa.widget_mask = key.widget_mask;
-    TRY(zkp_quotient_dev(ctx, k8, &qa, pr->T, 0));
-    TRY(ntt_run(ctx, pr->T->d, 0, n8, pr->T->d, 0, k8, true, true, 1));  // coset_idft -> t coefficients
+    if (pr->sharded) {
+        // quotient on this rank's cosets; then the 8n-point inverse coset transform as: n-point inverses of the
+        // local cosets (scaled by h_u^-e / 8), ONE exchange (slab s of every coset to rank s), and the 8 x 8
+        // combination across cosets, which leaves this rank with slab `rank` of every n-chunk of t(X);
+        // all-gathered chunk by chunk into the natural coefficient order for rounds 4 / 5
+        qa.coset_log_n = k;
+        qa.coset_first = pr->u0;
+        TRY(zkp_quotient_range_dev(ctx, 0, &qa, 0, pr->nl, pr->TL, 0));
+        TRY(coset8_inverse_local(ctx, pr->TL->d, k, pr->u0, pr->nloc));
+        TRY(comm_exchange_slabs(pr->comm, pr->TL->d, pr->YA->d, n, pr->nloc, ctx->stream));
+        TRY(coset8_combine(ctx, pr->YA->d, pr->TS->d, pr->slab, k));
+        for (unsigned q = 0; q < 8; q++)
+            TRY(comm_allgather(pr->comm, pr->TS->d + q * pr->slab, pr->T->d + q * n, pr->slab * sizeof(fr_t), ctx->stream));
+    } else {
+        TRY(zkp_quotient_dev(ctx, k8, &qa, pr->T, 0));
+        TRY(ntt_run(ctx, pr->T->d, 0, n8, pr->T->d, 0, k8, true, true, 1));  // coset_idft -> t coefficients
+    }
     const zkp_poly_ref tq[4] = {ref(pr->T, 0, n), ref(pr->T, n, n), ref(pr->T, 2 * n, n), ref(pr->T, 3 * n, 5 * n)};
     TRY(commit_group(pr, tq, 4, comms + 12 * 5));
     static const char* const tl[4] = {"t_low", "t_mid", "t_high", "t_4"};
@@ -628,12 +707,16 @@ using namespace zkp;
 
 extern "C" {
 
+static int drv_prover_create(zkp_ctx* ctx, zkp_comm* comm, bool sharded, const zkp_srs* srs, const zkp_proving_key* key,
+                             zkp_prover** out);
+
 int zkp_prover_destroy(zkp_prover* pr) {
     if (!pr) return ZKP_OK;
     zkp_ctx* ctx = pr->ctx;
     if (ctx) cudaSetDevice(ctx->device);
     if (pr->side) cudaStreamSynchronize(pr->side->stream);
-    zkp_buf** bufs[] = {&pr->W, &pr->Z, &pr->P7, &pr->E7, &pr->T, &pr->R, &pr->AGG, &pr->WZ, &pr->SAGG, &pr->WZW};
+    zkp_buf** bufs[] = {&pr->W, &pr->Z, &pr->P7, &pr->E7, &pr->T, &pr->R, &pr->AGG, &pr->WZ, &pr->SAGG, &pr->WZW,
+                        &pr->TL, &pr->YA, &pr->TS};
     for (zkp_buf** b : bufs) if (*b) { zkp_buf_free(ctx, *b); *b = nullptr; }
     if (pr->wire_idx) cudaFree(pr->wire_idx);
     if (pr->pi_idx) cudaFree(pr->pi_idx);
@@ -646,8 +729,23 @@ int zkp_prover_destroy(zkp_prover* pr) {
 }
 
 int zkp_prover_create(zkp_ctx* ctx, const zkp_srs* srs, const zkp_proving_key* key, zkp_prover** out) {
+    return drv_prover_create(ctx, nullptr, false, srs, key, out);
+}
+
+int zkp_prover_create_sharded(zkp_ctx* ctx, zkp_comm* comm, const zkp_srs* srs, const zkp_proving_key* key,
+                              zkp_prover** out) {
+    if (comm && comm->ctx != ctx) return ZKP_ERR_INVALID;
+    return drv_prover_create(ctx, comm, true, srs, key, out);
+}
+
+static int drv_prover_create(zkp_ctx* ctx, zkp_comm* comm, bool sharded, const zkp_srs* srs, const zkp_proving_key* key,
+                             zkp_prover** out) {
     if (!ctx || !srs || !key || !out || key->k < 1 || key->k > 25 || !key->roots) return ZKP_ERR_INVALID;
-    const size_t n = (size_t)1 << key->k, n8 = 8 * n;
+    const size_t n = (size_t)1 << key->k;
+    const unsigned G = comm ? (unsigned)comm->nranks : 1u, rank = comm ? (unsigned)comm->rank : 0u;
+    if (sharded && n < 8) return ZKP_ERR_INVALID;
+    // evaluations each coset-domain vector of the key holds on this rank: all 8n, or the rank's 8 / G cosets
+    const size_t n8 = sharded ? 8 * n / G : 8 * n;
     for (int j = 0; j < 15; j++) {
         const zkp_poly_ref &p = key->poly[j], &e = key->eval8[j];
         if (!p.buf || p.off + p.len > p.buf->n || p.len < n) return ZKP_ERR_INVALID;
@@ -670,12 +768,19 @@ int zkp_prover_create(zkp_ctx* ctx, const zkp_srs* srs, const zkp_proving_key* k
     pr->n = n;
     pr->k = key->k;
     pr->S = n + 8;  // the seven polynomials bound for the 8n coset sit side by side
+    pr->comm = comm;
+    pr->sharded = sharded;
+    if (sharded) {
+        pr->nloc = 8 / G; pr->u0 = rank * pr->nloc;
+        pr->nl = (size_t)pr->nloc * n; pr->slab = n / G;
+    }
     drv::fr_store(pr->n_inv, drv::F::inv(drv::F::from_u64((uint64_t)n)));
     struct { zkp_buf** b; size_t len; } want[] = {
-        {&pr->W, 4 * n}, {&pr->Z, n}, {&pr->P7, 7 * pr->S}, {&pr->E7, 7 * n8}, {&pr->T, n8}, {&pr->R, n + 3},
-        {&pr->AGG, 5 * n}, {&pr->WZ, 5 * n}, {&pr->SAGG, n + 3}, {&pr->WZW, n + 3}};
+        {&pr->W, 4 * n}, {&pr->Z, n}, {&pr->P7, 7 * pr->S}, {&pr->E7, 7 * n8}, {&pr->T, 8 * n}, {&pr->R, n + 3},
+        {&pr->AGG, 5 * n}, {&pr->WZ, 5 * n}, {&pr->SAGG, n + 3}, {&pr->WZW, n + 3},
+        {&pr->TL, sharded ? n8 : 0}, {&pr->YA, sharded ? n8 : 0}, {&pr->TS, sharded ? n8 : 0}};
     for (auto& w : want)
-        if ((rc = zkp_buf_alloc(ctx, w.len, w.b))) { zkp_prover_destroy(pr); return rc; }
+        if (w.len && (rc = zkp_buf_alloc(ctx, w.len, w.b))) { zkp_prover_destroy(pr); return rc; }
     if ((rc = zkp_buf_zero(ctx, pr->P7, 0, 7 * pr->S)) || (rc = zkp_ctx_create(ctx->device, &pr->side))) {
         zkp_prover_destroy(pr);
         return rc;

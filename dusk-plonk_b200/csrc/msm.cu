@@ -34,6 +34,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "comm.cuh"
 #include "fq_inv32.cuh"
 #include "host_inv.h"
 
@@ -45,6 +46,7 @@ static constexpr unsigned GIANT_PARTS = 64;    // buckets with more partial sums
 struct MsmBatch {
     const fr_t* sc[MSM_MAX_BATCH];
     uint32_t len[MSM_MAX_BATCH];
+    uint32_t off[MSM_MAX_BATCH];   // SRS index of the polynomial's first scalar (a rank's range of a sharded commit)
 };
 
 struct MsmScratch {
@@ -142,7 +144,7 @@ __global__ void msm_digits_kernel(const __grid_constant__ MsmBatch batch, uint32
     const unsigned pb = blockIdx.y;
     if (i >= batch.len[pb]) return;
     const fr_t sm = msm_ld_fr(batch.sc[pb] + i);
-    if (i >= srs_n) {
+    if ((uint64_t)batch.off[pb] + i >= srs_n) {
         if (!sm.is_zero()) meta[4 * pb + 2] = 1u;
         return;
     }
@@ -279,7 +281,7 @@ __global__ void msm_scatter_kernel(const __grid_constant__ MsmBatch batch, const
         const uint32_t enc = digits[(size_t)w * n + i];
         if (enc == DIGIT_ZERO) continue;
         const uint32_t pos = atomicAdd(&cursor[enc & 0x7fffffffu], 1u);
-        sorted[pos] = (w * stride + i) | (enc & 0x80000000u);
+        sorted[pos] = (w * stride + batch.off[pb] + i) | (enc & 0x80000000u);
     }
 }
 
@@ -1213,8 +1215,56 @@ static inline fq inv(const fq& a) {
     hostinv::inv_mod<6>(a.l, P, x.l);
     return mul(x, R3);
 }
+
+
+static inline fq add(const fq& a, const fq& b) {
+    uint64_t t[6], c = 0;
+    for (int i = 0; i < 6; i++) { u128 s = (u128)a.l[i] + b.l[i] + c; t[i] = (uint64_t)s; c = (uint64_t)(s >> 64); }
+    if (c || geq_p(t)) {
+        uint64_t br = 0;
+        for (int i = 0; i < 6; i++) { u128 d = (u128)t[i] - P[i] - br; t[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
+    }
+    fq r; memcpy(r.l, t, 48); return r;
+}
+static inline fq sub(const fq& a, const fq& b) {
+    uint64_t t[6], br = 0;
+    for (int i = 0; i < 6; i++) { u128 d = (u128)a.l[i] - b.l[i] - br; t[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
+    if (br) {
+        uint64_t c = 0;
+        for (int i = 0; i < 6; i++) { u128 s2 = (u128)t[i] + P[i] + c; t[i] = (uint64_t)s2; c = (uint64_t)(s2 >> 64); }
+    }
+    fq r; memcpy(r.l, t, 48); return r;
+}
+static inline bool is_zero(const fq& a) { uint64_t x = 0; for (int i = 0; i < 6; i++) x |= a.l[i]; return x == 0; }
 }  // namespace hostfq
 
+// acc <- acc + b on the host (add-2008-s / dbl-2008-s-1, same case analysis as g1.cuh): the G partial sums
+// of a sharded commitment are combined here, G - 1 additions per commitment
+static void host_xyzz_add(g1_xyzz& acc, const g1_xyzz& b) {
+    using namespace hostfq;
+    if (b.is_inf()) return;
+    if (acc.is_inf()) { acc = b; return; }
+    fq ax, ay, azz, azzz, bx, by, bzz, bzzz;
+    memcpy(ax.l, acc.x.l, 48); memcpy(ay.l, acc.y.l, 48); memcpy(azz.l, acc.zz.l, 48); memcpy(azzz.l, acc.zzz.l, 48);
+    memcpy(bx.l, b.x.l, 48); memcpy(by.l, b.y.l, 48); memcpy(bzz.l, b.zz.l, 48); memcpy(bzzz.l, b.zzz.l, 48);
+    const fq U1 = mul(ax, bzz), S1 = mul(ay, bzzz);
+    const fq Pp = sub(mul(bx, azz), U1), R = sub(mul(by, azzz), S1);
+    fq X3, Y3, ZZ3, ZZZ3;
+    if (is_zero(Pp)) {
+        if (!is_zero(R) || is_zero(ay)) { acc = g1_xyzz::inf(); return; }
+        const fq U = add(ay, ay), V = mul(U, U), W = mul(U, V), S = mul(ax, V), X2 = mul(ax, ax);
+        const fq M = add(add(X2, X2), X2);
+        X3 = sub(mul(M, M), add(S, S));
+        Y3 = sub(mul(M, sub(S, X3)), mul(W, ay));
+        ZZ3 = mul(V, azz); ZZZ3 = mul(W, azzz);
+    } else {
+        const fq PP = mul(Pp, Pp), PPP = mul(Pp, PP), Q = mul(U1, PP);
+        X3 = sub(sub(mul(R, R), PPP), add(Q, Q));
+        Y3 = sub(mul(R, sub(Q, X3)), mul(S1, PPP));
+        ZZ3 = mul(mul(azz, bzz), PP); ZZZ3 = mul(mul(azzz, bzzz), PPP);
+    }
+    memcpy(acc.x.l, X3.l, 48); memcpy(acc.y.l, Y3.l, 48); memcpy(acc.zz.l, ZZ3.l, 48); memcpy(acc.zzz.l, ZZZ3.l, 48);
+}
 // x = X / ZZ, y = Y / ZZZ with 1/ZZ = (ZZ / ZZZ)^2.  The count <= MSM_MAX_BATCH points of one commit
 // group share a single Fermat inversion (Montgomery's trick: prefix products, one inverse, unwind).
 static void host_xyzz_to_affine_batch(const g1_xyzz* a, unsigned count, g1_affine* out) {
@@ -1371,14 +1421,47 @@ int msm_highest_nonzero(zkp_ctx* ctx, const fr_t* scalars_dev, size_t n, long lo
     return ZKP_OK;
 }
 
+// All-gather of every rank's slot (8 XYZZ partial sums + meta words), then the same host-side combination
+// on every rank: G - 1 additions per commitment, one shared inversion, OR of the overflow flags.
+static int msm_gather_partials(zkp_ctx* ctx, zkp_comm* cm, unsigned nb, g1_affine* out_host, int* overflow) {
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = comm_allgather(cm, cm->gsend, cm->grecv, cm->slot_bytes, st))) return rc;
+    ZKP_CUDA(ctx, cudaMemcpyAsync(cm->hrecv, cm->grecv, cm->slot_bytes * (size_t)cm->nranks, cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(ctx, cudaStreamSynchronize(st));
+    g1_xyzz acc[MSM_MAX_BATCH];
+    for (unsigned b = 0; b < nb; b++) { acc[b] = g1_xyzz::inf(); overflow[b] = 0; }
+    for (int r = 0; r < cm->nranks; r++) {
+        const uint8_t* slot = cm->hrecv + (size_t)r * cm->slot_bytes;
+        const g1_xyzz* ps = reinterpret_cast<const g1_xyzz*>(slot);
+        const uint32_t* pm = reinterpret_cast<const uint32_t*>(slot + 8 * sizeof(g1_xyzz));
+        for (unsigned b = 0; b < nb; b++) {
+            host_xyzz_add(acc[b], ps[b]);
+            if (pm[4 * b + 2]) overflow[b] = 1;
+        }
+    }
+    host_xyzz_to_affine_batch(acc, nb, out_host);
+    return ZKP_OK;
+}
+
 // nb <= MSM_MAX_BATCH commitments against the same SRS in one set of launches.  lens[b] may exceed
 // srs->n: coefficients beyond the SRS must be zero, otherwise overflow[b] = 1 (commit's Err) and
 // out_host[b] is unspecified.
 int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_dev, const size_t* lens, unsigned nb,
                   g1_affine* out_host, int* overflow) {
+    return msm_run_batch_ex(ctx, nullptr, srs, scalars_dev, lens, nullptr, nb, out_host, overflow);
+}
+
+// cm / offs: this rank's share of a commitment sharded over GPUs -- scalar i of polynomial b multiplies
+// SRS power offs[b] + i; the ranks' partial sums (still XYZZ) and overflow flags are all-gathered and every
+// rank finishes with the same affine commitments.  EVERY rank of the communicator must make the call, also
+// with an empty range.
+int msm_run_batch_ex(zkp_ctx* ctx, zkp_comm* cm, const zkp_srs* srs, const fr_t* const* scalars_dev, const size_t* lens,
+                     const size_t* offs, unsigned nb, g1_affine* out_host, int* overflow) {
     int rc;
     if ((rc = set_device(ctx))) return rc;
     if (nb == 0 || nb > MSM_MAX_BATCH) return ZKP_ERR_INVALID;
+    const bool shared = cm && cm->nranks > 1;
     const unsigned c = srs->c, W = srs->W;
     if ((size_t)W * srs->n >= (1ull << 31)) return ZKP_ERR_INVALID;
     MsmBatch batch;
@@ -1386,25 +1469,43 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     size_t maxlen = 0, n = 0;  // n = scalars that can produce entries (<= srs->n)
     for (unsigned b = 0; b < nb; b++) {
         if (lens[b] >= (1ull << 31)) return ZKP_ERR_INVALID;
+        const size_t off = offs ? offs[b] : 0;
+        if (off >= (1ull << 31)) return ZKP_ERR_INVALID;
         batch.sc[b] = scalars_dev[b];
         batch.len[b] = (uint32_t)lens[b];
+        batch.off[b] = (uint32_t)off;
         if (lens[b] > maxlen) maxlen = lens[b];
-        const size_t eff = lens[b] < srs->n ? lens[b] : srs->n;
+        const size_t room = off < srs->n ? srs->n - off : 0;
+        const size_t eff = lens[b] < room ? lens[b] : room;
         if (eff > n) n = eff;
         ctx->msm_points += eff;
     }
-    if (maxlen == 0 || n == 0) {
+    int local_ovf[MSM_MAX_BATCH] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool have_work = maxlen != 0 && n != 0;
+    if (!have_work) {
         // nothing can be non-zero below the SRS length; still honour the overflow check
         for (unsigned b = 0; b < nb; b++) {
             long long top = -1;
             if (lens[b] && (rc = msm_highest_nonzero(ctx, scalars_dev[b], lens[b], &top))) return rc;
-            overflow[b] = top >= (long long)srs->n;
+            local_ovf[b] = top >= 0;   // every scalar of this call lies beyond the SRS
+            overflow[b] = local_ovf[b];
             memset(&out_host[b], 0, sizeof(g1_affine));
         }
-        return ZKP_OK;
+        if (!shared) return ZKP_OK;
     }
     MsmScratch* s;
     if ((rc = msm_scratch(ctx, &s))) return rc;
+    if (!have_work) {
+        // an empty range still takes part in the gather: infinity partial sums + the flags found above
+        cudaStream_t st0 = ctx->stream;
+        uint32_t* hm0 = reinterpret_cast<uint32_t*>(ctx->pinned);
+        memset(hm0, 0, 4 * MSM_MAX_BATCH * sizeof(uint32_t));
+        for (unsigned b = 0; b < nb; b++) hm0[4 * b + 2] = (uint32_t)local_ovf[b];
+        ZKP_CUDA(ctx, cudaMemsetAsync(cm->gsend, 0, cm->slot_bytes, st0));
+        ZKP_CUDA(ctx, cudaMemcpyAsync(cm->gsend + 8 * sizeof(g1_xyzz), hm0, 4 * MSM_MAX_BATCH * sizeof(uint32_t),
+                                      cudaMemcpyHostToDevice, st0));
+        return msm_gather_partials(ctx, cm, nb, out_host, overflow);
+    }
 
     const uint32_t B = 1u << (c - 1);
     const size_t E = (size_t)W * n;  // upper bound on the entries of one polynomial
@@ -1568,6 +1669,12 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
         ZKP_LAUNCHED(ctx);
     }
     }
+    if (shared) {
+        ZKP_CUDA(ctx, cudaMemcpyAsync(cm->gsend, sums, nb * sizeof(g1_xyzz), cudaMemcpyDeviceToDevice, st));
+        ZKP_CUDA(ctx, cudaMemcpyAsync(cm->gsend + 8 * sizeof(g1_xyzz), s->meta, 4 * MSM_MAX_BATCH * sizeof(uint32_t),
+                                      cudaMemcpyDeviceToDevice, st));
+        return msm_gather_partials(ctx, cm, nb, out_host, overflow);
+    }
     // the single inversion of each conversion to affine runs on the host (one Fq Fermat chain
     // would occupy one GPU thread for ~0.6 ms)
     g1_xyzz* hs = reinterpret_cast<g1_xyzz*>(ctx->pinned);
@@ -1578,6 +1685,27 @@ int msm_run_batch(zkp_ctx* ctx, const zkp_srs* srs, const fr_t* const* scalars_d
     for (unsigned b = 0; b < nb; b++) overflow[b] = hm[4 * b + 2] != 0;
     host_xyzz_to_affine_batch(hs, nb, out_host);
     return ZKP_OK;
+}
+
+// A batch of commitments split over the ranks of `cm` by SRS ranges: the coefficients that can meet an SRS
+// power, [0, min(len, srs->n)), are dealt out evenly; the last rank also takes whatever lies beyond the SRS
+// (it must be zero: commit's degree check).  cm == nullptr or one rank: the plain batch.
+int msm_commit_sharded(zkp_ctx* ctx, zkp_comm* cm, const zkp_srs* srs, const fr_t* const* polys, const size_t* lens,
+                       unsigned nb, g1_affine* out_host, int* overflow) {
+    if (!cm || cm->nranks == 1) return msm_run_batch(ctx, srs, polys, lens, nb, out_host, overflow);
+    if (nb == 0 || nb > MSM_MAX_BATCH) return ZKP_ERR_INVALID;
+    const fr_t* ptrs[MSM_MAX_BATCH];
+    size_t ls[MSM_MAX_BATCH], offs[MSM_MAX_BATCH];
+    const size_t G = (size_t)cm->nranks, r = (size_t)cm->rank;
+    for (unsigned b = 0; b < nb; b++) {
+        const size_t eff = lens[b] < srs->n ? lens[b] : srs->n;
+        const size_t lo = eff * r / G;
+        const size_t hi = (r + 1 == G) ? lens[b] : eff * (r + 1) / G;
+        ptrs[b] = polys[b] + lo;
+        ls[b] = hi - lo;
+        offs[b] = lo;
+    }
+    return msm_run_batch_ex(ctx, cm, srs, ptrs, ls, offs, nb, out_host, overflow);
 }
 
 // msm_curve_addition over the first n powers (n <= srs->n checked by the caller).

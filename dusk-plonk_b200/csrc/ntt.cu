@@ -23,6 +23,7 @@
 //    transform, g^-i n^-1 on output of the inverse) is fused into the first / last pass
 //    through two-level power tables (g^i = lo[i & 1023] * hi[i >> 10]).
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -113,7 +114,120 @@ static int get_domain(zkp_ctx* ctx, unsigned k, NttDomain** out) {
     return ZKP_OK;
 }
 
+// ------------------------------------------------------------------ cosets of the n-domain inside the 8n domain
+// The 8n-point quotient domain g <w_8n> is the union of the eight cosets h_u H_n, h_u = g w_8n^u, and
+// point 8 m + u of the reference's ordering is h_u w_n^m.  A polynomial's values on one coset are an
+// n-point transform of its coefficients scaled by h_u^e (coefficients beyond n fold back with h_u^n), and
+// the 8n-point inverse is eight n-point inverses, a scaling by h_u^-e / 8 and an 8 x 8 combination across
+// cosets (csrc/create_proof.cu) -- which is what lets a GPU own whole cosets of the quotient.
+__device__ __forceinline__ fr_t ld_fr(const fr_t* p);
+__device__ __forceinline__ fr_t ldg_fr(const fr_t* p);
+__device__ __forceinline__ void st_fr(fr_t* p, const fr_t& v);
+
+struct Coset8Tab {
+    fr_t* f_lo = nullptr;   // h^e,           e < 2^min(k,10)
+    fr_t* f_hi = nullptr;   // h^(e << 10)
+    fr_t* b_lo = nullptr;   // h^-e / 8
+    fr_t* b_hi = nullptr;   // h^-(e << 10)
+    fr_t fold;              // h^n
+};
+
+static int get_coset8(zkp_ctx* ctx, unsigned k, unsigned u, Coset8Tab** out) {
+    const unsigned key = k * 8 + u;
+    auto it = ctx->coset8.find(key);
+    if (it != ctx->coset8.end()) { *out = it->second; return ZKP_OK; }
+    Coset8Tab* t = new Coset8Tab();
+    const fr_t h = fft_constant_host(k, 3) * pow_u64(fft_constant_host(k + 3, 0), u);
+    const fr_t hi = inverse(h);
+    t->fold = pow_u64(h, 1ull << k);
+    const size_t nlo = (size_t)1 << (k < LOG_LO ? k : LOG_LO);
+    int rc;
+    if ((rc = build_table(ctx, &t->f_lo, nlo, h, fr_t::one()))) return rc;
+    if ((rc = build_table(ctx, &t->b_lo, nlo, hi, inverse(from_u64<FrParams>(8))))) return rc;
+    if (k > LOG_LO) {
+        const size_t nhi = (size_t)1 << (k - LOG_LO);
+        if ((rc = build_table(ctx, &t->f_hi, nhi, pow_u64(h, 1ull << LOG_LO), fr_t::one()))) return rc;
+        if ((rc = build_table(ctx, &t->b_hi, nhi, pow_u64(hi, 1ull << LOG_LO), fr_t::one()))) return rc;
+    }
+    ctx->coset8[key] = t;
+    *out = t;
+    return ZKP_OK;
+}
+
+struct Coset8Args {
+    const fr_t* lo[8];
+    const fr_t* hi[8];
+    fr_t fold[8];
+    const fr_t* in;
+    fr_t* out;
+    size_t in_stride, len_in, n;
+    unsigned k;
+    int use_fold;
+};
+
+// out[j][e] = (in_j[e] + fold_j in_j[n + e]) * tab_j(e), e < n; in_j = in + j in_stride (stride 0: one input)
+__global__ void __launch_bounds__(256) coset8_scale_kernel(const __grid_constant__ Coset8Args a) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned j = blockIdx.y;
+    if (e >= a.n) return;
+    const fr_t* in = a.in + (size_t)j * a.in_stride;
+    fr_t v = e < a.len_in ? ld_fr(in + e) : fr_t::zero();
+    if (a.use_fold && a.n + e < a.len_in) v = v + a.fold[j] * ld_fr(in + a.n + e);
+    fr_t f = ldg_fr(a.lo[j] + (e & ((1u << LOG_LO) - 1)));
+    if (a.k > LOG_LO) f = f * ldg_fr(a.hi[j] + (e >> LOG_LO));
+    st_fr(a.out + (size_t)j * a.n + e, v * f);
+}
+
+// values of one polynomial (len_in <= 2n coefficients) on the cosets first .. first + count - 1: out[j][m]
+int coset8_forward(zkp_ctx* ctx, const fr_t* in, size_t len_in, fr_t* out, unsigned k, unsigned first, unsigned count) {
+    const size_t n = (size_t)1 << k;
+    if (k > 25 || count == 0 || first + count > 8 || len_in > 2 * n) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    Coset8Args a;
+    memset(&a, 0, sizeof a);
+    for (unsigned j = 0; j < count; j++) {
+        Coset8Tab* t;
+        if ((rc = get_coset8(ctx, k, first + j, &t))) return rc;
+        a.lo[j] = t->f_lo; a.hi[j] = t->f_hi; a.fold[j] = t->fold;
+    }
+    a.in = in; a.out = out; a.in_stride = 0; a.len_in = len_in; a.n = n; a.k = k; a.use_fold = 1;
+    {
+        ProfScope prof(ctx, "ntt");
+        coset8_scale_kernel<<<dim3((unsigned)((n + 255) / 256), count), 256, 0, ctx->stream>>>(a);
+        ZKP_LAUNCHED(ctx);
+    }
+    return ntt_run(ctx, out, n, n, out, n, k, false, false, count);
+}
+
+// data[j][.] (values on coset first + j) -> inverse transform of each coset scaled by h_u^-e / 8, in place:
+// the per-coset term of the 8n-point inverse, ready for the cross-coset combination
+int coset8_inverse_local(zkp_ctx* ctx, fr_t* data, unsigned k, unsigned first, unsigned count) {
+    const size_t n = (size_t)1 << k;
+    if (k > 25 || count == 0 || first + count > 8) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = ntt_run(ctx, data, n, n, data, n, k, true, false, count))) return rc;
+    Coset8Args a;
+    memset(&a, 0, sizeof a);
+    for (unsigned j = 0; j < count; j++) {
+        Coset8Tab* t;
+        if ((rc = get_coset8(ctx, k, first + j, &t))) return rc;
+        a.lo[j] = t->b_lo; a.hi[j] = t->b_hi;
+    }
+    a.in = data; a.out = data; a.in_stride = n; a.len_in = n; a.n = n; a.k = k; a.use_fold = 0;
+    ProfScope prof(ctx, "ntt");
+    coset8_scale_kernel<<<dim3((unsigned)((n + 255) / 256), count), 256, 0, ctx->stream>>>(a);
+    ZKP_LAUNCHED(ctx);
+    return ZKP_OK;
+}
+
 void ntt_free_domains(zkp_ctx* ctx) {
+    for (auto& kv : ctx->coset8) {
+        Coset8Tab* t = kv.second;
+        cudaFree(t->f_lo); cudaFree(t->f_hi); cudaFree(t->b_lo); cudaFree(t->b_hi);
+        delete t;
+    }
+    ctx->coset8.clear();
     for (auto& kv : ctx->domains) {
         NttDomain* d = kv.second;
         cudaFree(d->tw); cudaFree(d->g_lo); cudaFree(d->g_hi); cudaFree(d->gi_lo); cudaFree(d->gi_hi);

@@ -243,6 +243,8 @@ struct QuotArgs {
     size_t n8;
     size_t first, count;  // evaluate indices [first, first + count) (a rank's slice when sharded)
     int sliced;           // w / z / pi / l1 hold only [first, first + count + 8): index them relative to first
+    unsigned coset_k;     // non-zero: coset layout (whole cosets of n = 2^coset_k points, see zkp_quotient_args)
+    unsigned coset_first;
     fr_t* out;
 };
 
@@ -255,9 +257,11 @@ __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ Q
     if (t_ >= q.count) return;
     const size_t i = q.first + t_;
     // "next gate" on the 8n coset (quotient_poly.rs:60-66).  wi / win index the witness-side vectors
-    // (wires, z, PI, L1): absolute, or relative to the slice (whose 8-element halo holds the wrap-around)
+    // (wires, z, PI, L1): absolute, or relative to the slice (whose 8-element halo holds the wrap-around);
+    // in the coset layout the next gate is the next point of the same coset
+    const size_t cmask = ((size_t)1 << q.coset_k) - 1;
     const size_t wi = q.sliced ? t_ : i;
-    const size_t win = q.sliced ? t_ + 8 : (i + 8) & (q.n8 - 1);
+    const size_t win = q.coset_k ? ((i & ~cmask) | ((i + 1) & cmask)) : q.sliced ? t_ + 8 : (i + 8) & (q.n8 - 1);
     const fr_t one = fr_t::one(), two = dbl(one), three = two + one;
     const fr_t a = pld(q.w[0] + wi), b = pld(q.w[1] + wi), c = pld(q.w[2] + wi), d = pld(q.w[3] + wi);
     const fr_t qc = pld(q.sel[4] + i);
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ Q
                     ((cg + q.beta * pld(q.sigma[2] + i)) * (dg + q.beta * pld(q.sigma[3] + i))) * zn;
         t = t + (ident - copy) * q.alpha + (z - one) * pld(q.l1 + wi);
     }
-    pst(q.out + i, t * q.zh_inv[i & 7]);
+    pst(q.out + i, t * q.zh_inv[q.coset_k ? ((q.coset_first + (i >> q.coset_k)) & 7) : (i & 7)]);
 }
 
 // ------------------------------------------------------------------ batched evaluation
@@ -642,8 +646,16 @@ int zkp_quotient_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* q, zkp_
 
 int zkp_quotient_range_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* q, size_t first, size_t count,
                            zkp_buf* out, size_t out_off) {
-    if (!ctx || !q || !out || k8 < 3 || k8 > 28) return ZKP_ERR_INVALID;
-    const size_t n8 = (size_t)1 << k8;
+    if (!ctx || !q || !out) return ZKP_ERR_INVALID;
+    const bool cosets = q->coset_log_n != 0;
+    if (cosets) {   // every vector holds `count` local points: whole cosets of n points
+        if (q->coset_log_n > 25 || first != 0 || q->sliced || (count & (((size_t)1 << q->coset_log_n) - 1)) ||
+            q->coset_first + (count >> q->coset_log_n) > 8)
+            return ZKP_ERR_INVALID;
+    } else if (k8 < 3 || k8 > 28) {
+        return ZKP_ERR_INVALID;
+    }
+    const size_t n8 = cosets ? count : (size_t)1 << k8;
     if (out_off + n8 > out->n || first + count > n8) return ZKP_ERR_INVALID;
     QuotArgs a;
     auto ptr = [&](const zkp_poly_ref& r, const fr_t** p) {
@@ -685,6 +697,8 @@ int zkp_quotient_range_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* q
     a.first = first;
     a.count = count;
     a.sliced = sliced ? 1 : 0;
+    a.coset_k = q->coset_log_n;
+    a.coset_first = q->coset_first;
     a.out = out->d + out_off;
     if (count == 0) return ZKP_OK;
     ProfScope prof(ctx, "quotient");

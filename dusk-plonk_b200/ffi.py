@@ -84,7 +84,8 @@ class QuotientArgs(ctypes.Structure):
     _fields_ = [("wires", PolyRef * 4), ("z", PolyRef), ("pi", PolyRef), ("l1", PolyRef),
                 ("sel", PolyRef * 11), ("sigma", PolyRef * 4), ("linear", PolyRef),
                 ("challenges", (ctypes.c_uint64 * 4) * 7), ("zh_inv", (ctypes.c_uint64 * 4) * 8),
-                ("widget_mask", ctypes.c_uint32), ("sliced", ctypes.c_uint32)]
+                ("widget_mask", ctypes.c_uint32), ("coset_log_n", ctypes.c_uint32), ("coset_first", ctypes.c_uint32),
+                ("sliced", ctypes.c_uint32)]
 
 
 SIGNATURES.update({
@@ -122,6 +123,16 @@ SIGNATURES.update({
     "zkp_linearization_scalars": (_int, [_uint, _vp, _vp, _vp]),
     "zkp_g1_compress": (_int, [_vp, _vp]),
     "zkp_fr_from_wide": (_int, [_vp, _vp]),
+    # one job over several GPUs
+    "zkp_comm_unique_id": (_int, [_vp]),
+    "zkp_comm_create": (_int, [_vp, _vp, _int, _int, ctypes.POINTER(_vp)]),
+    "zkp_comm_destroy": (_int, [_vp]),
+    "zkp_comm_rank": (_int, [_vp]),
+    "zkp_comm_size": (_int, [_vp]),
+    "zkp_comm_stats": (_int, [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    "zkp_commit_batch_sharded_dev": (_int, [_vp, _vp, _vp, ctypes.POINTER(PolyRef), _uint, _vp, ctypes.POINTER(_int)]),
+    "zkp_coset8_ntt_dev": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _uint, _uint, _uint]),
+    "zkp_prover_create_sharded": (_int, [_vp, _vp, _vp, ctypes.POINTER(ProvingKeyDesc), ctypes.POINTER(_vp)]),
 })
 
 _lib = None
@@ -331,6 +342,21 @@ class Context:
         self.check(self.lib.zkp_commit_batch_dev(self.h, srs.h, arr, len(refs), _ptr(out), st))
         return out, list(st)
 
+    def commit_batch_sharded_dev(self, comm, srs, refs):
+        """``commit_batch_dev`` over every rank of ``comm`` (collective): SRS ranges + partial-sum gather."""
+        arr = (PolyRef * len(refs))(*refs)
+        out = np.zeros((len(refs), 12), dtype=np.uint64)
+        st = (_int * len(refs))()
+        self.check(self.lib.zkp_commit_batch_sharded_dev(self.h, comm.h if comm is not None else None, srs.h, arr,
+                                                         len(refs), _ptr(out), st))
+        return out, list(st)
+
+    def coset8_ntt(self, src, src_off, len_in, dst, dst_off, k, first, count):
+        """dst[(u - first) n + m] = p(g w_8n^u w_n^m): the polynomial's values on whole cosets of the 8n domain."""
+        sb, so = _base(src)
+        db, do = _base(dst)
+        self.check(self.lib.zkp_coset8_ntt_dev(self.h, sb.h, so + src_off, len_in, db.h, do + dst_off, k, first, count))
+
     def set_msm_window(self, c):
         self.check(self.lib.zkp_msm_set_window(self.h, c))
 
@@ -531,11 +557,15 @@ class Srs:
 class NativeProver:
     """``zkp_prover``: the round driver of ``create_proof`` in native code (csrc/create_proof.cu)."""
 
-    def __init__(self, ctx, srs, desc, keepalive):
+    def __init__(self, ctx, srs, desc, keepalive, comm=None, sharded=False):
         self.ctx = ctx
-        self._keep = (srs, desc, keepalive)   # the key's buffers and the SRS must outlive the handle
+        self._keep = (srs, desc, keepalive, comm)   # the key's buffers, the SRS and the communicator must outlive the handle
         h = _vp()
-        ctx.check(ctx.lib.zkp_prover_create(ctx.h, srs.h, ctypes.byref(desc), ctypes.byref(h)))
+        if sharded:
+            ctx.check(ctx.lib.zkp_prover_create_sharded(ctx.h, comm.h if comm is not None else None, srs.h,
+                                                        ctypes.byref(desc), ctypes.byref(h)))
+        else:
+            ctx.check(ctx.lib.zkp_prover_create(ctx.h, srs.h, ctypes.byref(desc), ctypes.byref(h)))
         self.h = h
         self._comms = np.zeros((11, 12), dtype=np.uint64)
         self._evals = np.zeros((16, 4), dtype=np.uint64)
@@ -585,3 +615,46 @@ class NativeProver:
             self.close()
         except Exception:
             pass
+
+
+class NativeComm:
+    """``zkp_comm``: this rank's link to the GPUs that share one job (NCCL inside libzkp_b200.so).
+    ``world == 1`` needs no NCCL: the sharded code path on one GPU."""
+
+    def __init__(self, ctx, rank=0, world=1, unique_id=None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        h = _vp()
+        if world > 1:
+            assert unique_id is not None and len(unique_id) == 256
+            uid = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+            ctx.check(ctx.lib.zkp_comm_create(ctx.h, _ptr(uid), rank, world, ctypes.byref(h)))
+        else:
+            ctx.check(ctx.lib.zkp_comm_create(ctx.h, None, 0, 1, ctypes.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def unique_id():
+        out = np.zeros(256, dtype=np.uint8)
+        rc = load_library().zkp_comm_unique_id(_ptr(out))
+        if rc:
+            raise ZkpError(rc, "NCCL unavailable")
+        return bytes(out)
+
+    @classmethod
+    def from_torch_distributed(cls, ctx):
+        """One rank per process under torchrun: rank 0 makes the id, torch.distributed carries its 256 bytes."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(ctx, rank, world, box[0])
+
+    def stats(self):
+        c, b = ctypes.c_uint64(), ctypes.c_uint64()
+        self.ctx.check(self.ctx.lib.zkp_comm_stats(self.h, ctypes.byref(c), ctypes.byref(b)))
+        return int(c.value), int(b.value)
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.zkp_comm_destroy(self.h)
+        self.h = None

@@ -99,14 +99,26 @@ class PlonkKey:
             pk.poly[nm] = buf
         for nm, c in zip(SIGMAS, keypair.commit_batch([pk.poly[nm] for nm in SIGMAS])):   # `?` in the reference
             vk[nm] = c.affine()
-        for nm, p in pk.poly.items():
-            e8 = ctx.alloc(n8)
-            ctx.ntt_dev(p, n, e8, k + 3, False, True)
-            pk.eval8[nm] = e8
+        # 8n-coset evaluations (src/key.rs:226-245).  A rank of a sharded proof keeps only its cosets
+        # (g w_8n^u) H_n, u in [u0, u0 + nloc): n-point transforms, 8 / G of the memory
+        comm = getattr(keypair, "native_comm", None)
         lin = ctx.upload(fr_to_mont([0, 1]))
-        e8 = ctx.alloc(n8)
-        ctx.ntt_dev(lin, 2, e8, k + 3, False, True)
-        pk.eval8["linear"] = e8
+        if comm is not None:
+            nloc = 8 // comm.world
+            u0 = comm.rank * nloc
+            pk.cosets = (u0, nloc)
+            for nm, p in list(pk.poly.items()) + [("linear", lin)]:
+                e8 = ctx.alloc(nloc * n)
+                ctx.coset8_ntt(p, 0, p.n, e8, 0, k, u0, nloc)
+                pk.eval8[nm] = e8
+        else:
+            for nm, p in pk.poly.items():
+                e8 = ctx.alloc(n8)
+                ctx.ntt_dev(p, n, e8, k + 3, False, True)
+                pk.eval8[nm] = e8
+            e8 = ctx.alloc(n8)
+            ctx.ntt_dev(lin, 2, e8, k + 3, False, True)
+            pk.eval8["linear"] = e8
         # Z_H(g w8^i) = g^n (w8^n)^i - 1: eight distinct values (src/key.rs:291)
         g = 7
         w8 = fr_from_mont([_const(ctx, k + 3, 0)])[0]

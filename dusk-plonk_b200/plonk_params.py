@@ -70,3 +70,39 @@ class PlonkParams:
             return self.commit(poly)
         except Error:
             return Commitment(np.zeros(12, dtype=np.uint64))
+
+
+class ShardedNativeParams(PlonkParams):
+    """``PlonkParams`` of one rank of a job shared by several GPUs (BASELINE config 5), all inside
+    libzkp_b200.so: every commitment is split by SRS ranges over the ranks of ``comm`` (``zkp_comm``, NCCL) and
+    the partial sums are gathered and added on every rank, so all ranks see the same commitment and derive
+    the same transcript.  The SRS (and its window table) is complete on every rank: 2 GiB at 2^20 gates.
+    ``PlonkKey.compile`` / ``Prover.create_proof`` see an ordinary commit key; a key compiled from it owns
+    only this rank's cosets of the 8n domain and proves through ``zkp_prover_create_sharded``."""
+
+    def __init__(self, ctx, srs, comm):
+        super().__init__(ctx, srs)
+        self.native_comm = comm
+
+    @classmethod
+    def setup_synthetic(cls, ctx, comm, k, tau_mont):
+        return cls(ctx, ctx.srs_generate(tau_mont, (1 << k) + 7), comm)
+
+    def trim(self, n):
+        keep = min(self.srs.n, n + 7)
+        if keep == self.srs.n:
+            return self
+        return ShardedNativeParams(self.ctx, self.ctx.srs_load(self.srs.download(0, keep)), self.native_comm)
+
+    def commit(self, poly):
+        return self.commit_batch([poly])[0]
+
+    def commit_batch(self, polys):
+        refs = []
+        for p in polys:
+            b, off, n = (p.buf, p.off, p.n) if isinstance(p, BufferView) else (p, 0, p.n)
+            refs.append(self.ctx.ref(b, off, n))
+        out, status = self.ctx.commit_batch_sharded_dev(self.native_comm, self.srs, refs)
+        if any(st == ZKP_ERR_DEGREE for st in status):
+            raise Error("polynomial degree exceeds the SRS")
+        return [Commitment(out[i]) for i in range(len(polys))]

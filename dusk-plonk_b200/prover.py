@@ -11,7 +11,7 @@ from .field import R_MOD, K1, K2, K3, fr_from_mont, fr_to_mont, fr_to_mont1, g1_
 from .ffi import QuotientArgs, BufferView as _View
 from host_mirror.composer import SELECTORS, SynthesizedCircuit, Plonk
 from .widgets import linearization_scalars
-from .plonk_params import PlonkParams
+from .plonk_params import PlonkParams, ShardedNativeParams
 
 _r = R_MOD
 EVAL_NAMES = ("a_eval", "b_eval", "c_eval", "d_eval", "a_next_eval", "b_next_eval", "d_next_eval",
@@ -173,7 +173,9 @@ class Prover:
             pk, ref = self.prover_key, self.ctx.ref
             d = ProvingKeyDesc()
             d.k = pk.k
-            n, n8 = pk.n, 8 * pk.n
+            comm = getattr(self.keypair, "native_comm", None)
+            n = pk.n
+            n8 = 8 * n if comm is None else pk.cosets[1] * n     # a sharded key holds this rank's cosets only
             for i, nm in enumerate(SELECTORS + SIGMAS):
                 d.poly[i] = ref(pk.poly[nm], 0, n)
                 d.eval8[i] = ref(pk.eval8[nm], 0, n8)
@@ -188,7 +190,7 @@ class Prover:
             for l in range(4):
                 d.generator[l] = int(gen[l])
             d.widget_mask = pk.widget_mask
-            self._native = NativeProver(self.ctx, self.keypair.srs, d, (pk, self.keypair))
+            self._native = NativeProver(self.ctx, self.keypair.srs, d, (pk, self.keypair), comm, comm is not None)
         return self._native
 
     def _create_proof_native(self, tr, wa, bl):
@@ -227,7 +229,9 @@ class Prover:
         T = trace if trace is not None else None
         if isinstance(circuit, Plonk):
             circuit = SynthesizedCircuit.from_composer(circuit)
-        use_native = self.native and trace is None and type(self.keypair) is PlonkParams
+        use_native = self.native and trace is None and type(self.keypair) in (PlonkParams, ShardedNativeParams)
+        if type(self.keypair) is ShardedNativeParams and not use_native:
+            raise ValueError("a key sharded over GPUs proves through the native driver only")
         if isinstance(circuit, (WitnessAssignment, WitnessValues)):
             wa = circuit
         elif use_native:

@@ -7,7 +7,7 @@ __path__.insert(0, _real)
 
 from .ffi import *  # noqa: E402,F401,F403
 from .poly_commit import Fft, Coefficients, PointsValue, Commitment  # noqa: E402,F401
-from .plonk_params import PlonkParams, Error  # noqa: E402,F401
+from .plonk_params import PlonkParams, ShardedNativeParams, Error  # noqa: E402,F401
 from host_mirror.composer import Plonk, Constraint, SynthesizedCircuit  # noqa: E402,F401
 from .key import PlonkKey  # noqa: E402,F401
 from .prover import Prover, Proof, WitnessAssignment, WitnessValues  # noqa: E402,F401

@@ -45,6 +45,7 @@ extern "C" {
 typedef struct zkp_ctx zkp_ctx;
 typedef struct zkp_srs zkp_srs;   /* device-resident [tau^i]_1 powers (PlonkParams after trim)  */
 typedef struct zkp_buf zkp_buf;   /* device-resident vector of Fr                               */
+typedef struct zkp_comm zkp_comm; /* this rank's link to the GPUs sharing one job (NCCL)         */
 
 /* ---- context --------------------------------------------------------------------- */
 int zkp_ctx_create(int device, zkp_ctx** out);
@@ -199,6 +200,13 @@ typedef struct zkp_quotient_args {
     uint64_t zh_inv[8][4];        /* 1 / Z_H on the coset: period 8 */
     uint32_t widget_mask;         /* bit0 range, 1 logic, 2 fixed-base, 3 var-base: clear = selector
                                      polynomial identically zero, widget skipped (contributes 0) */
+    uint32_t coset_log_n;         /* non-zero (= log2 n): COSET layout.  Every vector holds the evaluations on a run
+                                     of whole cosets (g w_8n^u) H_n of the 8n domain, u = coset_first .. , n each:
+                                     element u_local * n + m is the point g w_8n^u w_n^m.  "Next gate" is m + 1 inside
+                                     the coset and 1 / Z_H is constant on it, so a rank that owns cosets evaluates
+                                     its part of the quotient with no data from any other rank; k8 is ignored and
+                                     zkp_quotient_range_dev's count is the number of local points */
+    uint32_t coset_first;
     uint32_t sliced;              /* zkp_quotient_range_dev only: wires, z, pi, l1 hold just the evaluations
                                      [first, first + count + 8) (indices mod 8n: the 8-element halo is the
                                      "next gate" of the last points) -- what a rank receives when the coset
@@ -262,6 +270,41 @@ int zkp_prover_prove(zkp_prover* prover, const uint8_t transcript[203], const ui
                      const zkp_buf* wires_dev, const uint64_t* pi_host, const zkp_buf* pi_dev,
                      const uint64_t blinders[44], uint64_t commitments[132], uint64_t evaluations[64],
                      uint8_t proof_bytes[1040], uint8_t transcript_out[203]);
+
+/* ---- one job over several GPUs (BASELINE north_star) ------------------------------------
+ * One rank (process or thread) per GPU, G in {1, 2, 4, 8}.  What is split:
+ *   - every KZG commitment by SRS ranges: rank r multiplies coefficients [r L / G, (r + 1) L / G) with the
+ *     matching powers; the G partial sums are all-gathered (192 bytes each) and added on every rank;
+ *   - the 8n-point quotient domain by COSETS: rank r owns the 8 / G cosets (g w_8n^u) H_n, u in
+ *     [8 r / G, 8 (r + 1) / G).  Each is an n-point coset transform of replicated coefficients (no exchange
+ *     going in), the quotient is point-wise within a coset, and the inverse transform needs ONE exchange: slab s
+ *     of every locally inverted coset goes to rank s, which combines the eight and ends up holding
+ *     coefficients [s n / G, (s + 1) n / G) of every n-chunk of t(X) -- exactly the range of t_low / t_mid /
+ *     t_high / t_4 its SRS range commits.
+ * rank 0 makes the id, the host ships its 256 bytes to the other ranks, all ranks call zkp_comm_create
+ * (collective).  nranks == 1 needs no id and no NCCL: the same code path on one GPU. */
+int zkp_comm_unique_id(uint8_t out[256]);
+int zkp_comm_create(zkp_ctx* ctx, const uint8_t id[256], int rank, int nranks, zkp_comm** out);
+int zkp_comm_destroy(zkp_comm* comm);
+int zkp_comm_rank(const zkp_comm* comm);
+int zkp_comm_size(const zkp_comm* comm);
+int zkp_comm_stats(const zkp_comm* comm, uint64_t* collectives, uint64_t* bytes_sent);
+/* zkp_commit_batch_dev over all ranks of `comm` (polynomials replicated, SRS complete on every rank):
+ * collective; every rank returns the same commitments / status. */
+int zkp_commit_batch_sharded_dev(zkp_ctx* ctx, zkp_comm* comm, const zkp_srs* srs, const zkp_poly_ref* polys,
+                                 unsigned count, uint64_t* out_xy /* count x 12 */, int* status /* count */);
+/* Fft::coset_dft restricted to whole cosets of the n-domain inside the 8n domain:
+ * out[(u - first) n + m] = p(g w_8n^u w_n^m) for u = first .. first + count - 1, m < n = 2^k.
+ * len_in <= 2n coefficients (a blinded polynomial has n + 3).  Concatenated over u = 0 .. 7 and read as
+ * out[u][m] -> index 8 m + u this is the reference's 8n-point coset_dft. */
+int zkp_coset8_ntt_dev(zkp_ctx* ctx, const zkp_buf* in, size_t in_off, size_t len_in, zkp_buf* out, size_t out_off,
+                       unsigned k, unsigned first, unsigned count);
+/* zkp_prover_create for rank zkp_comm_rank(comm) of a sharded proof: key->eval8[i] / linear8 hold this
+ * rank's cosets only (8 n / G evaluations each, zkp_coset8_ntt_dev layout), everything else is as for one
+ * GPU and replicated; the SRS is complete on every rank.  zkp_prover_prove / _prove_witness are then
+ * collective: every rank calls them with the same inputs and returns the same proof. */
+int zkp_prover_create_sharded(zkp_ctx* ctx, zkp_comm* comm, const zkp_srs* srs, const zkp_proving_key* key,
+                              zkp_prover** out);
 
 /* The same with the witness gather on the device (src/prover.rs:109-119, src/lib.rs:206-219): the
  * circuit's wiring is set once -- wire_idx[j * m + i] = witness index of wire j (a, b, o, d) at gate

@@ -62,6 +62,36 @@ def main():
         assert getattr(gproof, c) == getattr(oproof, c), c
     assert gproof.evaluations == oproof.evaluations
     assert oplonk.verify(ovk, circ.n, gproof, circ.pi_indexes, gpi, otr, oplonk.trapdoor_kzg_check(tau))
+    # 3. the native multi-GPU driver (zkp_comm: NCCL inside libzkp_b200.so, no Python between the rounds): the README
+    #    circuit against the oracle proof above, then the synthetic 2^16-gate circuit bench.py times against the
+    #    committed oracle digest -- byte-identical on every rank
+    import hashlib
+    import json
+    from host_mirror.composer import synthetic_circuit
+    from dusk_plonk_b200.plonk_params import ShardedNativeParams
+    if world in (1, 2, 4, 8):
+        ncomm = z.NativeComm.from_torch_distributed(ctx) if world > 1 else z.NativeComm(ctx)
+        np_ = ShardedNativeParams.setup_synthetic(ctx, ncomm, k + 1, taum)
+        nprover = z.PlonkKey.compile_with_circuit(np_, b"demo", circ)
+        nproof, npi = nprover.create_proof(bl, circ)
+        assert nproof.wire_bytes == oproof.to_bytes(), "native sharded proof differs from the oracle"
+        nprover.close()
+        circ16 = synthetic_circuit(16)
+        rng16 = SplitMix64(8349)
+        tau16 = fr_to_mont_limbs([rng16.fr()])[0]
+        bl16 = [rng16.fr() for _ in range(11)]
+        p16 = z.PlonkKey.compile(ShardedNativeParams.setup_synthetic(ctx, ncomm, 16, tau16), circ16)
+        proof16, _ = p16.create_proof(bl16, circ16)
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", "synthetic_proofs.json")))
+        dg = hashlib.sha256(proof16.wire_bytes).hexdigest()
+        assert dg == gold["16"]["sha256"], "2^16 sharded proof differs from the committed oracle digest"
+        digs = [None] * world
+        dist.all_gather_object(digs, dg)
+        assert all(d == dg for d in digs)
+        colls, sent = ncomm.stats()
+        assert world == 1 or (colls > 0 and sent > 0)
+        p16.close()
+        ncomm.close()
     dist.barrier()
     if rank == 0:
         print("MULTIGPU OK world=%d" % world, flush=True)
