@@ -383,6 +383,32 @@ int zkp_srs_generate_range(zkp_ctx* ctx, const uint64_t tau[4], size_t first, si
     return ZKP_OK;
 }
 
+/* PlonkParams::trim (src/key.rs:82) without leaving the device: the first `keep` powers of an SRS as a new one.
+ * When the window width stays the same the table rows are sliced (device-to-device copies), else rebuilt. */
+int zkp_srs_trim(zkp_ctx* ctx, const zkp_srs* srs, size_t keep, zkp_srs** out) {
+    if (!ctx || !srs || !out || keep > srs->n) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    zkp_srs* s = nullptr;
+    if ((rc = srs_alloc(ctx, keep, &s))) return rc;
+    cudaError_t e = cudaMemcpyAsync(s->d, srs->d, keep * sizeof(g1_affine), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess && keep && s->c == srs->c && srs->tab) {
+        e = cudaMalloc(&s->tab, (size_t)s->W * keep * sizeof(g1_tab));
+        for (unsigned w = 0; e == cudaSuccess && w < s->W; w++)
+            e = cudaMemcpyAsync(s->tab + (size_t)w * keep, srs->tab + (size_t)w * srs->n, keep * sizeof(g1_tab),
+                                cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    } else if (e == cudaSuccess) {
+        rc = srs_build_table(ctx, s);
+    }
+    if (e != cudaSuccess || rc) {
+        cudaFree(s->d); cudaFree(s->tab); delete s;
+        return rc ? rc : cuda_fail(ctx, e, "srs trim", __FILE__, __LINE__);
+    }
+    *out = s;
+    return ZKP_OK;
+}
+
 int zkp_srs_download(zkp_ctx* ctx, const zkp_srs* srs, size_t off, uint64_t* xy, size_t n) {
     if (!ctx || !srs || (!xy && n) || off + n > srs->n) return ZKP_ERR_INVALID;
     int rc;

@@ -2,6 +2,7 @@
 // error plumbing and the launch counter bench.py reports as gpu_launches.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges are no-ops unless a profiler injects itself
 #include <stdint.h>
 #include <stdio.h>
 #include <map>
@@ -97,6 +98,7 @@ inline int cuda_fail(zkp_ctx* ctx, cudaError_t e, const char* what, const char* 
 struct ProfScope {
     zkp_ctx* ctx; int idx = -1;
     ProfScope(zkp_ctx* c, const char* name) : ctx(c) {
+        nvtxRangePushA(name);   // every kernel group is also an NVTX range (nsys / ncu --nvtx)
         if (!c->prof_on) return;
         cudaEvent_t a, b;
         auto get = [&](cudaEvent_t* e) {
@@ -108,7 +110,16 @@ struct ProfScope {
         c->prof_spans.push_back({name, a, b});
         idx = (int)c->prof_spans.size() - 1;
     }
-    ~ProfScope() { if (idx >= 0) cudaEventRecord(ctx->prof_spans[idx].b, ctx->stream); }
+    ~ProfScope() {
+        if (idx >= 0) cudaEventRecord(ctx->prof_spans[idx].b, ctx->stream);
+        nvtxRangePop();
+    }
+};
+
+// NVTX range over a scope (the prover's rounds)
+struct NvtxScope {
+    explicit NvtxScope(const char* name) { nvtxRangePushA(name); }
+    ~NvtxScope() { nvtxRangePop(); }
 };
 
 inline int set_device(zkp_ctx* ctx) {

@@ -501,6 +501,9 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     tr.load(transcript_in);
 
     // round 1: wires -> iNTT -> blind -> commit (src/prover.rs:107-158)
+    nvtxRangePushA("create_proof");
+    struct PopAll { int depth = 1; ~PopAll() { while (depth-- > 0) nvtxRangePop(); } } nvtx_guard;   // also on early return
+    nvtxRangePushA("round 1: wire polynomials"); nvtx_guard.depth++;
     const zkp_buf* W = wires_dev;
     if (!W) {
         ZKP_CUDA(ctx, cudaMemcpyAsync(pr->W->d, wires_host, 4 * n * sizeof(fr_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -526,6 +529,7 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     for (unsigned j = 0; j < 4; j++) tr.append_commitment(wl[j], comms + 12 * j);
 
     // round 2: permutation accumulator (src/prover.rs:160-199)
+    nvtxRangePop(); nvtxRangePushA("round 2: permutation z");
     const fr beta = tr.challenge_scalar("beta");
     tr.append_scalar("beta", beta);
     const fr gamma = tr.challenge_scalar("gamma");
@@ -542,6 +546,7 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     tr.append_commitment("z", comms + 12 * 4);
 
     // round 3: quotient on the 8n coset (src/prover.rs:201-287, quotient_poly.rs)
+    nvtxRangePop(); nvtxRangePushA("round 3: quotient");
     fr ch[7];
     ch[0] = tr.challenge_scalar("alpha");
     ch[1] = beta;
@@ -593,6 +598,7 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     for (unsigned j = 0; j < 4; j++) tr.append_commitment(tl[j], comms + 12 * (5 + j));
 
     // rounds 4/5: evaluations, linearisation, openings (src/prover.rs:289-452)
+    nvtxRangePop(); nvtxRangePushA("rounds 4-5: openings");
     const fr zc = tr.challenge_scalar("z_challenge");
     const fr zw = F::mul(zc, fr_load(key.generator));
     // Every opening of the proof in ONE batched launch and one read-back: the 12 evaluations at z, the 4
@@ -605,7 +611,12 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     zkp_poly_ref ep[E_COUNT];
     uint8_t which[E_COUNT];
     memset(which, 0, sizeof which);
-    ep[E_T] = ref(pr->T, 0, n8);
+    // the t_4 commitment above passed its degree check, so every coefficient of t_4 = T[3n ..] at or beyond the
+    // SRS length is zero: the quotient is opened, aggregated and divided over its real length only (same
+    // field elements as over the zero-padded 8n / 5n vectors of quotient_poly.rs:115, prover.rs:253-259,422-434)
+    const size_t t4_len = pr->srs->n < 5 * n ? pr->srs->n : 5 * n;
+    const size_t agg_len = t4_len > n + 3 ? t4_len : n + 3;
+    ep[E_T] = ref(pr->T, 0, 3 * n + t4_len);
     for (unsigned j = 0; j < 4; j++) ep[E_A + j] = wp[j];
     ep[E_S1] = key.poly[S1]; ep[E_S2] = key.poly[S2]; ep[E_S3] = key.poly[S3];
     ep[E_QARITH] = key.poly[Q_ARITH]; ep[E_QC] = key.poly[Q_C]; ep[E_QL] = key.poly[Q_L]; ep[E_QR] = key.poly[Q_R];
@@ -662,7 +673,7 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     {
         const fr z_n = F::pow(zc, (uint64_t)n);
         const fr v1 = tr.challenge_scalar("v_challenge");
-        zkp_poly_ref ar[12] = {tq[0], tq[1], tq[2], tq[3], rr, wp[0], wp[1], wp[2], wp[3],
+        zkp_poly_ref ar[12] = {tq[0], tq[1], tq[2], ref(pr->T, 3 * n, t4_len), rr, wp[0], wp[1], wp[2], wp[3],
                                key.poly[S1], key.poly[S2], key.poly[S3]};
         fr as[12];
         as[0] = F::one();
@@ -672,8 +683,8 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
         as[4] = v1;
         for (unsigned j = 5; j < 12; j++) as[j] = F::mul(as[j - 1], v1);
         for (unsigned j = 0; j < 12; j++) fr_store(scl + 4 * j, as[j]);
-        TRY(zkp_poly_lincomb_dev(ctx, ar, scl, 12, pr->AGG, 0, 5 * n));
-        TRY(zkp_poly_div_linear_dev(ctx, ref(pr->AGG, 0, 5 * n), zc.l, pr->WZ, 0));
+        TRY(zkp_poly_lincomb_dev(ctx, ar, scl, 12, pr->AGG, 0, agg_len));
+        TRY(zkp_poly_div_linear_dev(ctx, ref(pr->AGG, 0, agg_len), zc.l, pr->WZ, 0));
         // the second v_challenge follows the first with nothing appended in between
         // (src/prover.rs:435-450): both witnesses are committed as one batch of two
         const fr v2 = tr.challenge_scalar("v_challenge");
@@ -684,7 +695,7 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
         for (unsigned j = 0; j < 4; j++) fr_store(scl + 4 * j, bs[j]);
         TRY(zkp_poly_lincomb_dev(ctx, br, scl, 4, pr->SAGG, 0, n + 3));
         TRY(zkp_poly_div_linear_dev(ctx, ref(pr->SAGG, 0, n + 3), zw.l, pr->WZW, 0));
-        const zkp_poly_ref wc[2] = {ref(pr->WZ, 0, 5 * n - 1), ref(pr->WZW, 0, n + 2)};
+        const zkp_poly_ref wc[2] = {ref(pr->WZ, 0, agg_len - 1), ref(pr->WZW, 0, n + 2)};
         TRY(commit_group(pr, wc, 2, comms + 12 * 9));
     }
 

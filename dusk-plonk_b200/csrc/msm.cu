@@ -1086,7 +1086,7 @@ __global__ void __launch_bounds__(128) srs_table_window_kernel(const g1_affine* 
             pre[g] = run;
             run = run * zzz[g];
         }
-        fq_t inv = inverse(run);
+        fq_t inv = fq_inverse_bingcd(run);
 #pragma unroll 1
         for (unsigned g = cnt; g-- > 0;) {
             const fq_t t = inv * pre[g];                          // 1 / ZZZ_g
@@ -1131,18 +1131,42 @@ __device__ __forceinline__ g1_affine g1_generator() {
     return g;
 }
 
-__global__ void srs_table_kernel(g1_affine* tbl) {
+// x = X / ZZ, y = Y / ZZZ through the binary-GCD inversion (88 multiplication times instead of the 618 of a
+// Fermat chain): same field elements as xyzz_to_affine
+__device__ __forceinline__ g1_affine xyzz_to_affine_gcd(const g1_xyzz& a) {
+    if (a.is_inf()) return g1_affine::inf();
+    const fq_t t = fq_inverse_bingcd(a.zzz);
+    const fq_t zinv = a.zz * t;
+    g1_affine r;
+    r.x = a.x * sqr(zinv);
+    r.y = a.y * t;
+    return r;
+}
+
+// base[w] = 2^(8 w) G: one thread per window walks its doublings (the longest chain is 248 doublings)
+__global__ void srs_table_bases_kernel(g1_xyzz* base) {
     const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= FB_W) return;
-    g1_affine g = g1_generator();
-    g1_xyzz base = g1_xyzz::inf();
-    xyzz_madd(base, g);
-    for (unsigned i = 0; i < 8 * w; i++) xyzz_dbl(base);
+    const g1_affine g = g1_generator();
+    g1_xyzz b = g1_xyzz::inf();
+    xyzz_madd(b, g);
+    for (unsigned i = 0; i < 8 * w; i++) xyzz_dbl(b);
+    base[w] = b;
+}
+
+// tbl[w][d - 1] = d * base[w]: one thread per entry, 8-bit double-and-add and its own conversion to affine
+// (was: one warp, 255 serial additions each followed by a Fermat chain -- 151 ms per SRS)
+__global__ void __launch_bounds__(128) srs_table_kernel(const g1_xyzz* base, g1_affine* tbl) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= FB_W * FB_D) return;
+    const unsigned w = t / FB_D, d = t % FB_D + 1;
+    const g1_xyzz b = base[w];
     g1_xyzz acc = g1_xyzz::inf();
-    for (unsigned d = 0; d < FB_D; d++) {
-        xyzz_add(acc, base);
-        tbl[w * FB_D + d] = xyzz_to_affine(acc);
+    for (int bit = 7; bit >= 0; bit--) {
+        xyzz_dbl(acc);
+        if ((d >> bit) & 1u) xyzz_add(acc, b);
     }
+    tbl[t] = xyzz_to_affine_gcd(acc);
 }
 
 __global__ void __launch_bounds__(128) srs_powers_kernel(const g1_affine* tbl, fr_t tau, size_t first, size_t n,
@@ -1155,13 +1179,17 @@ __global__ void __launch_bounds__(128) srs_powers_kernel(const g1_affine* tbl, f
         const uint32_t d = (s.l[w >> 2] >> (8 * (w & 3))) & 255u;
         if (d) xyzz_madd(acc, msm_ld_affine(tbl + w * FB_D + d - 1));
     }
-    out[i] = xyzz_to_affine(acc);
+    out[i] = xyzz_to_affine_gcd(acc);
 }
 
 int srs_generate(zkp_ctx* ctx, const fr_t& tau, size_t first, size_t n, g1_affine* out_dev) {
     g1_affine* tbl = nullptr;
+    g1_xyzz* base = nullptr;
     ZKP_CUDA(ctx, cudaMalloc(&tbl, sizeof(g1_affine) * FB_W * FB_D));
-    srs_table_kernel<<<1, 32, 0, ctx->stream>>>(tbl);
+    ZKP_CUDA(ctx, cudaMalloc(&base, sizeof(g1_xyzz) * FB_W));
+    srs_table_bases_kernel<<<1, 32, 0, ctx->stream>>>(base);
+    ZKP_LAUNCHED(ctx);
+    srs_table_kernel<<<(FB_W * FB_D + 127) / 128, 128, 0, ctx->stream>>>(base, tbl);
     ZKP_LAUNCHED(ctx);
     if (n) {
         srs_powers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(tbl, tau, first, n, out_dev);
@@ -1169,6 +1197,7 @@ int srs_generate(zkp_ctx* ctx, const fr_t& tau, size_t first, size_t n, g1_affin
     }
     ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ZKP_CUDA(ctx, cudaFree(tbl));
+    ZKP_CUDA(ctx, cudaFree(base));
     return ZKP_OK;
 }
 

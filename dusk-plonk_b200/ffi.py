@@ -64,6 +64,7 @@ SIGNATURES = {
     "zkp_srs_generate_range": (_int, [_vp, _vp, _sz, _sz, ctypes.POINTER(_vp)]),
     "zkp_poly_degree_dev": (_int, [_vp, _vp, _sz, _sz, ctypes.POINTER(ctypes.c_longlong)]),
     "zkp_srs_download": (_int, [_vp, _vp, _sz, _vp, _sz]),
+    "zkp_srs_trim": (_int, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
     "zkp_msm_g1": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "zkp_msm_g1_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp]),
     "zkp_commit": (_int, [_vp, _vp, _vp, _sz, _vp]),
@@ -541,6 +542,15 @@ class Srs:
         out = np.empty((n, 12), dtype=np.uint64)
         self.ctx.check(self.ctx.lib.zkp_srs_download(self.ctx.h, self.h, off, _ptr(out), n))
         return out
+
+    def trim(self, keep):
+        """The first ``keep`` powers as a new SRS, without leaving the device (``zkp_srs_trim``)."""
+        t = object.__new__(Srs)
+        t.ctx, t.n = self.ctx, keep
+        h = _vp()
+        self.ctx.check(self.ctx.lib.zkp_srs_trim(self.ctx.h, self.h, keep, ctypes.byref(h)))
+        t.h = h
+        return t
 
     def free(self):
         if self.h and self.ctx.h:

@@ -35,7 +35,7 @@ class PlonkParams:
         keep = min(self.srs.n, n + 7)
         if keep == self.srs.n:
             return self
-        return PlonkParams(self.ctx, self.ctx.srs_load(self.srs.download(0, keep)))
+        return PlonkParams(self.ctx, self.srs.trim(keep))   # device-side slice: no download / re-upload
 
     def commit(self, poly):
         """-> Commitment, raising ``Error`` when degree > SRS (Err in the reference)."""
@@ -92,7 +92,7 @@ class ShardedNativeParams(PlonkParams):
         keep = min(self.srs.n, n + 7)
         if keep == self.srs.n:
             return self
-        return ShardedNativeParams(self.ctx, self.ctx.srs_load(self.srs.download(0, keep)), self.native_comm)
+        return ShardedNativeParams(self.ctx, self.srs.trim(keep), self.native_comm)
 
     def commit(self, poly):
         return self.commit_batch([poly])[0]

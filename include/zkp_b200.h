@@ -130,6 +130,9 @@ size_t zkp_srs_len(const zkp_srs* srs);
 int zkp_srs_generate(zkp_ctx* ctx, const uint64_t tau[4], size_t n, zkp_srs** out);
 /* Powers [tau^(first + i) * G]_{i<n}: one rank's slice of a sharded SRS. */
 int zkp_srs_generate_range(zkp_ctx* ctx, const uint64_t tau[4], size_t first, size_t n, zkp_srs** out);
+/* PlonkParams::trim (src/key.rs:82; tests/range.rs:24-26) on the device: the first `keep` powers as a new SRS
+ * (window-table rows sliced device-to-device when the window width is unchanged, else rebuilt). */
+int zkp_srs_trim(zkp_ctx* ctx, const zkp_srs* srs, size_t keep, zkp_srs** out);
 int zkp_srs_download(zkp_ctx* ctx, const zkp_srs* srs, size_t off, uint64_t* xy, size_t n);
 
 /* msm_curve_addition(&bases[..n], &scalars[..n]) -> affine (Commitment::new).
