@@ -20,6 +20,7 @@ const char* zkp_strerror(int code) {
         case ZKP_ERR_CUDA: return "CUDA failure";
         case ZKP_ERR_DEGREE: return "polynomial degree exceeds the SRS";
         case ZKP_ERR_NOMEM: return "out of memory";
+        case ZKP_ERR_VERIFY: return "proof rejected";
         case ZKP_ERR_STATE: return "call out of order (prove_witness before set_wiring)";
         default: return "unknown error";
     }

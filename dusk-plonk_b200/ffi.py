@@ -16,6 +16,7 @@ ZKP_ERR_CUDA = -2
 ZKP_ERR_DEGREE = -3
 ZKP_ERR_NOMEM = -4
 ZKP_ERR_STATE = -5
+ZKP_ERR_VERIFY = -6
 
 _u64p = ctypes.POINTER(ctypes.c_uint64)
 _vp = ctypes.c_void_p
@@ -113,6 +114,11 @@ class ProvingKeyDesc(ctypes.Structure):
                 ("generator", ctypes.c_uint64 * 4), ("widget_mask", ctypes.c_uint32)]
 
 
+class VerifierKeyDesc(ctypes.Structure):
+    """``zkp_verifier_key``."""
+    _fields_ = [("k", _uint), ("constraints", ctypes.c_uint64), ("commitments", (ctypes.c_uint64 * 12) * 15)]
+
+
 SIGNATURES.update({
     "zkp_prover_create": (_int, [_vp, _vp, ctypes.POINTER(ProvingKeyDesc), ctypes.POINTER(_vp)]),
     "zkp_prover_destroy": (_int, [_vp]),
@@ -124,6 +130,12 @@ SIGNATURES.update({
     "zkp_linearization_scalars": (_int, [_uint, _vp, _vp, _vp]),
     "zkp_g1_compress": (_int, [_vp, _vp]),
     "zkp_fr_from_wide": (_int, [_vp, _vp]),
+    # verifier glue (host code)
+    "zkp_g2_generator_mul": (_int, [_vp, _vp]),
+    "zkp_g1_generator_mul": (_int, [_vp, _vp]),
+    "zkp_pairing_check": (_int, [_vp, _vp, _sz]),
+    "zkp_kzg_batch_check": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "zkp_verify": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
     # one job over several GPUs
     "zkp_comm_unique_id": (_int, [_vp]),
     "zkp_comm_create": (_int, [_vp, _vp, _int, _int, ctypes.POINTER(_vp)]),

@@ -54,6 +54,17 @@ def fr_column_to_mont(col, n):
     return out
 
 
+_FQ_R = (1 << 384) % P_MOD
+
+
+def g1_to_mont(pt):
+    """(x, y) canonical ints / None -> 12 x uint64 Montgomery limbs (zeros for the identity)."""
+    if pt is None:
+        return np.zeros(12, dtype=np.uint64)
+    raw = (pt[0] * _FQ_R % P_MOD).to_bytes(48, "little") + (pt[1] * _FQ_R % P_MOD).to_bytes(48, "little")
+    return np.frombuffer(raw, dtype="<u8").copy()
+
+
 def g1_from_mont(xy):
     """12 x uint64 Montgomery (x, y) -> (x, y) canonical ints, or None for the identity."""
     raw = np.ascontiguousarray(np.asarray(xy, dtype="<u8").reshape(12)).tobytes()

@@ -125,7 +125,15 @@ class PlonkKey:
         gn, wn = pow(g, n, R_MOD), pow(w8, n, R_MOD)
         pk.zh_inv = fr_to_mont([pow((gn * pow(wn, i, R_MOD) - 1) % R_MOD, -1, R_MOD) for i in range(8)])
         transcript = Transcript.base(label, vk.transcript_list(), m)      # src/prover.rs:54-55
-        return Prover(ctx, keypair, pk, vk, transcript, circ.pi_indexes)
+        prover = Prover(ctx, keypair, pk, vk, transcript, circ.pi_indexes)
+        prover.label = label
+        return prover
+
+    @staticmethod
+    def compile_pair(pp, circuit, label=b"plonk"):
+        """``PlonkKey::compile`` as the reference returns it (src/key.rs:46-50,304-327): (Prover, Verifier)."""
+        prover = PlonkKey.compile_with_circuit(pp, label, circuit)
+        return prover, prover.verifier()
 
     @staticmethod
     def compile(pp, circuit, label=b"plonk"):

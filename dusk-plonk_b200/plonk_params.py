@@ -12,20 +12,30 @@ class Error(Exception):
 
 
 class PlonkParams:
-    def __init__(self, ctx: Context, srs):
+    def __init__(self, ctx: Context, srs, opening_key=None):
         self.ctx = ctx
         self.srs = srs
+        self.opening_key = opening_key   # EvaluationKey: the G2 side ([tau]_2), carried along by trim
 
     @classmethod
     def setup_synthetic(cls, ctx, k, tau_mont):
         """SRS with the structure of ``PlonkParams::setup(k, rng)`` (tests/range.rs:26):
         [tau^i]_1 for i < 2^k + 7 (the prover needs n + 7 powers for t_4).
         tau is an explicit input because the reference's RNG derivation is unreachable."""
-        return cls(ctx, ctx.srs_generate(tau_mont, (1 << k) + 7))
+        from .verifier import EvaluationKey
+        return cls(ctx, ctx.srs_generate(tau_mont, (1 << k) + 7), EvaluationKey.from_tau(tau_mont))
 
     @classmethod
-    def from_points(cls, ctx, xy):
-        return cls(ctx, ctx.srs_load(xy))
+    def from_points(cls, ctx, xy, beta_h=None):
+        """An SRS handed over as points (a ceremony's output): G1 powers and, for verification, [tau]_2."""
+        from .verifier import EvaluationKey
+        return cls(ctx, ctx.srs_load(xy), EvaluationKey(beta_h) if beta_h is not None else None)
+
+    def verification_key(self):
+        """``keypair.verification_key()`` (src/key.rs:320): the ``EvaluationKey`` a ``Verifier`` opens with."""
+        if self.opening_key is None:
+            raise Error("this SRS was loaded without its G2 element [tau]_2")
+        return self.opening_key
 
     def max_degree(self):
         return self.srs.n - 1
@@ -35,7 +45,7 @@ class PlonkParams:
         keep = min(self.srs.n, n + 7)
         if keep == self.srs.n:
             return self
-        return PlonkParams(self.ctx, self.srs.trim(keep))   # device-side slice: no download / re-upload
+        return PlonkParams(self.ctx, self.srs.trim(keep), self.opening_key)   # device-side slice: no download / re-upload
 
     def commit(self, poly):
         """-> Commitment, raising ``Error`` when degree > SRS (Err in the reference)."""
@@ -80,19 +90,20 @@ class ShardedNativeParams(PlonkParams):
     ``PlonkKey.compile`` / ``Prover.create_proof`` see an ordinary commit key; a key compiled from it owns
     only this rank's cosets of the 8n domain and proves through ``zkp_prover_create_sharded``."""
 
-    def __init__(self, ctx, srs, comm):
-        super().__init__(ctx, srs)
+    def __init__(self, ctx, srs, comm, opening_key=None):
+        super().__init__(ctx, srs, opening_key)
         self.native_comm = comm
 
     @classmethod
     def setup_synthetic(cls, ctx, comm, k, tau_mont):
-        return cls(ctx, ctx.srs_generate(tau_mont, (1 << k) + 7), comm)
+        from .verifier import EvaluationKey
+        return cls(ctx, ctx.srs_generate(tau_mont, (1 << k) + 7), comm, EvaluationKey.from_tau(tau_mont))
 
     def trim(self, n):
         keep = min(self.srs.n, n + 7)
         if keep == self.srs.n:
             return self
-        return ShardedNativeParams(self.ctx, self.srs.trim(keep), self.native_comm)
+        return ShardedNativeParams(self.ctx, self.srs.trim(keep), self.native_comm, self.opening_key)
 
     def commit(self, poly):
         return self.commit_batch([poly])[0]

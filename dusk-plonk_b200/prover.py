@@ -150,6 +150,14 @@ class Prover:
             self._side = Context(self.ctx.device)
         return self._side
 
+    def verifier(self, opening_key=None):
+        """The ``Verifier`` half of ``PlonkKey::compile``'s pair (src/key.rs:316-325): same verification key, the
+        commit key's ``verification_key()`` as opening key."""
+        from .verifier import Verifier
+        ok = opening_key if opening_key is not None else self.keypair.verification_key()
+        return Verifier(getattr(self, "label", b"plonk"), self.verifier_key, ok, self.pi_indexes, self.size,
+                        self.verifier_key["n"])
+
     def close(self):
         """Release the workspace and the side stream (the proving key stays with its buffers)."""
         if getattr(self, "_side", None) is not None:

@@ -12,4 +12,5 @@ from host_mirror.composer import Plonk, Constraint, SynthesizedCircuit  # noqa: 
 from .key import PlonkKey  # noqa: E402,F401
 from .prover import Prover, Proof, WitnessAssignment, WitnessValues  # noqa: E402,F401
 from .transcript import Transcript  # noqa: E402,F401
+from .verifier import Verifier, EvaluationKey  # noqa: E402,F401
 from . import sharding  # noqa: E402,F401

@@ -40,6 +40,7 @@ extern "C" {
 #define ZKP_ERR_CUDA (-2)      /* CUDA runtime failure; see zkp_last_error()                     */
 #define ZKP_ERR_DEGREE (-3)    /* polynomial degree exceeds the SRS: PlonkParams::commit's Err   */
 #define ZKP_ERR_NOMEM (-4)
+#define ZKP_ERR_VERIFY (-6)    /* proof rejected (Error::ProofVerificationError / PairingCheckFailure)   */
 #define ZKP_ERR_STATE (-5)     /* call out of order (zkp_prover_prove_witness before set_wiring)   */
 
 typedef struct zkp_ctx zkp_ctx;
@@ -334,6 +335,33 @@ int zkp_linearization_scalars(unsigned k, const uint64_t challenges[32], const u
                               uint64_t out[48]);
 int zkp_g1_compress(const uint64_t xy[12], uint8_t out[48]);
 int zkp_fr_from_wide(const uint8_t bytes[64], uint64_t out_mont[4]);
+
+/* ---- verifier glue (host code) ------------------------------------------------
+ * VerificationKey (src/key.rs:203-214, fields of zksnarks::plonk::VerificationKey): the 15 commitments in the
+ * order of zkp_proving_key.poly, the padded size 2^k and the constraint count the transcript was seeded with. */
+typedef struct zkp_verifier_key {
+    unsigned k;
+    uint64_t constraints;
+    uint64_t commitments[15][12];   /* affine Montgomery, zeros = identity */
+} zkp_verifier_key;
+/* [s]_2 / [s]_1 for a Montgomery-form scalar: the G2 half of the opening key PlonkParams::verification_key()
+ * returns (EvaluationKey { g, h, beta_h }, src/commitment_scheme.rs:51-58): beta_h = [tau]_2 for an SRS made
+ * from tau, h = [1]_2.  G2 affine as x0 x1 y0 y1 (6 uint64 each, Montgomery), zeros = identity. */
+int zkp_g2_generator_mul(const uint64_t scalar[4], uint64_t out[24]);
+int zkp_g1_generator_mul(const uint64_t scalar[4], uint64_t out[12]);
+/* prod_i e(g1_i, g2_i) == 1: ZKP_OK or ZKP_ERR_VERIFY (multi_miller_loop(..).final_exp() == identity). */
+int zkp_pairing_check(const uint64_t* g1 /* count x 12 */, const uint64_t* g2 /* count x 24 */, size_t count);
+/* commitment_scheme::batch_check (src/commitment_scheme.rs:24-66): `count` opening proofs (point, commitment to the
+ * witness, claimed evaluation, commitment to the polynomial) against the opening key; draws the "batch" challenge
+ * from the transcript state (updated in place). */
+int zkp_kzg_batch_check(const uint64_t beta_h[24], const uint64_t* points, const uint64_t* witness_comms,
+                        const uint64_t* evals, const uint64_t* poly_comms, size_t count, uint8_t transcript[203]);
+/* Verifier::verify (src/verifier.rs:46-81) + Proof::verify (src/prover/proof.rs:70-383).  transcript: the
+ * verifier's base transcript (Transcript::base(label, vk, constraints)); the public inputs are appended here.
+ * commitments / evaluations: as zkp_prover_prove returns them.  ZKP_OK = accepted, ZKP_ERR_VERIFY = rejected. */
+int zkp_verify(const zkp_verifier_key* vk, const uint64_t beta_h[24], const uint8_t transcript[203],
+               const uint64_t commitments[132], const uint64_t evaluations[64], const uint32_t* pi_idx,
+               const uint64_t* pi_values, size_t pi_count);
 
 #ifdef __cplusplus
 }
