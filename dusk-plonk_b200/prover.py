@@ -150,6 +150,21 @@ class Prover:
             self._side = Context(self.ctx.device)
         return self._side
 
+    def clone(self):
+        """``Prover: Clone`` (src/prover.rs:28): a second prover over the SAME device-resident key and SRS with its own
+        context (stream, MSM / NTT scratch) and workspace, so that several proofs can be in flight on one GPU --
+        one proof's latency-bound bucket reductions and transcript synchronisations run under another's
+        accumulation.  The library is re-entrant per context; clones are driven from separate host threads."""
+        from .ffi import Context
+        if getattr(self.keypair, "native_comm", None) is not None:
+            raise ValueError("a prover sharded over GPUs is not cloned: its ranks already fill the GPUs")
+        ctx2 = Context(self.ctx.device)
+        kp2 = type(self.keypair)(ctx2, self.keypair.srs, getattr(self.keypair, "opening_key", None))
+        c = Prover(ctx2, kp2, self.prover_key, self.verifier_key, self.transcript, self.pi_indexes)
+        c.label = getattr(self, "label", b"plonk")
+        c._owns_ctx = True
+        return c
+
     def verifier(self, opening_key=None):
         """The ``Verifier`` half of ``PlonkKey::compile``'s pair (src/key.rs:316-325): same verification key, the
         commit key's ``verification_key()`` as opening key."""
@@ -167,6 +182,9 @@ class Prover:
             self._native.close()
             self._native = None
         self._ws = None
+        if getattr(self, "_owns_ctx", False):
+            self.ctx.close()
+            self._owns_ctx = False
 
     def _commit(self, buf, off=0, n=None):
         return self.keypair.commit(_View(buf, off, n)).affine()

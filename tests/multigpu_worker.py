@@ -92,9 +92,42 @@ def main():
         assert world == 1 or (colls > 0 and sent > 0)
         p16.close()
         ncomm.close()
+    # 4. BASELINE sizes (set ZKP_WORKER_BIG=1: minutes of host-side checking): four-step NTT 2^24 against the
+    #    single-GPU kernel run on this rank's own GPU, sharded MSM 2^24 by known discrete log
+    if os.environ.get("ZKP_WORKER_BIG"):
+        from oracle import curve
+        from oracle.fields import FR_MONT_RINV, R_MOD, _from_limbs_fast, g1_from_mont_limbs
+        k24, n24 = 24, 1 << 24
+        host = random_fr_raw_limbs(2424, n24)
+        fs = FourStepNtt(ctx, comm, k24)
+        for inverse, coset in ((False, False), (True, True)):
+            fs.scatter_input(host)
+            fs.run(inverse=inverse, coset=coset)
+            mine = np.zeros((n24, 4), dtype=np.uint64)
+            fs.gather_output(mine)
+            ref = ctx.upload(host)
+            ctx.ntt_dev(ref, n24, ref, k24, inverse, coset)
+            full = ref.download().reshape(fs.C, fs.R, 4)[:, rank * fs.Rl:(rank + 1) * fs.Rl, :]
+            got = mine.reshape(fs.C, fs.R, 4)[:, rank * fs.Rl:(rank + 1) * fs.Rl, :]
+            assert np.array_equal(got, full), ("four-step 2^24", inverse, coset)
+        del fs
+        tau24 = SplitMix64(4242).fr()
+        lo, hi = z.sharding.shard_range(n24, rank, world)
+        sp24 = ShardedPlonkParams(ctx, comm, n24, lo, hi, ctx.srs_generate(fr_to_mont_limbs([tau24])[0], hi - lo, first=lo))
+        sc = random_fr_raw_limbs(55555, n24)
+        got = sp24.commit(ctx.upload(sc)).affine()
+        if rank == 0:
+            acc, t = 0, 1
+            for v in _from_limbs_fast(sc, 4):
+                acc = (acc + v * t) % R_MOD
+                t = t * tau24 % R_MOD
+            assert got == curve.mul(curve.G1_GEN, acc * FR_MONT_RINV % R_MOD), "sharded MSM 2^24"
+        digs = [None] * world
+        dist.all_gather_object(digs, got)
+        assert all(d == got for d in digs)
     dist.barrier()
     if rank == 0:
-        print("MULTIGPU OK world=%d" % world, flush=True)
+        print("MULTIGPU OK world=%d%s" % (world, " (+2^24 sizes)" if os.environ.get("ZKP_WORKER_BIG") else ""), flush=True)
     ctx.close()
     dist.destroy_process_group()
 

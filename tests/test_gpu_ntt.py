@@ -98,7 +98,7 @@ def test_device_resident_and_batched(ctx, cport):
     assert np.array_equal(one.download(), cport.ntt(data[:n], k, coset=True))
 
 
-@pytest.mark.parametrize("k", [22, 26])
+@pytest.mark.parametrize("k", [22, 24, 26])
 def test_full_size_properties(ctx, k):
     """BASELINE sizes: round trip, spot evaluation against Horner, and linearity -- the
     size-independent properties of an exact DFT."""

@@ -452,3 +452,36 @@ def test_native_round_driver_equals_python_driven_rounds(ctx, name):
     assert vproof == nproof
     assert z.Proof.from_bytes(nproof.wire_bytes) == nproof
     assert oplonk.verify(ovk, circ.n, nproof, circ.pi_indexes, npi, otr, oplonk.trapdoor_kzg_check(tau))
+
+
+def test_cloned_provers_prove_concurrently(ctx):
+    """``Prover: Clone`` (src/prover.rs:28): three provers over one device-resident key, each on its own context and
+    host thread, 6 proofs each with different blinders -- every proof equals the one the original prover
+    makes alone for the same blinders (no cross-talk between streams / scratch), and verifies."""
+    import threading
+    circ, tau, pp, prover, bl = _synthetic_setup(ctx, 12)
+    sets = [[(b + 17 * j) % R_MOD for b in bl] for j in range(6)]
+    want = [prover.create_proof(b, circ)[0].wire_bytes for b in sets]
+    clones = [prover, prover.clone(), prover.clone()]
+    got = [[None] * len(sets) for _ in clones]
+    errs = []
+
+    def work(p, out):
+        try:
+            for j, b in enumerate(sets):
+                out[j] = p.create_proof(b, circ)[0].wire_bytes
+        except Exception as e:   # surfaced below: a thread must not die silently
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(p, o)) for p, o in zip(clones, got)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for o in got:
+        assert o == want
+    ver = prover.verifier()
+    ver.verify(z.Proof.from_bytes(got[2][5]), list(circ.pi_values))
+    for p in clones[1:]:
+        p.close()
+    prover.close()

@@ -136,3 +136,98 @@ def test_native_sharded_prover_rejects_unsatisfied_circuit(ctx):
         prover.create_proof(bl, bad)
     prover.close()
     comm.close()
+
+
+# ---------------------------------------------------------------- BASELINE sizes of the sharded paths
+def _sparse_poly(k, seed):
+    n = 1 << k
+    idxs = [0, 1, 5, n // 3, n // 2 + 1, n - 1]
+    rng = SplitMix64(seed)
+    vals = [rng.fr() for _ in idxs]
+    sp = np.zeros((n, 4), dtype=np.uint64)
+    sp[idxs] = fr_to_mont_limbs(vals)
+    return sp, idxs, vals
+
+
+@pytest.mark.parametrize("inverse,coset", [(False, False), (True, True)])
+def test_four_step_2p24_equals_single_gpu_kernel(ctx, inverse, coset):
+    """BASELINE config 4 threshold size: the four-step path (column transforms, twiddle, transpose, row
+    transforms) against the single-GPU kernel on the same 2^24 random vector, element for element."""
+    from dusk_plonk_b200.sharding import FourStepNtt, LocalCommunicator
+    k, n = 24, 1 << 24
+    host = random_fr_raw_limbs(2400 + inverse, n)
+    fs = FourStepNtt(ctx, LocalCommunicator(), k)
+    fs.scatter_input(host)
+    fs.run(inverse=inverse, coset=coset)
+    out = np.zeros((n, 4), dtype=np.uint64)
+    fs.gather_output(out)
+    ref = ctx.upload(host)
+    ctx.ntt_dev(ref, n, ref, k, inverse, coset)
+    assert np.array_equal(out, ref.download())
+
+
+def test_four_step_2p26_spot_horner(ctx):
+    """Largest BASELINE size: out[j] = sum_i a_i w^(i j) at sampled j for a sparse polynomial (cheap exact
+    Horner on the host), plus the round trip through the inverse four-step transform of a random vector."""
+    from dusk_plonk_b200.sharding import FourStepNtt, LocalCommunicator
+    from oracle.fields import domain_generator, fr_from_mont_limbs
+    k, n = 26, 1 << 26
+    sp, idxs, vals = _sparse_poly(k, 26)
+    fs = FourStepNtt(ctx, LocalCommunicator(), k)
+    fs.scatter_input(sp)
+    fs.run()
+    out = np.zeros((n, 4), dtype=np.uint64)
+    fs.gather_output(out)
+    w = domain_generator(k)
+    for j in [0, 1, 2, n // 2, n - 1, 123457]:
+        x = pow(w, j, R_MOD)
+        exp = sum(v * pow(x, i, R_MOD) for i, v in zip(idxs, vals)) % R_MOD
+        assert fr_from_mont_limbs(out[j:j + 1]) == [exp], j
+    fs.scatter_input(out)
+    fs.run(inverse=True)
+    back = np.zeros((n, 4), dtype=np.uint64)
+    fs.gather_output(back)
+    assert np.array_equal(back, sp)
+
+
+def _known_dlog_commit(tau, sc_mont):
+    from oracle.fields import FR_MONT_RINV, _from_limbs_fast
+    acc, t = 0, 1
+    for v in _from_limbs_fast(sc_mont, 4):
+        acc = (acc + v * t) % R_MOD
+        t = t * tau % R_MOD
+    return curve.mul(curve.G1_GEN, acc * FR_MONT_RINV % R_MOD)
+
+
+def test_sharded_msm_2p24_known_dlog(ctx):
+    """BASELINE config 3 at its largest size through the sharded commit path (SRS range + partial-sum
+    combination; one rank here, 2 .. 8 in tests/multigpu_worker.py): (sum_i s_i tau^i) G by known dlog."""
+    from dusk_plonk_b200.sharding import LocalCommunicator, ShardedPlonkParams
+    n = 1 << 24
+    tau = SplitMix64(4242).fr()
+    sp = ShardedPlonkParams(ctx, LocalCommunicator(), n, 0, n, ctx.srs_generate(fr_to_mont_limbs([tau])[0], n))
+    sc = random_fr_raw_limbs(55555, n)
+    got = sp.commit(ctx.upload(sc)).affine()
+    assert got == _known_dlog_commit(tau, sc)
+
+
+def test_native_sharded_commit_2p22_known_dlog(ctx):
+    """zkp_commit_batch_sharded_dev (offsets into the SRS, XYZZ partial-sum gather) at 2^22, batch of two, with a
+    coefficient beyond the SRS reported as the degree error on the right polynomial only."""
+    import dusk_plonk_b200 as z
+    from dusk_plonk_b200.plonk_params import Error, ShardedNativeParams
+    n = 1 << 22
+    tau = SplitMix64(777).fr()
+    comm = z.NativeComm(ctx)
+    sp = ShardedNativeParams(ctx, ctx.srs_generate(fr_to_mont_limbs([tau])[0], n), comm)
+    sc1, sc2 = random_fr_raw_limbs(1, n), random_fr_raw_limbs(2, n - 12345)
+    c1, c2 = sp.commit_batch([ctx.upload(sc1), ctx.upload(sc2)])
+    assert c1.affine() == _known_dlog_commit(tau, sc1) and c2.affine() == _known_dlog_commit(tau, sc2)
+    over = np.zeros((n + 3, 4), dtype=np.uint64)
+    over[:n] = sc1
+    over[n + 2] = fr_to_mont_limbs([1])[0]
+    with pytest.raises(Error):
+        sp.commit(ctx.upload(over))
+    over[n + 2] = 0
+    assert sp.commit(ctx.upload(over)).affine() == c1.affine()       # zeros beyond the SRS are fine
+    comm.close()
