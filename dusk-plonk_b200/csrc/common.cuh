@@ -155,5 +155,7 @@ void msm_free(zkp_ctx* ctx);
 
 // prover.cu
 void prover_free(zkp_ctx* ctx);
+int poly_eval2_launch(zkp_ctx* ctx, const zkp_poly_ref* polys, const uint8_t* which, unsigned count,
+                      const uint64_t points[8], fr_t** res_dev);
 
 }  // namespace zkp

@@ -72,6 +72,15 @@ __global__ void gather_wires_kernel(const fr_t* witness, size_t num_w, const uin
     o[0] = a; o[1] = b;
 }
 
+// *flag = 1 if any of the n elements is non-zero (degree check of the quotient's upper chunks)
+__global__ void any_nonzero_kernel(const fr_t* p, size_t n, uint32_t* flag) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* q = reinterpret_cast<const uint4*>(p + i);
+    const uint4 a = q[0], b = q[1];
+    if (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) *flag = 1u;
+}
+
 // dense public-input vector (src/lib.rs:206-219): pi[idx[c]] = values[c] on a zeroed n-vector
 __global__ void scatter_pi_kernel(const fr_t* values, const uint32_t* idx, size_t count, size_t n, fr_t* pi) {
     const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,6 +199,201 @@ static int commit_group(zkp_prover* pr, const zkp_poly_ref* polys, unsigned coun
     return ZKP_OK;
 }
 
+// Rounds 4 / 5 of a proof shared by several GPUs, on the slabs where the quotient's inverse transform left them:
+// rank s works on coefficients [lo, hi) = [s slab, (s + 1) slab) of every polynomial (the last rank also on
+// the few coefficients at and beyond n).  Openings are sums of per-slab Horner values weighed by z^lo (one
+// gather of the partial values); the linearisation and
+// the aggregated witness polynomials are built slab by slab; the division by (X - z) is a suffix scan whose
+// carry into a slab is the Horner value of everything above it (one gather of two values).  Same field
+// elements, same transcript, same commitments as on one GPU.
+static int commit_group(zkp_prover* pr, const zkp_poly_ref* polys, unsigned count, uint64_t* out_xy);
+static int openings_sharded(zkp_prover* pr, Transcript& tr, const fr ch[7], const fr& zc, const fr& zw,
+                            const zkp_poly_ref wp[4], const zkp_poly_ref& zp, uint64_t* comms, uint64_t* evals,
+                            uint8_t* proof_bytes, uint8_t* transcript_out) {
+    zkp_ctx* ctx = pr->ctx;
+    zkp_comm* cm = pr->comm;
+    const zkp_proving_key& key = pr->key;
+    const size_t n = pr->n, slab = pr->slab;
+    const unsigned G = cm ? (unsigned)cm->nranks : 1u, rank = cm ? (unsigned)cm->rank : 0u;
+    const bool last = rank + 1 == G;
+    const size_t lo = (size_t)rank * slab;
+    cudaStream_t st = ctx->stream;
+    // a rank's range of a replicated polynomial of `len` coefficients
+    auto part = [&](const zkp_poly_ref& p) {
+        const size_t hi = last ? p.len : (lo + slab < p.len ? lo + slab : p.len);
+        return ref(p.buf, p.off + (lo < p.len ? lo : p.len), hi > lo ? hi - lo : 0);
+    };
+    // ---- openings: 8 chunk slabs of t, 20 polynomials at z, 4 at z w
+    enum { E_T0 = 0, E_A = 4, E_B, E_C, E_D, E_S1, E_S2, E_S3, E_QARITH, E_QC, E_QL, E_QR,
+           E_QM, E_QO, E_QD, E_QRANGE, E_QLOGIC, E_QFIXED, E_QVAR, E_Z, E_S4,
+           E_AN, E_BN, E_DN, E_PERM, E_COUNT };
+    static_assert(E_COUNT == 28, "one evaluation launch");
+    const size_t tail = pr->srs->n - n;      // coefficients of t_4 at and beyond n: behind the last rank's chunk-3 slab
+    zkp_poly_ref ep[E_COUNT];
+    uint8_t which[E_COUNT];
+    memset(which, 0, sizeof which);
+    for (unsigned q = 0; q < 4; q++) ep[E_T0 + q] = ref(pr->TS, q * slab, slab + (q == 3 && last ? tail : 0));
+    for (unsigned j = 0; j < 4; j++) ep[E_A + j] = part(wp[j]);
+    ep[E_S1] = part(key.poly[S1]); ep[E_S2] = part(key.poly[S2]); ep[E_S3] = part(key.poly[S3]);
+    ep[E_QARITH] = part(key.poly[Q_ARITH]); ep[E_QC] = part(key.poly[Q_C]); ep[E_QL] = part(key.poly[Q_L]);
+    ep[E_QR] = part(key.poly[Q_R]); ep[E_QM] = part(key.poly[Q_M]); ep[E_QO] = part(key.poly[Q_O]);
+    ep[E_QD] = part(key.poly[Q_D]); ep[E_QRANGE] = part(key.poly[Q_RANGE]); ep[E_QLOGIC] = part(key.poly[Q_LOGIC]);
+    ep[E_QFIXED] = part(key.poly[Q_FIXED]); ep[E_QVAR] = part(key.poly[Q_VAR]); ep[E_Z] = part(zp);
+    ep[E_S4] = part(key.poly[S4]);
+    ep[E_AN] = part(wp[0]); ep[E_BN] = part(wp[1]); ep[E_DN] = part(wp[3]); ep[E_PERM] = part(zp);
+    for (unsigned j = E_AN; j < E_COUNT; j++) which[j] = 1;
+    uint64_t pts[8];
+    memcpy(pts, zc.l, 32);
+    memcpy(pts + 4, zw.l, 32);
+    fr_t* res = nullptr;
+    TRY(poly_eval2_launch(ctx, ep, which, E_COUNT, pts, &res));
+    // gather the partial values
+    const size_t blob = E_COUNT * sizeof(fr_t);
+    uint8_t* send = cm ? cm->gsend : reinterpret_cast<uint8_t*>(pr->YA->d);
+    uint8_t* recv = cm ? cm->grecv : reinterpret_cast<uint8_t*>(pr->YA->d + 64);
+    ZKP_CUDA(ctx, cudaMemcpyAsync(send, res, E_COUNT * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+    TRY(comm_allgather(cm, send, recv, blob, st));
+    uint8_t* hb = cm ? cm->hrecv : reinterpret_cast<uint8_t*>(ctx->pinned);
+    ZKP_CUDA(ctx, cudaMemcpyAsync(hb, recv, blob * G, cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(ctx, cudaStreamSynchronize(st));
+    const fr z_n = F::pow(zc, (uint64_t)n);
+    const fr zs = F::pow(zc, (uint64_t)slab), zws = F::pow(zw, (uint64_t)slab);
+    fr full[E_COUNT];
+    for (unsigned j = 0; j < E_COUNT; j++) full[j] = F::zero();
+    {
+        fr wz = F::one(), wzw = F::one();            // z^lo_s, (z w)^lo_s
+        for (unsigned s2 = 0; s2 < G; s2++) {
+            const uint64_t* pv = reinterpret_cast<const uint64_t*>(hb + blob * s2);
+            for (unsigned j = 0; j < E_COUNT; j++)
+                full[j] = F::add(full[j], F::mul(fr_load(pv + 4 * j), which[j] ? wzw : wz));
+            wz = F::mul(wz, zs); wzw = F::mul(wzw, zws);
+        }
+    }
+    fr t_eval = F::zero();
+    {
+        fr zq = F::one();
+        for (unsigned q = 0; q < 4; q++) { t_eval = F::add(t_eval, F::mul(zq, full[E_T0 + q])); zq = F::mul(zq, z_n); }
+    }
+    auto E = [&](int i) { return full[i]; };
+    const fr a = E(E_A), b = E(E_B), c = E(E_C), d = E(E_D);
+    const fr s1 = E(E_S1), s2 = E(E_S2), s3 = E(E_S3);
+    const fr qarith = E(E_QARITH), qc = E(E_QC), ql = E(E_QL), qr = E(E_QR);
+    const fr an = E(E_AN), bn = E(E_BN), dn = E(E_DN), pe = E(E_PERM);
+    fr sc[12];
+    {
+        fr ch8[8];
+        for (unsigned j = 0; j < 7; j++) ch8[j] = ch[j];
+        ch8[7] = zc;
+        const fr e15[15] = {a, b, c, d, an, bn, dn, s1, s2, s3, qarith, qc, ql, qr, pe};
+        linearization_scalars((uint64_t)n, ch8, e15, sc);
+    }
+    fr r_eval = F::zero();
+    {
+        static const int lin_eval[12] = {E_QM, E_QL, E_QR, E_QO, E_QD, E_QC, E_QRANGE, E_QLOGIC, E_QFIXED, E_QVAR, E_Z, E_S4};
+        for (unsigned j = 0; j < 12; j++) r_eval = F::add(r_eval, F::mul(sc[j], E(lin_eval[j])));
+    }
+    const fr ev[16] = {a, b, c, d, an, bn, dn, s1, s2, s3, qarith, qc, ql, qr, pe, r_eval};
+    static const char* const el[15] = {"a_eval", "b_eval", "c_eval", "d_eval", "a_next_eval", "b_next_eval",
+                                       "d_next_eval", "s_sigma_1_eval", "s_sigma_2_eval", "s_sigma_3_eval",
+                                       "q_arith_eval", "q_c_eval", "q_l_eval", "q_r_eval", "perm_eval"};
+    for (unsigned j = 0; j < 15; j++) tr.append_scalar(el[j], ev[j]);
+    tr.append_scalar("t_eval", t_eval);
+    tr.append_scalar("r_eval", r_eval);
+
+    // ---- r(X), the aggregated polynomials and their quotients by (X - z), (X - z w): this rank's range only
+    const size_t agg_len = pr->srs->n > n + 3 ? pr->srs->n : n + 3;     // <= n + 8 here
+    const size_t hiR = last ? n + 3 : lo + slab, hiA = last ? agg_len : lo + slab, hiS = last ? n + 3 : lo + slab;
+    uint64_t scl[16 * 4];
+    {
+        static const int lin_key[10] = {Q_M, Q_L, Q_R, Q_O, Q_D, Q_C, Q_RANGE, Q_LOGIC, Q_FIXED, Q_VAR};
+        zkp_poly_ref lr[12];
+        for (unsigned j = 0; j < 10; j++) lr[j] = part(key.poly[lin_key[j]]);
+        lr[10] = part(zp);
+        lr[11] = part(key.poly[S4]);
+        for (unsigned j = 0; j < 12; j++) fr_store(scl + 4 * j, sc[j]);
+        TRY(zkp_poly_lincomb_dev(ctx, lr, scl, 12, pr->R, lo, hiR - lo));
+    }
+    const fr v1 = tr.challenge_scalar("v_challenge");
+    const fr v2 = tr.challenge_scalar("v_challenge");     // nothing is appended in between (src/prover.rs:435-450)
+    {
+        // main part [lo, min(hi, n)): the four chunk slabs + the replicated polynomials' slabs
+        zkp_poly_ref ar[12] = {ref(pr->TS, 0, slab), ref(pr->TS, slab, slab), ref(pr->TS, 2 * slab, slab),
+                               ref(pr->TS, 3 * slab, slab), ref(pr->R, lo, slab), ref(wp[0].buf, wp[0].off + lo, slab),
+                               ref(wp[1].buf, wp[1].off + lo, slab), ref(wp[2].buf, wp[2].off + lo, slab),
+                               ref(wp[3].buf, wp[3].off + lo, slab), ref(key.poly[S1].buf, key.poly[S1].off + lo, slab),
+                               ref(key.poly[S2].buf, key.poly[S2].off + lo, slab),
+                               ref(key.poly[S3].buf, key.poly[S3].off + lo, slab)};
+        fr as[12];
+        as[0] = F::one(); as[1] = z_n; as[2] = F::sqr(z_n); as[3] = F::mul(as[2], z_n); as[4] = v1;
+        for (unsigned j = 5; j < 12; j++) as[j] = F::mul(as[j - 1], v1);
+        for (unsigned j = 0; j < 12; j++) fr_store(scl + 4 * j, as[j]);
+        TRY(zkp_poly_lincomb_dev(ctx, ar, scl, 12, pr->AGG, lo, slab));
+        if (last) {
+            // tail [n, agg_len): z^3n * (t_4's coefficients beyond n, behind the chunk-3 slab) + v r + v^2 a + .. + v^5 d
+            zkp_poly_ref tr6[6] = {ref(pr->TS, 4 * slab, tail), ref(pr->R, n, 3), ref(wp[0].buf, wp[0].off + n, 2),
+                                   ref(wp[1].buf, wp[1].off + n, 2), ref(wp[2].buf, wp[2].off + n, 2),
+                                   ref(wp[3].buf, wp[3].off + n, 2)};
+            const fr ts[6] = {as[3], as[4], as[5], as[6], as[7], as[8]};
+            for (unsigned j = 0; j < 6; j++) fr_store(scl + 4 * j, ts[j]);
+            TRY(zkp_poly_lincomb_dev(ctx, tr6, scl, 6, pr->AGG, n, agg_len - n));
+        }
+        const zkp_poly_ref br[4] = {part(zp), part(wp[0]), part(wp[1]), part(wp[3])};
+        fr bs[4];
+        bs[0] = F::one();
+        for (unsigned j = 1; j < 4; j++) bs[j] = F::mul(bs[j - 1], v2);
+        for (unsigned j = 0; j < 4; j++) fr_store(scl + 4 * j, bs[j]);
+        TRY(zkp_poly_lincomb_dev(ctx, br, scl, 4, pr->SAGG, lo, hiS - lo));
+    }
+    // Horner value of each rank's range -> the carries of the two divisions
+    fr carry1 = F::zero(), carry2 = F::zero();
+    if (G > 1) {
+        const zkp_poly_ref hp[2] = {ref(pr->AGG, lo, hiA - lo), ref(pr->SAGG, lo, hiS - lo)};
+        const uint8_t hw[2] = {0, 1};
+        TRY(poly_eval2_launch(ctx, hp, hw, 2, pts, &res));
+        ZKP_CUDA(ctx, cudaMemcpyAsync(send, res, 2 * sizeof(fr_t), cudaMemcpyDeviceToDevice, st));
+        TRY(comm_allgather(cm, send, recv, 2 * sizeof(fr_t), st));
+        ZKP_CUDA(ctx, cudaMemcpyAsync(hb, recv, 2 * sizeof(fr_t) * G, cudaMemcpyDeviceToHost, st));
+        ZKP_CUDA(ctx, cudaStreamSynchronize(st));
+        // c_s = P_(s+1) + z^(len_(s+1)) c_(s+1), from the top; len of the last range differs between the two
+        const fr zlast1 = F::pow(zc, (uint64_t)(agg_len - (size_t)(G - 1) * slab));
+        const fr zlast2 = F::pow(zw, (uint64_t)(n + 3 - (size_t)(G - 1) * slab));
+        for (unsigned s2 = G - 1; s2 > rank; s2--) {
+            const uint64_t* pv = reinterpret_cast<const uint64_t*>(hb + 2 * sizeof(fr_t) * s2);
+            carry1 = F::add(fr_load(pv), F::mul(s2 == G - 1 ? zlast1 : zs, carry1));
+            carry2 = F::add(fr_load(pv + 4), F::mul(s2 == G - 1 ? zlast2 : zws, carry2));
+        }
+    }
+    {
+        // [0, a_(lo+1) .. a_(hi-1), carry] / (X - z) -> w_lo .. w_(hi-1)   (the last rank has no carry element)
+        uint64_t* hp2 = reinterpret_cast<uint64_t*>(ctx->pinned);
+        memset(hp2, 0, 32);
+        fr_store(hp2 + 4, carry1);
+        fr_store(hp2 + 8, carry2);
+        ZKP_CUDA(ctx, cudaMemcpyAsync(pr->AGG->d + lo, hp2, sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        ZKP_CUDA(ctx, cudaMemcpyAsync(pr->SAGG->d + lo, hp2, sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        if (!last) {
+            ZKP_CUDA(ctx, cudaMemcpyAsync(pr->AGG->d + hiA, hp2 + 4, sizeof(fr_t), cudaMemcpyHostToDevice, st));
+            ZKP_CUDA(ctx, cudaMemcpyAsync(pr->SAGG->d + hiS, hp2 + 8, sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        }
+        const size_t l1 = hiA - lo + (last ? 0 : 1), l2 = hiS - lo + (last ? 0 : 1);
+        TRY(zkp_poly_div_linear_dev(ctx, ref(pr->AGG, lo, l1), zc.l, pr->WZ, lo));
+        TRY(zkp_poly_div_linear_dev(ctx, ref(pr->SAGG, lo, l2), zw.l, pr->WZW, lo));
+        const fr_t* ptrs[2] = {pr->WZ->d + lo, pr->WZW->d + lo};
+        const size_t lens[2] = {l1 - 1, l2 - 1}, offs[2] = {lo, lo};
+        int ovf[2];
+        TRY(msm_run_batch_ex(ctx, cm, pr->srs, ptrs, lens, offs, 2, reinterpret_cast<g1_affine*>(comms + 12 * 9), ovf));
+        if (ovf[0] || ovf[1]) return ZKP_ERR_DEGREE;
+    }
+    for (unsigned j = 0; j < 16; j++) fr_store(evals + 4 * j, ev[j]);
+    if (proof_bytes) {
+        for (unsigned j = 0; j < 11; j++) g1_compress(comms + 12 * j, proof_bytes + 48 * j);
+        static const int wire_order[16] = {0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 7, 8, 9, 15, 14};
+        for (unsigned j = 0; j < 16; j++) fr_bytes(ev[wire_order[j]], proof_bytes + 48 * 11 + 32 * j);
+    }
+    if (transcript_out) tr.save(transcript_out);
+    return ZKP_OK;
+}
+
 static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_t* wires_host, const zkp_buf* wires_dev,
                  const uint64_t* pi_host, const zkp_buf* pi_dev, const uint64_t* blinders, uint64_t* comms,
                  uint64_t* evals, uint8_t* proof_bytes, uint8_t* transcript_out) {
@@ -248,6 +452,7 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
 
     // round 3: quotient on the 8n coset (src/prover.rs:201-287, quotient_poly.rs)
     nvtxRangePop(); nvtxRangePushA("round 3: quotient");
+    bool slab_openings = false;
     fr ch[7];
     ch[0] = tr.challenge_scalar("alpha");
     ch[1] = beta;
@@ -287,14 +492,53 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
         TRY(coset8_inverse_local(ctx, pr->TL->d, k, pr->u0, pr->nloc));
         TRY(comm_exchange_slabs(pr->comm, pr->TL->d, pr->YA->d, n, pr->nloc, ctx->stream));
         TRY(coset8_combine(ctx, pr->YA->d, pr->TS->d, pr->slab, k));
-        for (unsigned q = 0; q < 8; q++)
-            TRY(comm_allgather(pr->comm, pr->TS->d + q * pr->slab, pr->T->d + q * n, pr->slab * sizeof(fr_t), ctx->stream));
+        // rounds 4 / 5 work on the slabs where they lie unless the SRS is long enough for t_4 to reach beyond its
+        // first eight tail coefficients (then: gather t(X) chunk by chunk and continue as one GPU would)
+        slab_openings = pr->srs->n <= n + 8;
+        if (!slab_openings)
+            for (unsigned q = 0; q < 8; q++)
+                TRY(comm_allgather(pr->comm, pr->TS->d + q * pr->slab, pr->T->d + q * n, pr->slab * sizeof(fr_t), ctx->stream));
     } else {
         TRY(zkp_quotient_dev(ctx, k8, &qa, pr->T, 0));
         TRY(ntt_run(ctx, pr->T->d, 0, n8, pr->T->d, 0, k8, true, true, 1));  // coset_idft -> t coefficients
     }
     const zkp_poly_ref tq[4] = {ref(pr->T, 0, n), ref(pr->T, n, n), ref(pr->T, 2 * n, n), ref(pr->T, 3 * n, 5 * n)};
-    TRY(commit_group(pr, tq, 4, comms + 12 * 5));
+    if (slab_openings) {
+        // This rank holds coefficients [lo, lo + slab) of every n-chunk of t.  t_4 = chunk 3 followed by the few
+        // coefficients of chunk 4 that still meet an SRS power (they live on rank 0 and move to the last rank,
+        // behind its chunk-3 slab, where the SRS continues); everything else of chunks 4 .. 7 must be zero --
+        // commit's degree check -- which every rank verifies on its own slabs.  One small gather carries both.
+        zkp_comm* cm = pr->comm;
+        const unsigned G = cm ? (unsigned)cm->nranks : 1u, rank = cm ? (unsigned)cm->rank : 0u;
+        const size_t slab = pr->slab, lo = (size_t)rank * slab, tail = pr->srs->n - n;   // <= 8
+        const bool last = rank + 1 == G;
+        uint8_t* send = cm ? cm->gsend : reinterpret_cast<uint8_t*>(pr->YA->d);
+        uint8_t* recv = cm ? cm->grecv : reinterpret_cast<uint8_t*>(pr->YA->d + 64);
+        uint8_t* hb = cm ? cm->hrecv : reinterpret_cast<uint8_t*>(ctx->pinned);
+        const size_t blob = 9 * sizeof(fr_t);             // [8 head coefficients of chunk 4][flag word]
+        ZKP_CUDA(ctx, cudaMemsetAsync(send, 0, blob, ctx->stream));
+        ZKP_CUDA(ctx, cudaMemcpyAsync(send, pr->TS->d + 4 * slab, 8 * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        const size_t skip = rank == 0 ? tail : 0;
+        any_nonzero_kernel<<<(unsigned)((4 * slab - skip + 255) / 256), 256, 0, ctx->stream>>>(
+            pr->TS->d + 4 * slab + skip, 4 * slab - skip, reinterpret_cast<uint32_t*>(send + 8 * sizeof(fr_t)));
+        ZKP_LAUNCHED(ctx);
+        TRY(comm_allgather(cm, send, recv, blob, ctx->stream));
+        ZKP_CUDA(ctx, cudaMemcpyAsync(hb, recv, blob * G, cudaMemcpyDeviceToHost, ctx->stream));
+        if (last && G > 1)   // rank 0's head of chunk 4 -> behind this rank's chunk-3 slab (G == 1: already there)
+            ZKP_CUDA(ctx, cudaMemcpyAsync(pr->TS->d + 4 * slab, recv, 8 * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (unsigned r2 = 0; r2 < G; r2++)
+            if (*reinterpret_cast<const uint32_t*>(hb + blob * r2 + 8 * sizeof(fr_t))) return ZKP_ERR_DEGREE;
+        const fr_t* ptrs[4];
+        size_t lens[4], offs[4];
+        int ovf[4];
+        for (unsigned q = 0; q < 4; q++) { ptrs[q] = pr->TS->d + q * slab; lens[q] = slab; offs[q] = lo; }
+        if (last) lens[3] = slab + tail;
+        TRY(msm_run_batch_ex(ctx, cm, pr->srs, ptrs, lens, offs, 4, reinterpret_cast<g1_affine*>(comms + 12 * 5), ovf));
+        for (unsigned q = 0; q < 4; q++) if (ovf[q]) return ZKP_ERR_DEGREE;
+    } else {
+        TRY(commit_group(pr, tq, 4, comms + 12 * 5));
+    }
     static const char* const tl[4] = {"t_low", "t_mid", "t_high", "t_4"};
     for (unsigned j = 0; j < 4; j++) tr.append_commitment(tl[j], comms + 12 * (5 + j));
 
@@ -302,6 +546,8 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
     nvtxRangePop(); nvtxRangePushA("rounds 4-5: openings");
     const fr zc = tr.challenge_scalar("z_challenge");
     const fr zw = F::mul(zc, fr_load(key.generator));
+    if (slab_openings)
+        return openings_sharded(pr, tr, ch, zc, zw, wp, zp, comms, evals, proof_bytes, transcript_out);
     // Every opening of the proof in ONE batched launch and one read-back: the 12 evaluations at z, the 4
     // at z w, and the nine linearisation polynomials not among them at z -- r(X) = sum_j sc_j p_j(X) is
     // linear in the p_j, so r(z) = sum_j sc_j p_j(z) needs no evaluation of r itself

@@ -276,7 +276,8 @@ __global__ void msm_scatter_kernel(const __grid_constant__ MsmBatch batch, const
                                    unsigned W, uint32_t stride, uint32_t B, uint32_t* cursor, uint32_t* sorted) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned pb = blockIdx.y;
-    if (i >= n || i >= batch.len[pb]) return;
+    // (stride is the SRS length: scalars that meet no SRS power produced no digits -- msm_digits_kernel)
+    if (i >= n || i >= batch.len[pb] || (uint64_t)batch.off[pb] + i >= stride) return;
     digits += (size_t)pb * W * n; sorted += (size_t)pb * W * n; cursor += (size_t)pb * B;
     for (unsigned w = 0; w < W; w++) {
         const uint32_t enc = digits[(size_t)w * n + i];

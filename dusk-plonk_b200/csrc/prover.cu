@@ -707,9 +707,12 @@ int zkp_quotient_range_dev(zkp_ctx* ctx, unsigned k8, const zkp_quotient_args* q
     return ZKP_OK;
 }
 
-int zkp_poly_eval2_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, const uint8_t* which, unsigned count,
-                       const uint64_t points[8], uint64_t* out) {
-    if (!ctx || !polys || !points || !out || count == 0 || count > EV_MAX) return ZKP_ERR_INVALID;
+}  // extern "C"
+
+// launches only: the count results stay on the device (*res_dev, valid until the context's next scratch use)
+int zkp::poly_eval2_launch(zkp_ctx* ctx, const zkp_poly_ref* polys, const uint8_t* which, unsigned count,
+                           const uint64_t points[8], fr_t** res_dev) {
+    if (!ctx || !polys || !points || !res_dev || count == 0 || count > EV_MAX) return ZKP_ERR_INVALID;
     size_t maxlen = 0;
     for (unsigned i = 0; i < count; i++) {
         if (!CHECK_REF(polys[i]) || (which && which[i] > 1)) return ZKP_ERR_INVALID;
@@ -748,6 +751,18 @@ int zkp_poly_eval2_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, const uint8_t* w
     ZKP_LAUNCHED(ctx);
     eval_final_kernel<<<count, EV_T, 0, ctx->stream>>>(a, res);
     ZKP_LAUNCHED(ctx);
+    *res_dev = res;
+    return ZKP_OK;
+}
+
+extern "C" {
+
+int zkp_poly_eval2_dev(zkp_ctx* ctx, const zkp_poly_ref* polys, const uint8_t* which, unsigned count,
+                       const uint64_t points[8], uint64_t* out) {
+    if (!out) return ZKP_ERR_INVALID;
+    fr_t* res = nullptr;
+    int rc = poly_eval2_launch(ctx, polys, which, count, points, &res);
+    if (rc) return rc;
     fr_t* h = reinterpret_cast<fr_t*>(ctx->pinned);
     ZKP_CUDA(ctx, cudaMemcpyAsync(h, res, count * sizeof(fr_t), cudaMemcpyDeviceToHost, ctx->stream));
     ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

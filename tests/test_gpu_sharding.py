@@ -73,7 +73,7 @@ def test_coset8_ntt_is_the_8n_coset_dft(ctx, cport, k):
         assert np.array_equal(part.download(), dst.download()[4 * n:7 * n])
 
 
-@pytest.mark.parametrize("name", ["range", "readme", "logic", "synthetic12", "synthetic16"])
+@pytest.mark.parametrize("name", ["range", "readme", "logic", "chain60", "synthetic12", "synthetic16"])
 def test_native_sharded_prover_world1_bit_exact(ctx, name):
     """The multi-GPU code path of the native driver (commit through zkp_commit_batch_sharded_dev, the quotient on
     cosets, coset-wise inverse + combination) on ONE rank: key commitments and the 1040 proof bytes equal the
@@ -91,8 +91,9 @@ def test_native_sharded_prover_world1_bit_exact(ctx, name):
         k = int(name[9:])
         circ, label = synthetic_circuit(k), b"plonk"
     else:
+        # chain60: m = 60 gates in n = 64, so trim keeps 2 n + 7 powers -- the rounds-4/5 path that gathers t(X)
         comp = {"range": lambda: circuits.range_circuit(424242), "readme": circuits.readme_circuit,
-                "logic": circuits.logic_curve_circuit}[name]()
+                "logic": circuits.logic_curve_circuit, "chain60": lambda: circuits.arithmetic_chain(60)}[name]()
         circ, label = SynthesizedCircuit.from_composer(comp), b"demo"
         k = circ.n.bit_length() - 1
     bl = [rng.fr() for _ in range(11)]
