@@ -241,7 +241,8 @@ def workload_config(args, world=1):
                         "slab exchange for the inverse transform)" % world,
                "compile": "ONE compile over %d GPUs, commits sharded by SRS ranges" % world,
                "msm": "ONE MSM over %d GPUs: SRS ranges + 96-byte partial-sum all-gather" % world,
-               "ntt": "ONE transform over %d GPUs: four-step NTT, one NCCL all-to-all" % world}[args.workload]
+               "ntt": "ONE transform over %d GPUs: four-step NTT (twiddle fused into the transpose), one NCCL "
+                      "all-to-all issued by the library on its own stream" % world}[args.workload]
     else:
         par = "%d independent job(s), one per GPU, no data-path collective" % world
     if args.workload in ("prove", "compile"):
@@ -367,7 +368,7 @@ def main():
         import torch
         from dusk_plonk_b200.sharding import Communicator, FourStepNtt, ShardedPlonkParams
         comm = Communicator(torch.device("cuda", local_rank))
-        if args.workload in ("prove", "compile"):
+        if args.workload in ("prove", "compile", "ntt"):
             ncomm = z.NativeComm.from_torch_distributed(ctx)
     # seeds: independent jobs differ per rank, a sharded job is the same job on every rank
     jr = 0 if shard or world == 1 else rank
@@ -431,10 +432,10 @@ def main():
     else:
         host_data = pinned_copy(z, random_fr_raw_limbs(8349 + jr, n))
         if shard:
-            fs = FourStepNtt(ctx, comm, args.logn)
+            fs = FourStepNtt(ctx, ncomm, args.logn)      # all-to-all by the library's own NCCL communicator
             fs.scatter_input(host_data)
             step = lambda: fs.run()
-            host_out = np.zeros((n, 4), dtype=np.uint64)
+            host_out = z.pinned_empty((n, 4), np.uint64)
 
             def e2e_step():
                 fs.scatter_input(host_data)

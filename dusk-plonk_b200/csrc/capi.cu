@@ -183,6 +183,42 @@ int zkp_scale_matrix_dev(zkp_ctx* ctx, zkp_buf* data, size_t off, size_t rows, s
     return ntt_scale_matrix(ctx, data->d + off, rows, cols, a0, b1, b2, mode);
 }
 
+int zkp_twiddle_transpose_dev(zkp_ctx* ctx, const zkp_buf* in, size_t in_off, zkp_buf* out, size_t out_off, size_t rows,
+                              size_t cols, size_t a0, unsigned k, int inverse) {
+    if (!ctx || !in || !out) return ZKP_ERR_INVALID;
+    const size_t total = rows * cols;
+    if (in_off + total > in->n || out_off + total > out->n || in->d + in_off == out->d + out_off) return ZKP_ERR_INVALID;
+    return ntt_twiddle_transpose(ctx, in->d + in_off, out->d + out_off, rows, cols, a0, k, inverse != 0);
+}
+
+/* strided host <-> device copies: `height` rows of `width` Fr; the host side has a row pitch of `host_pitch` Fr,
+ * the device side is dense.  (A rank's column slab of a natural-order host vector) */
+int zkp_buf_upload_2d(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const uint64_t* src, size_t width, size_t height,
+                      size_t host_pitch) {
+    if (!ctx || !dst || (!src && width * height) || dst_off + width * height > dst->n || host_pitch < width)
+        return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    if (width * height == 0) return ZKP_OK;
+    ZKP_CUDA(ctx, cudaMemcpy2DAsync(dst->d + dst_off, width * sizeof(fr_t), src, host_pitch * sizeof(fr_t),
+                                    width * sizeof(fr_t), height, cudaMemcpyHostToDevice, ctx->stream));
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKP_OK;
+}
+
+int zkp_buf_download_2d(zkp_ctx* ctx, const zkp_buf* src, size_t src_off, uint64_t* dst, size_t width, size_t height,
+                        size_t host_pitch) {
+    if (!ctx || !src || (!dst && width * height) || src_off + width * height > src->n || host_pitch < width)
+        return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    if (width * height == 0) return ZKP_OK;
+    ZKP_CUDA(ctx, cudaMemcpy2DAsync(dst, host_pitch * sizeof(fr_t), src->d + src_off, width * sizeof(fr_t),
+                                    width * sizeof(fr_t), height, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKP_OK;
+}
+
 size_t zkp_buf_len(const zkp_buf* buf) { return buf ? buf->n : 0; }
 
 int zkp_buf_upload(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const uint64_t* src, size_t n) {

@@ -175,6 +175,18 @@ int zkp_comm_destroy(zkp_comm* cm) {
 int zkp_comm_rank(const zkp_comm* cm) { return cm ? cm->rank : 0; }
 int zkp_comm_size(const zkp_comm* cm) { return cm ? cm->nranks : 1; }
 
+/* all-to-all of equal blocks between device vectors: block p of src goes to rank p, block r of dst comes from
+ * rank r (count Fr elements each); on the context's stream, no host synchronisation */
+int zkp_comm_all_to_all_dev(zkp_comm* cm, const zkp_buf* src, size_t src_off, zkp_buf* dst, size_t dst_off, size_t count) {
+    if (!cm || !src || !dst) return ZKP_ERR_INVALID;
+    const size_t G = (size_t)cm->nranks;
+    if (src_off + G * count > src->n || dst_off + G * count > dst->n) return ZKP_ERR_INVALID;
+    int rc;
+    if ((rc = set_device(cm->ctx))) return rc;
+    // one "coset" of G * count elements whose slab p goes to rank p: exactly comm_exchange_slabs with local = 1
+    return comm_exchange_slabs(cm, src->d + src_off, dst->d + dst_off, G * count, 1, cm->ctx->stream);
+}
+
 /* collectives issued / bytes this rank put on the wire since creation (bench.py reports them) */
 int zkp_comm_stats(const zkp_comm* cm, uint64_t* collectives, uint64_t* bytes_sent) {
     if (!cm || !collectives || !bytes_sent) return ZKP_ERR_INVALID;

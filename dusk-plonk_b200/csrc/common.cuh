@@ -18,6 +18,7 @@ namespace zkp {
 
 struct NttDomain;  // ntt.cu
 struct Coset8Tab;  // ntt.cu
+struct TwTab;      // ntt.cu
 struct MsmScratch; // msm.cu
 
 }  // namespace zkp
@@ -47,6 +48,7 @@ struct zkp_ctx {
     uint64_t msm_points = 0;  // points summed by msm_run since creation (roofline accounting)
     unsigned msm_window = 0;
     std::map<unsigned, zkp::NttDomain*> domains;
+    std::map<unsigned, zkp::TwTab*> twtabs;       // four-step twiddle tables per (k, direction)
     std::map<unsigned, zkp::Coset8Tab*> coset8;   // key 8 k + u: scaling tables of coset u of the 8n domain
     zkp::fr_t* ntt_scratch = nullptr;
     size_t ntt_scratch_n = 0;
@@ -136,6 +138,8 @@ int coset8_inverse_local(zkp_ctx* ctx, fr_t* data, unsigned k, unsigned first, u
 int ntt_elements(zkp_ctx* ctx, unsigned k, fr_t* out);
 fr_t fft_constant_host(unsigned k, int kind);
 int ntt_permute(zkp_ctx* ctx, const fr_t* in, fr_t* out, size_t A, size_t B, size_t w);
+int ntt_twiddle_transpose(zkp_ctx* ctx, const fr_t* in, fr_t* out, size_t rows, size_t cols, size_t a0, unsigned k,
+                          bool inverse);
 int ntt_scale_matrix(zkp_ctx* ctx, fr_t* data, size_t rows, size_t cols, size_t a0, const fr_t& base1,
                      const fr_t& base2, int mode);
 

@@ -124,6 +124,8 @@ __device__ __forceinline__ fr_t ld_fr(const fr_t* p);
 __device__ __forceinline__ fr_t ldg_fr(const fr_t* p);
 __device__ __forceinline__ void st_fr(fr_t* p, const fr_t& v);
 
+struct TwTab { fr_t* lo = nullptr; fr_t* hi = nullptr; unsigned h = 0; };   // four-step twiddles (below)
+
 struct Coset8Tab {
     fr_t* f_lo = nullptr;   // h^e,           e < 2^min(k,10)
     fr_t* f_hi = nullptr;   // h^(e << 10)
@@ -228,6 +230,8 @@ void ntt_free_domains(zkp_ctx* ctx) {
         delete t;
     }
     ctx->coset8.clear();
+    for (auto& kv : ctx->twtabs) { cudaFree(kv.second->lo); cudaFree(kv.second->hi); delete kv.second; }
+    ctx->twtabs.clear();
     for (auto& kv : ctx->domains) {
         NttDomain* d = kv.second;
         cudaFree(d->tw); cudaFree(d->g_lo); cudaFree(d->g_hi); cudaFree(d->gi_lo); cudaFree(d->gi_hi);
@@ -551,6 +555,62 @@ __global__ void __launch_bounds__(128) scale_matrix_kernel(fr_t* data, size_t ro
         st_fr(row + b, ld_fr(row + b) * f);
         f = f * ratio;
     }
+}
+
+// Four-step twiddle fused into the transpose: out[b][a] = in[a][b] * w_N^(+-(a0 + a) b), a < rows, b < cols.
+// The exponent e = (a0 + a) b < N indexes a two-level table (w^e = lo[e & (2^h - 1)] hi[e >> h], h = ceil(k / 2)):
+// two multiplications per element instead of the ~5 of per-thread powers, and one pass over the data
+// instead of two (scale, then transpose).
+static int get_twtab(zkp_ctx* ctx, unsigned k, bool inverse, TwTab** out) {
+    const unsigned key = 64 * 8 + k * 2 + (inverse ? 1 : 0);     // shares the coset8 map's key space above 8 * 64
+    auto it = ctx->twtabs.find(key);
+    if (it != ctx->twtabs.end()) { *out = it->second; return ZKP_OK; }
+    TwTab* t = new TwTab();
+    t->h = (k + 1) / 2;
+    const fr_t w = fft_constant_host(k, inverse ? 1 : 0);
+    int rc;
+    if ((rc = build_table(ctx, &t->lo, (size_t)1 << t->h, w, fr_t::one()))) return rc;
+    if ((rc = build_table(ctx, &t->hi, (size_t)1 << (k - t->h), pow_u64(w, 1ull << t->h), fr_t::one()))) return rc;
+    ctx->twtabs[key] = t;
+    *out = t;
+    return ZKP_OK;
+}
+
+__global__ void __launch_bounds__(256) twiddle_transpose_kernel(const fr_t* in, fr_t* out, size_t A, size_t B, size_t a0,
+                                                               const fr_t* lo, const fr_t* hi, unsigned h) {
+    // in: A x B row-major (a rows), out: B x A; 16 x 16 tiles through shared memory, both sides coalesced
+    __shared__ uint4 t_lo[16][17], t_hi[16][17];
+    const unsigned tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const size_t b0 = (size_t)blockIdx.x * 16, r0 = (size_t)blockIdx.y * 16;
+    if (r0 + ty < A && b0 + tx < B) {
+        const size_t a = r0 + ty, b = b0 + tx;
+        fr_t v = ld_fr(in + a * B + b);
+        const size_t e = (a0 + a) * b;
+        v = v * (ldg_fr(lo + (e & (((size_t)1 << h) - 1))) * ldg_fr(hi + (e >> h)));
+        t_lo[ty][tx] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        t_hi[ty][tx] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    }
+    __syncthreads();
+    if (b0 + ty < B && r0 + tx < A) {
+        uint4* q = reinterpret_cast<uint4*>(out + (b0 + ty) * A + r0 + tx);
+        q[0] = t_lo[tx][ty];
+        q[1] = t_hi[tx][ty];
+    }
+}
+
+int ntt_twiddle_transpose(zkp_ctx* ctx, const fr_t* in, fr_t* out, size_t rows, size_t cols, size_t a0, unsigned k,
+                          bool inverse) {
+    int rc;
+    if ((rc = set_device(ctx))) return rc;
+    if (rows == 0 || cols == 0) return ZKP_OK;
+    if (k > 28 || (a0 + rows - 1) * (cols - 1) >= ((size_t)1 << k)) return ZKP_ERR_INVALID;
+    TwTab* t;
+    if ((rc = get_twtab(ctx, k, inverse, &t))) return rc;
+    ProfScope prof(ctx, "ntt");
+    dim3 grid((unsigned)((cols + 15) / 16), (unsigned)((rows + 15) / 16));
+    twiddle_transpose_kernel<<<grid, 256, 0, ctx->stream>>>(in, out, rows, cols, a0, t->lo, t->hi, t->h);
+    ZKP_LAUNCHED(ctx);
+    return ZKP_OK;
 }
 
 int ntt_permute(zkp_ctx* ctx, const fr_t* in, fr_t* out, size_t A, size_t B, size_t w) {

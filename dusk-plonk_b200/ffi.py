@@ -46,6 +46,8 @@ SIGNATURES = {
     "zkp_buf_upload": (_int, [_vp, _vp, _sz, _vp, _sz]),
     "zkp_buf_download": (_int, [_vp, _vp, _sz, _vp, _sz]),
     "zkp_buf_wrap": (_int, [_vp, _vp, _sz, ctypes.POINTER(_vp)]),
+    "zkp_buf_upload_2d": (_int, [_vp, _vp, _sz, _vp, _sz, _sz, _sz]),
+    "zkp_buf_download_2d": (_int, [_vp, _vp, _sz, _vp, _sz, _sz, _sz]),
     "zkp_permute_dev": (_int, [_vp, _vp, _sz, _vp, _sz, _sz, _sz, _sz]),
     "zkp_scale_matrix_dev": (_int, [_vp, _vp, _sz, _sz, _sz, _sz, _vp, _vp, _int]),
     "zkp_buf_zero": (_int, [_vp, _vp, _sz, _sz]),
@@ -142,6 +144,8 @@ SIGNATURES.update({
     "zkp_comm_destroy": (_int, [_vp]),
     "zkp_comm_rank": (_int, [_vp]),
     "zkp_comm_size": (_int, [_vp]),
+    "zkp_comm_all_to_all_dev": (_int, [_vp, _vp, _sz, _vp, _sz, _sz]),
+    "zkp_twiddle_transpose_dev": (_int, [_vp, _vp, _sz, _vp, _sz, _sz, _sz, _sz, _uint, _int]),
     "zkp_comm_stats": (_int, [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "zkp_commit_batch_sharded_dev": (_int, [_vp, _vp, _vp, ctypes.POINTER(PolyRef), _uint, _vp, ctypes.POINTER(_int)]),
     "zkp_coset8_ntt_dev": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _uint, _uint, _uint]),
@@ -363,6 +367,13 @@ class Context:
         self.check(self.lib.zkp_commit_batch_sharded_dev(self.h, comm.h if comm is not None else None, srs.h, arr,
                                                          len(refs), _ptr(out), st))
         return out, list(st)
+
+    def twiddle_transpose(self, src, src_off, dst, dst_off, rows, cols, a0, k, inverse):
+        """dst[b][a] = src[a][b] * w_N^(+-(a0 + a) b): the four-step twiddle fused into the transpose."""
+        sb, so = _base(src)
+        db, do = _base(dst)
+        self.check(self.lib.zkp_twiddle_transpose_dev(self.h, sb.h, so + src_off, db.h, do + dst_off, rows, cols, a0, k,
+                                                      int(inverse)))
 
     def coset8_ntt(self, src, src_off, len_in, dst, dst_off, k, first, count):
         """dst[(u - first) n + m] = p(g w_8n^u w_n^m): the polynomial's values on whole cosets of the 8n domain."""
@@ -670,6 +681,12 @@ class NativeComm:
         box = [cls.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         return cls(ctx, rank, world, box[0])
+
+    def all_to_all(self, src, dst, count):
+        """Block p of ``src`` -> rank p, block r of ``dst`` <- rank r (``count`` Fr each), on the context's stream."""
+        sb, so = _base(src)
+        db, do = _base(dst)
+        self.ctx.check(self.ctx.lib.zkp_comm_all_to_all_dev(self.h, sb.h, so, db.h, do, count))
 
     def stats(self):
         c, b = ctypes.c_uint64(), ctypes.c_uint64()

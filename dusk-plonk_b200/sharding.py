@@ -8,6 +8,8 @@ crosses NVLink: the exchange is latency only.  ``ShardedPlonkParams`` is a drop-
 ``PlonkParams`` (same ``commit`` / ``commit_or_default`` / ``trim``), so ``PlonkKey.compile``
 and ``Prover.create_proof`` run unchanged and every rank derives the same transcript.
 """
+import ctypes
+
 import numpy as np
 
 from .ffi import BufferView
@@ -177,25 +179,39 @@ class FourStepNtt:
         assert self.C % G == 0 and self.R % G == 0, "world size must divide both factors"
         self.Cl, self.Rl = self.C // G, self.R // G
         self.nloc = (1 << k) // G
-        dev = torch_device if torch_device is not None else torch.device("cuda", ctx.device)
-        # two ping-pong slabs that NCCL and the kernels both address
-        self.ta = torch.empty(self.nloc * 4, dtype=torch.int64, device=dev)
-        self.tb = torch.empty(self.nloc * 4, dtype=torch.int64, device=dev)
-        self.a = ctx.wrap(self.ta.data_ptr(), self.nloc)
-        self.b = ctx.wrap(self.tb.data_ptr(), self.nloc)
+        # two ping-pong slabs.  With the library's own communicator (``ffi.NativeComm``: NCCL inside
+        # libzkp_b200.so, the all-to-all is queued on the context's stream, no host synchronisation) or on one
+        # rank they are plain device vectors; with the torch communicator NCCL addresses them as tensors
+        self.native = hasattr(comm, "h") or not hasattr(comm, "dist")
+        if self.native:
+            self.a, self.b = ctx.alloc(self.nloc), ctx.alloc(self.nloc)
+        else:
+            dev = torch_device if torch_device is not None else torch.device("cuda", ctx.device)
+            self.ta = torch.empty(self.nloc * 4, dtype=torch.int64, device=dev)
+            self.tb = torch.empty(self.nloc * 4, dtype=torch.int64, device=dev)
+            self.a = ctx.wrap(self.ta.data_ptr(), self.nloc)
+            self.b = ctx.wrap(self.tb.data_ptr(), self.nloc)
 
     # ---- host <-> device placement (natural-order host vector)
     def scatter_input(self, host):
-        """host: (N, 4) uint64 natural order -> in_buf [c_loc][r] of this rank."""
+        """host: (N, 4) uint64 natural order -> in_buf [c_loc][r] of this rank: one strided copy of the rank's
+        column slab (R rows of Cl elements, pitch C) and a transpose on the device -- the host never reorders."""
         s = self.comm.rank
-        m = host.reshape(self.R, self.C, 4)[:, s * self.Cl:(s + 1) * self.Cl, :]
-        self.a.upload(np.ascontiguousarray(m.transpose(1, 0, 2)).reshape(self.nloc, 4))
+        host = np.ascontiguousarray(host, dtype=np.uint64).reshape(self.R * self.C, 4)
+        base = host.ctypes.data + s * self.Cl * 32
+        bb, bo = _base_of(self.b)
+        self.ctx.check(self.ctx.lib.zkp_buf_upload_2d(self.ctx.h, bb.h, bo, ctypes.c_void_p(base), self.Cl, self.R, self.C))
+        self.ctx.permute(self.b, 0, self.a, 0, self.Cl, self.R, 1)       # [r][c_loc] -> [c_loc][r]
 
     def gather_output(self, host_out):
-        """out_buf [jr_loc][jc] -> host_out[jc R + jr] for this rank's rows (other ranks' stay)."""
+        """out_buf [jr_loc][jc] -> host_out[jc R + jr] for this rank's rows (other ranks' stay): transpose on the
+        device, one strided copy."""
         s = self.comm.rank
-        loc = self.a.download().reshape(self.Rl, self.C, 4)
-        host_out.reshape(self.C, self.R, 4)[:, s * self.Rl:(s + 1) * self.Rl, :] = loc.transpose(1, 0, 2)
+        assert host_out.flags["C_CONTIGUOUS"] and host_out.dtype == np.uint64
+        self.ctx.permute(self.a, 0, self.b, 0, self.C, self.Rl, 1)       # [jr_loc][jc] -> [jc][jr_loc]
+        base = host_out.ctypes.data + s * self.Rl * 32
+        bb, bo = _base_of(self.b)
+        self.ctx.check(self.ctx.lib.zkp_buf_download_2d(self.ctx.h, bb.h, bo, ctypes.c_void_p(base), self.Rl, self.C, self.R))
 
     # ---- the transform: in_buf (self.a) -> out_buf (self.a)
     def run(self, inverse=False, coset=False):
@@ -203,22 +219,23 @@ class FourStepNtt:
         ctx, G, s = self.ctx, self.comm.world, self.comm.rank
         R, C, Rl, Cl, k = self.R, self.C, self.Rl, self.Cl, self.k
         a, b = self.a, self.b
-        one = fft_constant(0, 0)                        # w_1 = 1 in Montgomery form
-        wN = fft_constant(k, 1 if inverse else 0)
         g, gi = fft_constant(k, 3), fft_constant(k, 4)
         if coset and not inverse:
             # x[r C + c] *= g^(r C + c): rows a = c_loc, columns b = r
             ctx.scale_matrix(a, 0, Cl, R, s * Cl, g, _pow_mont(ctx, g, C), 1)
         # step 1: size-R transforms of the Cl local columns
         ctx.ntt_dev_batch(a, R, R, a, R, self.kr, inverse, False, Cl)
-        # step 2: twiddle, then rows <-> columns so that a destination's rows are contiguous
-        ctx.scale_matrix(a, 0, Cl, R, s * Cl, wN, one, 0)
-        ctx.permute(a, 0, b, 0, R, Cl, 1)                # b[jr][c_loc]
+        # step 2: twiddle w_N^(c jr) fused into the transpose that makes a destination's rows contiguous:
+        # one pass over the data, two-level twiddle table (zkp_twiddle_transpose_dev)
+        ctx.twiddle_transpose(a, 0, b, 0, Cl, R, s * Cl, k, inverse)      # b[jr][c_loc]
         # step 3: all-to-all (rank t receives its rows jr from every source)
-        ctx.sync()
         if G > 1:
-            self.comm.dist.all_to_all_single(self.ta, self.tb)
-            self.torch.cuda.synchronize()
+            if self.native:
+                self.comm.all_to_all(b, a, Rl * Cl)          # on the context's stream, behind the transpose
+            else:
+                ctx.sync()
+                self.comm.dist.all_to_all_single(self.ta, self.tb)
+                self.torch.cuda.synchronize()
             src = a                                      # [src][jr_loc][c_loc]
             dst = b
         else:
@@ -234,6 +251,11 @@ class FourStepNtt:
             # X[jc R + jr] *= g^-(jc R + jr): rows a = jr_loc, columns b = jc
             ctx.scale_matrix(a, 0, Rl, C, s * Rl, gi, _pow_mont(ctx, gi, R), 1)
         ctx.sync()
+
+
+def _base_of(buf):
+    from .ffi import _base
+    return _base(buf)
 
 
 def _pow_mont(ctx, base_mont, e):

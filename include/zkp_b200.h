@@ -80,6 +80,12 @@ int zkp_buf_upload(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const uint64_t* s
 int zkp_buf_download(zkp_ctx* ctx, const zkp_buf* src, size_t src_off, uint64_t* dst, size_t n);
 /* Wrap device memory owned by the caller (e.g. the tensor an NCCL collective reads and writes) as
  * a zkp_buf; zkp_buf_free on it releases only the handle. */
+/* Strided copies between a host matrix with a row pitch of host_pitch Fr and a dense device matrix of height x
+ * width Fr: a rank's column slab of a natural-order host vector and back (four-step NTT). */
+int zkp_buf_upload_2d(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const uint64_t* src, size_t width, size_t height,
+                      size_t host_pitch);
+int zkp_buf_download_2d(zkp_ctx* ctx, const zkp_buf* src, size_t src_off, uint64_t* dst, size_t width, size_t height,
+                        size_t host_pitch);
 int zkp_buf_wrap(zkp_ctx* ctx, void* device_ptr, size_t n, zkp_buf** out);
 int zkp_buf_zero(zkp_ctx* ctx, zkp_buf* buf, size_t off, size_t n);
 int zkp_buf_copy(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const zkp_buf* src, size_t src_off,
@@ -293,6 +299,14 @@ int zkp_comm_destroy(zkp_comm* comm);
 int zkp_comm_rank(const zkp_comm* comm);
 int zkp_comm_size(const zkp_comm* comm);
 int zkp_comm_stats(const zkp_comm* comm, uint64_t* collectives, uint64_t* bytes_sent);
+/* All-to-all of equal blocks of `count` Fr between device vectors (block p of src -> rank p; block r of dst <-
+ * rank r), queued on the context's stream: the transpose step of the four-step NTT. */
+int zkp_comm_all_to_all_dev(zkp_comm* comm, const zkp_buf* src, size_t src_off, zkp_buf* dst, size_t dst_off,
+                            size_t count);
+/* Four-step twiddle fused into the transpose: out[b][a] = in[a][b] * w_N^(+-(a0 + a) b) for an a-major rows x cols
+ * matrix, N = 2^k (two-level twiddle table, one pass over the data). */
+int zkp_twiddle_transpose_dev(zkp_ctx* ctx, const zkp_buf* in, size_t in_off, zkp_buf* out, size_t out_off, size_t rows,
+                              size_t cols, size_t a0, unsigned k, int inverse);
 /* zkp_commit_batch_dev over all ranks of `comm` (polynomials replicated, SRS complete on every rank):
  * collective; every rank returns the same commitments / status. */
 int zkp_commit_batch_sharded_dev(zkp_ctx* ctx, zkp_comm* comm, const zkp_srs* srs, const zkp_poly_ref* polys,

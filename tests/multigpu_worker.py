@@ -29,10 +29,14 @@ def main():
     ctx = z.Context(local)
     comm = Communicator(torch.device("cuda", local))
     # 1. four-step NTT, every kind, natural order in / out
-    for k in (10, 15, 20):
+    ncomm_ntt = z.NativeComm.from_torch_distributed(ctx) if world in (2, 4, 8) else None
+    for k, use_native in ((10, False), (10, True), (15, True), (20, True)):
+        if use_native and ncomm_ntt is None:
+            continue
         n = 1 << k
         host = random_fr_raw_limbs(k, n)
-        fs = FourStepNtt(ctx, comm, k)
+        # torch.distributed all-to-all (tensors) and the library's own NCCL all-to-all (ffi.NativeComm)
+        fs = FourStepNtt(ctx, ncomm_ntt if use_native else comm, k)
         for inverse, coset in ((False, False), (True, False), (False, True), (True, True)):
             fs.scatter_input(host)
             fs.run(inverse=inverse, coset=coset)
@@ -99,7 +103,7 @@ def main():
         from oracle.fields import FR_MONT_RINV, R_MOD, _from_limbs_fast, g1_from_mont_limbs
         k24, n24 = 24, 1 << 24
         host = random_fr_raw_limbs(2424, n24)
-        fs = FourStepNtt(ctx, comm, k24)
+        fs = FourStepNtt(ctx, ncomm_ntt if ncomm_ntt is not None else comm, k24)
         for inverse, coset in ((False, False), (True, True)):
             fs.scatter_input(host)
             fs.run(inverse=inverse, coset=coset)
