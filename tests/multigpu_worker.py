@@ -80,6 +80,16 @@ def main():
         nproof, npi = nprover.create_proof(bl, circ)
         assert nproof.wire_bytes == oproof.to_bytes(), "native sharded proof differs from the oracle"
         nprover.close()
+        # a tiny circuit (n = 32): with 8 ranks a slab holds 4 coefficients, fewer than t_4's tail -- the gather path
+        rc_ = SynthesizedCircuit.from_composer(circuits.range_circuit(99))
+        rk = rc_.n.bit_length() - 1
+        rprover = z.PlonkKey.compile_with_circuit(ShardedNativeParams.setup_synthetic(ctx, ncomm, rk + 1, taum), b"demo", rc_)
+        ropk, rovk = oplonk.compile_circuit(rc_, commit, (1 << (rk + 1)) + 7)
+        rotr = OTranscript.base(b"demo", oplonk.vk_transcript_list(rovk), rc_.m)
+        rproof, _ = rprover.create_proof(bl, rc_)
+        roproof, _ = oplonk.create_proof(ropk, rc_, commit, rotr, bl)
+        assert rproof.wire_bytes == roproof.to_bytes(), "native sharded proof of the range circuit differs from the oracle"
+        rprover.close()
         circ16 = synthetic_circuit(16)
         rng16 = SplitMix64(8349)
         tau16 = fr_to_mont_limbs([rng16.fr()])[0]
