@@ -76,3 +76,33 @@ def test_round_driver_entry_points_reject_bad_arguments_without_a_gpu():
     assert lib.zkp_transcript_append(None, b"x", None, 0) == z.ZKP_ERR_INVALID
     assert lib.zkp_linearization_scalars(5, None, None, None) == z.ZKP_ERR_INVALID
     assert lib.zkp_g1_compress(None, None) == z.ZKP_ERR_INVALID
+
+
+def test_multi_gpu_and_verifier_entry_points_reject_bad_arguments_without_a_gpu():
+    """The round-2 entry points (zkp_comm, sharded commit / prover, coset transforms, verifier glue) check their
+    arguments before any CUDA or NCCL call: ZKP_ERR_INVALID, not a crash -- and the library loads and answers
+    on a box with neither a GPU nor an NCCL communicator."""
+    import ctypes
+    import numpy as np
+    import dusk_plonk_b200 as z
+    lib = z.load_library()
+    out = ctypes.c_void_p()
+    assert lib.zkp_comm_create(None, None, 0, 1, ctypes.byref(out)) == z.ZKP_ERR_INVALID
+    assert lib.zkp_comm_destroy(None) == z.ZKP_OK
+    assert lib.zkp_comm_rank(None) == 0 and lib.zkp_comm_size(None) == 1
+    assert lib.zkp_comm_all_to_all_dev(None, None, 0, None, 0, 0) == z.ZKP_ERR_INVALID
+    assert lib.zkp_commit_batch_sharded_dev(None, None, None, None, 0, None, None) == z.ZKP_ERR_INVALID
+    assert lib.zkp_coset8_ntt_dev(None, None, 0, 0, None, 0, 3, 0, 8) == z.ZKP_ERR_INVALID
+    assert lib.zkp_prover_create_sharded(None, None, None, None, ctypes.byref(out)) == z.ZKP_ERR_INVALID
+    assert lib.zkp_twiddle_transpose_dev(None, None, 0, None, 0, 1, 1, 0, 4, 0) == z.ZKP_ERR_INVALID
+    assert lib.zkp_srs_trim(None, None, 0, ctypes.byref(out)) == z.ZKP_ERR_INVALID
+    assert lib.zkp_buf_upload_2d(None, None, 0, None, 0, 0, 0) == z.ZKP_ERR_INVALID
+    assert lib.zkp_verify(None, None, None, None, None, None, None, 0) == z.ZKP_ERR_INVALID
+    assert lib.zkp_kzg_batch_check(None, None, None, None, None, 0, None) == z.ZKP_ERR_INVALID
+    assert lib.zkp_g2_generator_mul(None, None) == z.ZKP_ERR_INVALID
+    # a G2 element that is not on the twist is an invalid argument, not a rejected proof
+    bad = np.zeros(24, dtype=np.uint64); bad[3] = 9
+    g1 = np.zeros(12, dtype=np.uint64)
+    assert lib.zkp_pairing_check(ctypes.c_void_p(g1.ctypes.data), ctypes.c_void_p(bad.ctypes.data), 1) == z.ZKP_ERR_INVALID
+    assert lib.zkp_pairing_check(None, None, 0) == z.ZKP_OK          # the empty product is one
+    assert lib.zkp_strerror(z.ZKP_ERR_VERIFY) == b"proof rejected"
