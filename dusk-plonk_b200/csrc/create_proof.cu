@@ -495,7 +495,8 @@ static int prove(zkp_prover* pr, const uint8_t transcript_in[203], const uint64_
         // rounds 4 / 5 work on the slabs where they lie unless the SRS is long enough for t_4 to reach beyond its
         // first eight tail coefficients (then: gather t(X) chunk by chunk and continue as one GPU would)
         // (and the slab must hold those eight: tiny circuits on many GPUs take the gather path as well)
-        slab_openings = pr->srs->n <= n + 8 && pr->slab >= 8;
+        // (and the local vectors are large enough to double as staging when there is no communicator)
+        slab_openings = pr->srs->n <= n + 8 && pr->slab >= 8 && pr->nl >= 256;
         if (!slab_openings)
             for (unsigned q = 0; q < 8; q++)
                 TRY(comm_allgather(pr->comm, pr->TS->d + q * pr->slab, pr->T->d + q * n, pr->slab * sizeof(fr_t), ctx->stream));
