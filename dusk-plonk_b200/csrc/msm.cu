@@ -301,23 +301,49 @@ __global__ void msm_scatter_kernel(const __grid_constant__ MsmBatch batch, const
 // through, equal points are doubled through the same inversion (denominator 2 y, numerator 3 x^2), opposite
 // points give infinity.
 
-// plan[q] = position of the first input of output q at the previous level | (1 << 31 if it has no partner)
+// plan[q] = position of the first input of output q at the previous level | (1 << 31 if it has no partner).
+// A thread plans 8 consecutive outputs: one binary search for the first, then it walks the (non-empty) buckets.
+static constexpr unsigned PLAN_PER = 8;
 __global__ void __launch_bounds__(256) msm_affine_plan_kernel(const uint32_t* offsets, const uint32_t* counts,
                                                              const uint32_t* totals, uint32_t B, unsigned nb,
                                                              unsigned r, size_t plan_stride, uint32_t* plan) {
     const unsigned pb = blockIdx.y;
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= totals[r * MSM_MAX_BATCH + pb]) return;
+    const uint32_t total = totals[r * MSM_MAX_BATCH + pb];
+    const uint64_t q64 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * PLAN_PER;
+    if (q64 >= total) return;
+    const uint32_t q0 = (uint32_t)q64;
     const uint32_t* off_out = offsets + ((size_t)r * nb + pb) * B;
     const uint32_t* off_in = offsets + ((size_t)(r - 1) * nb + pb) * B;
+    const uint32_t* cnt = counts + (size_t)pb * B;
     uint32_t blo = 0, bhi = B;      // the last bucket whose offset is <= q is never an empty one
     while (bhi - blo > 1) {
         const uint32_t mid = (blo + bhi) >> 1;
-        if (off_out[mid] <= q) blo = mid; else bhi = mid;
+        if (off_out[mid] <= q0) blo = mid; else bhi = mid;
     }
-    const uint32_t j = q - off_out[blo];
-    const uint32_t cin = level_count(counts[(size_t)pb * B + blo], r - 1);
-    plan[(size_t)pb * plan_stride + q] = (off_in[blo] + 2 * j) | ((2 * j + 1 >= cin) ? 0x80000000u : 0u);
+    uint32_t b = blo, obeg = off_out[b], oend = obeg + level_count(cnt[b], r), ibeg = off_in[b];
+    uint32_t cin = level_count(cnt[b], r - 1);
+    uint32_t v[PLAN_PER];
+    const uint32_t qe = q0 + PLAN_PER < total ? q0 + PLAN_PER : total;
+#pragma unroll
+    for (unsigned i = 0; i < PLAN_PER; i++) {
+        const uint32_t q = q0 + i;
+        v[i] = 0;
+        if (q >= qe) continue;
+        if (q >= oend) {
+            do { b++; } while (cnt[b] == 0);
+            obeg = off_out[b]; oend = obeg + level_count(cnt[b], r); ibeg = off_in[b];
+            cin = level_count(cnt[b], r - 1);
+        }
+        const uint32_t j = q - obeg;
+        v[i] = (ibeg + 2 * j) | ((2 * j + 1 >= cin) ? 0x80000000u : 0u);
+    }
+    uint32_t* out = plan + (size_t)pb * plan_stride + q0;
+    if (q0 + PLAN_PER <= total && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+        reinterpret_cast<uint4*>(out)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<uint4*>(out)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    } else {
+        for (unsigned i = 0; i < PLAN_PER && q0 + i < total; i++) out[i] = v[i];
+    }
 }
 
 __device__ __forceinline__ fq_t msm_ld_fq(const fq_t* p) {
@@ -1562,7 +1588,7 @@ int msm_run_batch_ex(zkp_ctx* ctx, zkp_comm* cm, const zkp_srs* srs, const fr_t*
         size_t K = (bound * nb + waves * slots * 128 - 1) / (waves * slots * 128);
         if (K < 8) K = 8;
         if (K > kmax) K = kmax;
-        msm_affine_plan_kernel<<<dim3((unsigned)((bound + 255) / 256), nb), 256, 0, st>>>(
+        msm_affine_plan_kernel<<<dim3((unsigned)((bound + 256 * PLAN_PER - 1) / (256 * PLAN_PER)), nb), 256, 0, st>>>(
             s->offsets, s->counts, s->totals, B, nb, r, half, s->plan);
         ZKP_LAUNCHED(ctx);
         const dim3 rgrid((unsigned)((bound + K * 128 - 1) / (K * 128)), nb);
