@@ -304,7 +304,9 @@ class ProveJob:
         # proof ships the same values to its own GPU)
         self.wa_host = z.WitnessValues.from_circuit(circ)
         self.wa_host.witness_mont = pinned_copy(z, self.wa_host.witness_mont)
-        self.h2d = (self.wa_host.witness_mont.shape[0] + len(self.wa_host.pi_values) + 19) * 32
+        # (a rank of a sharded proof uploads 1 / G of the witness; the ranks all-gather the slices over NVLink)
+        g = comm.world if comm is not None else 1
+        self.h2d = (-(-self.wa_host.witness_mont.shape[0] // g) + len(self.wa_host.pi_values) + 19) * 32
         self.wa_dev = z.WitnessAssignment.from_circuit(circ, circ.n).to_device(ctx)
         self.d2h = 11 * 96 + 17 * 32
         self.proofs = []
@@ -413,7 +415,9 @@ def main():
         dominant, metric, n = "msm_accumulate", "compile_throughput", 1
     elif args.workload == "prove":
         job = ProveJob(z, ctx, args.logn, ncomm)
-        step, e2e_step, h2d, d2h = job.step, job.e2e_step, job.h2d, job.d2h
+        step, e2e_step = job.step, job.e2e_step
+        # whole-job bytes per step: every rank of a sharded proof ships its slice of the witness and reads the proof back
+        h2d, d2h = job.h2d * (world if shard else 1), job.d2h * (world if shard else 1)
         extra["srs_setup_ms"], extra["compile_ms"] = job.srs_ms, job.compile_ms
         dominant, metric, n = "msm_accumulate", "create_proof_throughput", 1
     elif args.workload == "msm":

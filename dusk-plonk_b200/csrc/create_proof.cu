@@ -813,7 +813,11 @@ int zkp_prover_prove_witness(zkp_prover* pr, const uint8_t transcript[203], cons
     zkp_ctx* ctx = pr->ctx;
     int rc;
     if ((rc = set_device(ctx))) return rc;
-    const size_t n = pr->n, need = num_w + pr->pi_count + 1;
+    // a sharded proof: every rank has the same host witness, so each uploads 1 / G of it over its own PCIe
+    // link and the ranks all-gather the slices over NVLink (the public-input values sit behind the padded witness)
+    const size_t G = pr->sharded && pr->comm ? (size_t)pr->comm->nranks : 1;
+    const size_t chunk = (num_w + G - 1) / G, wslots = chunk * G;
+    const size_t n = pr->n, need = wslots + pr->pi_count + 1;
     if (pr->wv_cap < need) {
         ZKP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (pr->wv) cudaFree(pr->wv);
@@ -822,13 +826,20 @@ int zkp_prover_prove_witness(zkp_prover* pr, const uint8_t transcript[203], cons
         pr->wv_cap = need;
     }
     cudaStream_t st = ctx->stream;
-    if (num_w) ZKP_CUDA(ctx, cudaMemcpyAsync(pr->wv, witness, num_w * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+    if (G > 1 && num_w) {
+        const size_t lo = (size_t)pr->comm->rank * chunk, hi = lo + chunk < num_w ? lo + chunk : num_w;
+        if (hi > lo)
+            ZKP_CUDA(ctx, cudaMemcpyAsync(pr->wv + lo, witness + 4 * lo, (hi - lo) * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+        if ((rc = comm_allgather(pr->comm, pr->wv + lo, pr->wv, chunk * sizeof(fr_t), st))) return rc;   // in place
+    } else if (num_w) {
+        ZKP_CUDA(ctx, cudaMemcpyAsync(pr->wv, witness, num_w * sizeof(fr_t), cudaMemcpyHostToDevice, st));
+    }
     drv::gather_wires_kernel<<<(unsigned)((4 * n + 255) / 256), 256, 0, st>>>(pr->wv, num_w, pr->wire_idx, pr->m, n, pr->W->d);
     ZKP_LAUNCHED(ctx);
     fr_t* pi = pr->P7->d + 4 * pr->S;
     ZKP_CUDA(ctx, cudaMemsetAsync(pi, 0, n * sizeof(fr_t), st));
     if (pr->pi_count) {
-        fr_t* pv = pr->wv + num_w;
+        fr_t* pv = pr->wv + wslots;
         ZKP_CUDA(ctx, cudaMemcpyAsync(pv, pi_values, pr->pi_count * sizeof(fr_t), cudaMemcpyHostToDevice, st));
         drv::scatter_pi_kernel<<<(unsigned)((pr->pi_count + 255) / 256), 256, 0, st>>>(pv, pr->pi_idx, pr->pi_count, n, pi);
         ZKP_LAUNCHED(ctx);
