@@ -227,7 +227,7 @@ def run_reference(args, rank, world):
     val = n / dt if unit.endswith("s/s") and n == 1 else n / dt / 1e6
     line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "strong" if (world > 1 and not args.independent) else "weak", "vs_baseline": None,
+            "scaling": "weak" if (args.independent and world > 1) else "strong", "vs_baseline": None,
             "dtype": "u64 limbs (modular integer)", "data": "synthetic", "config": workload_config(args, world),
             "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
                              "note": PORT_NOTE},
@@ -627,7 +627,8 @@ def main():
         roofline["traffic"], roofline["traffic_source"] = measured_traffic(args.workload, args.logn)
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong" if shard else "weak",
+                # one job whatever N is (strong scaling) unless --independent gives every GPU its own job
+                "scaling": "weak" if (args.independent and world > 1) else "strong",
                 "vs_baseline": None, "dtype": "u32 limbs (modular integer)", "data": "synthetic",
                 "config": workload_config(args, world),
                 "roofline": roofline,
