@@ -82,6 +82,70 @@ static P1 p1_mul(const P1& p, const fr& s) {
     }
     return acc;
 }
+// k * p for a raw 256-bit little-endian integer k (not reduced: the subgroup check multiplies by r itself)
+static P1 p1_mul_raw(const P1& p, const uint64_t k[4]) {
+    P1 acc = p1_inf();
+    for (int i = 255; i >= 0; i--) {
+        p1_dbl(acc);
+        if ((k[i >> 6] >> (i & 63)) & 1) p1_add(acc, p);
+    }
+    return acc;
+}
+// a^e for a little-endian multi-word exponent
+static fq fq_pow_words(const fq& a, const uint64_t* e, int words) {
+    fq acc = Q::one();
+    for (int i = 64 * words - 1; i >= 0; i--) {
+        acc = Q::sqr(acc);
+        if ((e[i >> 6] >> (i & 63)) & 1) acc = Q::mul(acc, a);
+    }
+    return acc;
+}
+// 48-byte compressed G1 (zcash / dusk G1Affine::from_bytes) -> affine Montgomery; false on ANY malformed input:
+// missing compression flag, x >= p, stray bits with the infinity flag, x not on the curve, point outside the
+// r-torsion (BLS12-381 G1 has a cofactor)
+static bool g1_decompress(const uint8_t in[48], uint64_t out_xy[12]) {
+    memset(out_xy, 0, 96);
+    if (!(in[0] & 0x80)) return false;
+    if (in[0] & 0x40) {
+        if (in[0] & 0x3f) return false;
+        for (int i = 1; i < 48; i++) if (in[i]) return false;
+        return true;
+    }
+    fq xr;
+    memset(xr.l, 0, 48);
+    for (int i = 0; i < 48; i++) {
+        const uint8_t b = i == 0 ? (uint8_t)(in[0] & 0x1f) : in[i];
+        xr.l[(47 - i) / 8] |= (uint64_t)b << (8 * ((47 - i) % 8));
+    }
+    if (Q::geq_p(xr.l)) return false;
+    const fq x = Q::to_mont(xr);
+    const fq y2 = Q::add(Q::mul(Q::sqr(x), x), Q::from_u64(4));
+    // p = 3 mod 4: a square root of y2, if there is one, is y2^((p + 1) / 4)
+    uint64_t e[6];
+    {
+        const uint64_t* p = Q::C().p;
+        unsigned __int128 c = 1;
+        uint64_t t[6];
+        for (int i = 0; i < 6; i++) { c += p[i]; t[i] = (uint64_t)c; c >>= 64; }   // p + 1 (no carry out: p < 2^381)
+        for (int i = 0; i < 6; i++) e[i] = (t[i] >> 2) | (i < 5 ? t[i + 1] << 62 : 0);
+    }
+    fq y = fq_pow_words(y2, e, 6);
+    if (!fq_eq(Q::sqr(y), y2)) return false;
+    // the flag says whether y is the lexicographically larger root
+    const fq yc = Q::from_mont(y), ny = Q::from_mont(Q::neg(y));
+    bool larger = false;
+    for (int i = 5; i >= 0; i--) {
+        if (yc.l[i] > ny.l[i]) { larger = true; break; }
+        if (yc.l[i] < ny.l[i]) break;
+    }
+    if (larger != ((in[0] & 0x20) != 0)) y = Q::neg(y);
+    P1 pt;
+    pt.x = x; pt.y = y; pt.zz = pt.zzz = Q::one();
+    if (!p1_mul_raw(pt, F::C().p).inf()) return false;      // [r] P must be the identity
+    memcpy(out_xy, x.l, 48); memcpy(out_xy + 6, y.l, 48);
+    return true;
+}
+
 static void p1_to_affine(const P1& a, fq* x, fq* y, bool* inf) {
     *inf = a.inf();
     if (*inf) { *x = *y = Q::zero(); return; }
@@ -379,6 +443,30 @@ using zkp::drv::fr;
 using zkp::drv::fr_load;
 
 extern "C" {
+
+int zkp_g1_decompress(const uint8_t in[48], uint64_t out_xy[12]) {
+    if (!in || !out_xy) return ZKP_ERR_INVALID;
+    return vf::g1_decompress(in, out_xy) ? ZKP_OK : ZKP_ERR_INVALID;
+}
+
+/* Proof decoding (src/prover/proof.rs:36-66 derives Decode; "subgroup checks are done when the proof is deserialized",
+ * proof.rs:77): 11 compressed G1 + 16 canonical little-endian scalars -> what zkp_verify takes. */
+int zkp_proof_decode(const uint8_t bytes[1040], uint64_t commitments[132], uint64_t evaluations[64]) {
+    if (!bytes || !commitments || !evaluations) return ZKP_ERR_INVALID;
+    for (int j = 0; j < 11; j++)
+        if (!vf::g1_decompress(bytes + 48 * j, commitments + 12 * j)) return ZKP_ERR_INVALID;
+    // wire order of `Evaluations` (linearization_poly.rs:113-130) -> EVAL order of zkp_prover_prove
+    static const int wire_order[16] = {0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 7, 8, 9, 15, 14};
+    for (int j = 0; j < 16; j++) {
+        fr v;
+        memset(v.l, 0, 32);
+        const uint8_t* b = bytes + 48 * 11 + 32 * j;
+        for (int i = 0; i < 32; i++) v.l[i / 8] |= (uint64_t)b[i] << (8 * (i % 8));
+        if (F::geq_p(v.l)) return ZKP_ERR_INVALID;          // non-canonical scalar
+        drv::fr_store(evaluations + 4 * wire_order[j], F::to_mont(v));
+    }
+    return ZKP_OK;
+}
 
 int zkp_g2_generator_mul(const uint64_t scalar[4], uint64_t out[24]) {
     if (!scalar || !out) return ZKP_ERR_INVALID;

@@ -135,6 +135,8 @@ SIGNATURES.update({
     # verifier glue (host code)
     "zkp_g2_generator_mul": (_int, [_vp, _vp]),
     "zkp_g1_generator_mul": (_int, [_vp, _vp]),
+    "zkp_g1_decompress": (_int, [_vp, _vp]),
+    "zkp_proof_decode": (_int, [_vp, _vp, _vp]),
     "zkp_pairing_check": (_int, [_vp, _vp, _sz]),
     "zkp_kzg_batch_check": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "zkp_verify": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),

@@ -66,18 +66,22 @@ class Proof:
 
     @classmethod
     def from_bytes(cls, data):
-        from .field import g1_decompress
+        """Decode and VALIDATE untrusted proof bytes with the library's host decoder (``zkp_proof_decode``): every
+        commitment must be a canonical compressed point of the prime-order subgroup, every scalar canonical
+        (src/prover/proof.rs:77: "subgroup checks are done when the proof is deserialized").  ``ValueError`` otherwise."""
+        import ctypes
+        from .ffi import load_library
         if len(data) != 48 * 11 + 32 * 16:
             raise ValueError("a proof is 1040 bytes")
-        p = cls()
-        for i, c in enumerate(COMM_NAMES):
-            setattr(p, c, g1_decompress(data[48 * i:48 * (i + 1)]))
-        off = 48 * 11
-        for i, k in enumerate(cls.WIRE_EVAL_ORDER):
-            v = int.from_bytes(data[off + 32 * i:off + 32 * (i + 1)], "little")
-            if v >= _r:
-                raise ValueError("non-canonical scalar")
-            p.evaluations[k] = v
+        raw = np.frombuffer(bytes(data), dtype=np.uint8).copy()
+        comms = np.zeros((11, 12), dtype=np.uint64)
+        evals = np.zeros((16, 4), dtype=np.uint64)
+        rc = load_library().zkp_proof_decode(ctypes.c_void_p(raw.ctypes.data), ctypes.c_void_p(comms.ctypes.data),
+                                             ctypes.c_void_p(evals.ctypes.data))
+        if rc:
+            raise ValueError("malformed proof: non-canonical encoding, point off the curve or outside the subgroup")
+        p = cls.from_limbs(comms, evals, bytes(data))
+        p.evaluations          # decoded proofs are materialised at once (callers may edit fields)
         return p
 
 

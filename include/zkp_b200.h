@@ -362,6 +362,13 @@ typedef struct zkp_verifier_key {
  * returns (EvaluationKey { g, h, beta_h }, src/commitment_scheme.rs:51-58): beta_h = [tau]_2 for an SRS made
  * from tau, h = [1]_2.  G2 affine as x0 x1 y0 y1 (6 uint64 each, Montgomery), zeros = identity. */
 int zkp_g2_generator_mul(const uint64_t scalar[4], uint64_t out[24]);
+/* Untrusted bytes -> validated values.  zkp_g1_decompress: 48-byte compressed G1 (zcash / dusk encoding) -> affine
+ * Montgomery, ZKP_ERR_INVALID for a missing flag, x >= p, stray bits with the infinity flag, x off the curve or a
+ * point outside the prime-order subgroup.  zkp_proof_decode: the 1040-byte proof (src/prover/proof.rs:36-66) ->
+ * commitments / evaluations in the layout of zkp_prover_prove and zkp_verify, every point checked as above and
+ * every scalar required to be canonical ("subgroup checks are done when the proof is deserialized", proof.rs:77). */
+int zkp_g1_decompress(const uint8_t in[48], uint64_t out_xy[12]);
+int zkp_proof_decode(const uint8_t bytes[1040], uint64_t commitments[132], uint64_t evaluations[64]);
 int zkp_g1_generator_mul(const uint64_t scalar[4], uint64_t out[12]);
 /* prod_i e(g1_i, g2_i) == 1: ZKP_OK or ZKP_ERR_VERIFY (multi_miller_loop(..).final_exp() == identity). */
 int zkp_pairing_check(const uint64_t* g1 /* count x 12 */, const uint64_t* g2 /* count x 24 */, size_t count);

@@ -124,3 +124,58 @@ def test_verifier_accepts_golden_proofs_and_rejects_tampering(entry):
                      circ.n, circ.m)
     with pytest.raises(Error):
         wrong.verify(proof, pis)
+
+
+def test_native_proof_decoder_validates_untrusted_bytes(lib):
+    """zkp_proof_decode / zkp_g1_decompress (host code): the golden proofs decode to the values the Python decoder
+    gives; every malformed encoding the zcash / dusk ``from_compressed`` rejects is rejected -- missing flag,
+    x >= p, stray bits with the infinity flag, x off the curve, a curve point outside the prime-order subgroup,
+    a non-canonical scalar (src/prover/proof.rs:77)."""
+    from dusk_plonk_b200.field import g1_decompress as py_decompress, g1_mul
+    from dusk_plonk_b200.prover import COMM_NAMES
+    from dusk_plonk_b200.transcript import g1_compress
+    for entry in GOLD["proofs"]:
+        raw = bytes.fromhex(entry["proof_bytes"])
+        p = z.Proof.from_bytes(raw)
+        for i, c in enumerate(COMM_NAMES):
+            assert getattr(p, c) == py_decompress(raw[48 * i:48 * (i + 1)])
+        assert p.to_bytes() == raw
+    raw = bytearray(bytes.fromhex(GOLD["proofs"][0]["proof_bytes"]))
+
+    def rejected(buf):
+        try:
+            z.Proof.from_bytes(bytes(buf))
+        except ValueError:
+            return True
+        return False
+    bad = bytearray(raw); bad[0] &= 0x7F                      # compression flag cleared
+    assert rejected(bad)
+    bad = bytearray(raw); bad[0:48] = bytes([0xC0]) + bytes(46) + b"\x01"   # infinity with a stray bit
+    assert rejected(bad)
+    bad = bytearray(raw); bad[0:48] = bytes([0x9F]) + b"\xff" * 47           # x >= p
+    assert rejected(bad)
+    bad = bytearray(raw); bad[48 * 11 + 31] = 0xFF                           # scalar >= r
+    assert rejected(bad)
+    ok = bytearray(raw); ok[0:48] = bytes([0xC0]) + bytes(47)                # a well-formed identity is fine
+    assert not rejected(ok)
+    # x off the curve, and a curve point of the wrong order (G1 has cofactor ~2^126: almost every curve point)
+    off = on_not_sub = None
+    x = 5
+    while off is None or on_not_sub is None:
+        y2 = (pow(x, 3, P_MOD) + 4) % P_MOD
+        y = pow(y2, (P_MOD + 1) // 4, P_MOD)
+        if y * y % P_MOD != y2:
+            off = off or x
+        elif g1_mul((x, y), R_MOD) is not None:      # (unreduced scalar: [r] P for a point of another order)
+            on_not_sub = on_not_sub or (x, y)
+        x += 1
+    bad = bytearray(raw); bad[0:48] = bytes([0x80 | (off >> 376)]) + off.to_bytes(48, "big")[1:]
+    assert rejected(bad)
+    bad = bytearray(raw); bad[0:48] = g1_compress(on_not_sub)
+    assert rejected(bad)
+    out = np.zeros(12, dtype=np.uint64)
+    good = np.frombuffer(g1_compress(curve.mul(curve.G1_GEN, 12345)), dtype=np.uint8).copy()
+    assert lib.zkp_g1_decompress(_ptr(good), _ptr(out)) == 0
+    assert g1_from_mont(out) == curve.mul(curve.G1_GEN, 12345)
+    notsub = np.frombuffer(g1_compress(on_not_sub), dtype=np.uint8).copy()
+    assert lib.zkp_g1_decompress(_ptr(notsub), _ptr(out)) == z.ZKP_ERR_INVALID
