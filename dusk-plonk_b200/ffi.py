@@ -138,6 +138,7 @@ SIGNATURES.update({
     "zkp_g1_decompress": (_int, [_vp, _vp]),
     "zkp_proof_decode": (_int, [_vp, _vp, _vp]),
     "zkp_pairing_check": (_int, [_vp, _vp, _sz]),
+    "zkp_pairing_selftest": (_int, [_vp, _vp]),
     "zkp_kzg_batch_check": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "zkp_verify": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
     # one job over several GPUs

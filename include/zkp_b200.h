@@ -372,6 +372,9 @@ int zkp_proof_decode(const uint8_t bytes[1040], uint64_t commitments[132], uint6
 int zkp_g1_generator_mul(const uint64_t scalar[4], uint64_t out[12]);
 /* prod_i e(g1_i, g2_i) == 1: ZKP_OK or ZKP_ERR_VERIFY (multi_miller_loop(..).final_exp() == identity). */
 int zkp_pairing_check(const uint64_t* g1 /* count x 12 */, const uint64_t* g2 /* count x 24 */, size_t count);
+/* Self-check: for e(g1, g2) the Frobenius-based final exponentiation the checks use equals the cube of the plain
+ * (p^12 - 1) / r square-and-multiply, and the pairing is not degenerate. */
+int zkp_pairing_selftest(const uint64_t g1[12], const uint64_t g2[24]);
 /* commitment_scheme::batch_check (src/commitment_scheme.rs:24-66): `count` opening proofs (point, commitment to the
  * witness, claimed evaluation, commitment to the polynomial) against the opening key; draws the "batch" challenge
  * from the transcript state (updated in place). */

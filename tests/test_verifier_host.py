@@ -85,6 +85,9 @@ def test_pairing_is_bilinear_and_agrees_with_the_oracle(lib):
     assert pairing.pairing_product_is_one([(P1, Q1), (P2, Q2)])
     bad = np.zeros(24, dtype=np.uint64); bad[0] = 5
     assert check([(g1(1), bad)]) == z.ZKP_ERR_INVALID            # not on the twist
+    # the Frobenius-based final exponentiation == the cube of the plain (p^12 - 1) / r power, on several pairings
+    for s1, s2 in ((1, 1), (a, b), (R_MOD - 1, 3)):
+        assert lib.zkp_pairing_selftest(_ptr(g1(s1)), _ptr(g2(s2))) == 0
 
 
 def _golden_case(entry):
