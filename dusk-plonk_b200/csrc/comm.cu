@@ -125,9 +125,7 @@ int zkp_comm_unique_id(uint8_t out[256]) {
     memset(out, 0, 256);
     ncclUniqueId id;
     if (g_nccl.GetUniqueId(&id) != ncclSuccess) return ZKP_ERR_CUDA;
-    memcpy(out, &id, sizeof id);
-    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return ZKP_ERR_CUDA;   // second communicator (side stream)
-    memcpy(out + 128, &id, sizeof id);
+    memcpy(out, &id, sizeof id);      // bytes 128 .. 255 are reserved (zero)
     return ZKP_OK;
 }
 
