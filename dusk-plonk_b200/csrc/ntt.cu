@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(128) scale_matrix_kernel(fr_t* data, size_t ro
 // two multiplications per element instead of the ~5 of per-thread powers, and one pass over the data
 // instead of two (scale, then transpose).
 static int get_twtab(zkp_ctx* ctx, unsigned k, bool inverse, TwTab** out) {
-    const unsigned key = k * 2 + (inverse ? 1 : 0);
+    const unsigned key = 64 * 8 + k * 2 + (inverse ? 1 : 0);     // shares the coset8 map's key space above 8 * 64
     auto it = ctx->twtabs.find(key);
     if (it != ctx->twtabs.end()) { *out = it->second; return ZKP_OK; }
     TwTab* t = new TwTab();
