@@ -78,14 +78,14 @@ int zkp_buf_free(zkp_ctx* ctx, zkp_buf* buf);
 size_t zkp_buf_len(const zkp_buf* buf);
 int zkp_buf_upload(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const uint64_t* src, size_t n);
 int zkp_buf_download(zkp_ctx* ctx, const zkp_buf* src, size_t src_off, uint64_t* dst, size_t n);
-/* Wrap device memory owned by the caller (e.g. the tensor an NCCL collective reads and writes) as
- * a zkp_buf; zkp_buf_free on it releases only the handle. */
 /* Strided copies between a host matrix with a row pitch of host_pitch Fr and a dense device matrix of height x
  * width Fr: a rank's column slab of a natural-order host vector and back (four-step NTT). */
 int zkp_buf_upload_2d(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const uint64_t* src, size_t width, size_t height,
                       size_t host_pitch);
 int zkp_buf_download_2d(zkp_ctx* ctx, const zkp_buf* src, size_t src_off, uint64_t* dst, size_t width, size_t height,
                         size_t host_pitch);
+/* Wrap device memory owned by the caller (e.g. the tensor an NCCL collective reads and writes) as
+ * a zkp_buf; zkp_buf_free on it releases only the handle. */
 int zkp_buf_wrap(zkp_ctx* ctx, void* device_ptr, size_t n, zkp_buf** out);
 int zkp_buf_zero(zkp_ctx* ctx, zkp_buf* buf, size_t off, size_t n);
 int zkp_buf_copy(zkp_ctx* ctx, zkp_buf* dst, size_t dst_off, const zkp_buf* src, size_t src_off,
